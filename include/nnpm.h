@@ -1,0 +1,170 @@
+/* nnpm.h -- C ABI of libnnpm.so, the B200-native particle-mesh gravity step for NoName.
+ *
+ * The reference (yipihey/NoName, pure Julia) has no FFI of its own; its extension mechanism is
+ * function-name dispatch from the .conf file (src/NoName.jl:82-83) onto free functions that
+ * mutate plain Float64 arrays (src/ParticleMesh.jl).  Each entry point below names the reference
+ * function (file:line under /root/reference) it replaces.  A Julia host binds them with `ccall`
+ * (julia/NoNameB200.jl); the Python host in noname_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types; every call returns 0 on success or a
+ *     negative nnpm_status; nnpm_last_error(ctx) gives the message (owned by ctx).
+ *   - host arrays use the reference's Julia column-major layout AS IS:
+ *       mesh   rho/phi[i,j,k]   -> double[i + N1*(j + N2*k)]
+ *       acc[c,i,j,k]            -> double[c + 3*(i + N1*(j + N2*k))]   (first dim always 3)
+ *       particles x/v/pa[d,n]   -> double[d + rank*n]                  (rank = 2 or 3)
+ *   - one host thread drives one context; one context drives ONE GPU (one process per GPU).
+ *     With nranks > 1 the mesh is slab-decomposed along k (the slowest Julia index): rank r owns
+ *     planes [r*N3/P, (r+1)*N3/P) and the particles whose floor(x3*N3) falls in them; mesh
+ *     get/set calls then move only the local slab.
+ *   - the device state (SoA x,v, mesh) stays resident between calls; host copies happen only in
+ *     upload/download/get/set calls.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     NNPM_ERR_CUDA.
+ */
+#ifndef NNPM_H
+#define NNPM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNPM_VERSION 1
+
+typedef struct nnpm_ctx nnpm_ctx;
+
+typedef enum {
+  NNPM_OK = 0,
+  NNPM_ERR_ARG = -1,      /* bad argument / unsupported configuration */
+  NNPM_ERR_CUDA = -2,     /* CUDA runtime error (incl. "no device") */
+  NNPM_ERR_CUFFT = -3,
+  NNPM_ERR_NCCL = -4,
+  NNPM_ERR_CAPACITY = -5, /* particle capacity exceeded on this rank */
+  NNPM_ERR_STATE = -6     /* call sequence error (e.g. interp before accel) */
+} nnpm_status;
+
+/* ParticleDepositInterpolation / ParticleBackInterpolation = none | cic  (src/default.conf:32-33) */
+enum { NNPM_INTERP_NONE = 0, NNPM_INTERP_CIC = 1 };
+/* deposit accumulation: f64 atomics (default) or deterministic int64 fixed point */
+enum { NNPM_DEPOSIT_ATOMIC = 0, NNPM_DEPOSIT_FIXED = 1 };
+/* fields for nnpm_get_field / nnpm_set_field */
+enum { NNPM_FIELD_RHO = 0, NNPM_FIELD_PHI = 1, NNPM_FIELD_ACC = 2, NNPM_FIELD_PA = 3 };
+/* synthetic initial conditions generated on the device (nnpm_init_synthetic) */
+enum { NNPM_IC_LATTICE = 0, NNPM_IC_ZELDOVICH_MODES = 1 };
+
+typedef struct {
+  int32_t struct_size;      /* = sizeof(nnpm_config), for ABI checks */
+  int32_t rank;             /* particle dimensionality: 2 or 3 (ParticleMesh.jl:105) */
+  int64_t ngrid[3];         /* TopgridDimensions N1,N2,N3 (N3 = 1 when rank == 2) */
+  int64_t npart_total;      /* prod(ParticleDimensions): particles over all ranks */
+  int64_t part_capacity;    /* per-rank particle capacity; 0 = npart_total/nranks * 1.25 + 4096 */
+  int32_t deposit;          /* NNPM_INTERP_* */
+  int32_t backinterp;       /* NNPM_INTERP_* */
+  int32_t deposit_mode;     /* NNPM_DEPOSIT_* */
+  int32_t fixed_bits;       /* fractional bits of the fixed-point deposit (0 = 44) */
+  int32_t sort_every;       /* counting-sort particles by cell every n steps (0 = never) */
+  int32_t bugcompat_interp_z; /* 1 = reproduce ParticleMesh.jl:706/:647 literally (rank 3) */
+  int32_t device;           /* CUDA device ordinal */
+  int32_t nranks;           /* slab decomposition width P (1 = single GPU) */
+  int32_t rank_id;          /* this context's slab index in [0,P) */
+  int32_t timing;           /* 1 = record per-phase CUDA-event times into nnpm_stats.ms */
+  void *stream;             /* cudaStream_t to run on; NULL = the library creates its own */
+} nnpm_config;
+
+enum {
+  NNPM_MS_DEPOSIT = 0, /* zero + (drift) + scatter + ghost-plane add (+ fixed->f64) */
+  NNPM_MS_SOLVE = 1,   /* forward FFTs, Green multiply, inverse FFTs, transposes, ghost planes */
+  NNPM_MS_PUSH = 2,    /* gradient + gather + kick + drift + wrap + reductions */
+  NNPM_MS_SORT = 3,    /* counting sort (when it ran this step) */
+  NNPM_MS_EXCHANGE = 4,/* particle migration between slabs */
+  NNPM_MS_COMM = 5,    /* of SOLVE: time inside the all-to-all transposes */
+  NNPM_MS_COUNT = 8
+};
+
+/* per-step reductions the reference prints / uses for dt control
+ * (src/ParticleMesh.jl:782, :875-878) */
+typedef struct {
+  double max_abs_v;   /* maximum(abs(v)) over this rank (the host adds 1e-30) */
+  double max_v;       /* maximum(v), signed */
+  double max_pa;      /* maximum(pa), signed */
+  double rho_sum;     /* sum of the local deposit (mass conservation check) */
+  int64_t npart_local;/* particles on this rank after the step */
+  int64_t n_migrated; /* particles this rank sent away this step */
+  float ms[NNPM_MS_COUNT]; /* CUDA-event milliseconds per phase (timing=1), else 0 */
+  int32_t kernel_launches; /* kernels + cuFFT execs + NCCL ops launched by this call */
+  int32_t pad;
+} nnpm_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int nnpm_version(void);
+/* Replaces the buffer allocation at src/ParticleMesh.jl:754-757 / :833-838 and the
+ * GridPatch/GridData/particle-dict containers (src/GridTypes.jl:4-16, ParticleMesh.jl:112-124). */
+int nnpm_create(nnpm_ctx **out, const nnpm_config *cfg);
+int nnpm_destroy(nnpm_ctx *ctx);
+const char *nnpm_last_error(const nnpm_ctx *ctx); /* ctx may be NULL: error of a failed create */
+
+/* Multi-GPU (new; the reference has no parallelism, Readme.md:53).  Rank 0 calls
+ * nnpm_comm_unique_id, the host broadcasts the 128 bytes by any means (torch.distributed, MPI,
+ * a file), then every rank calls nnpm_comm_init.  Not needed when nranks == 1. */
+int nnpm_comm_unique_id(uint8_t id_out[128]);
+int nnpm_comm_init(nnpm_ctx *ctx, const uint8_t id[128]);
+
+/* pinned host memory for fast upload/download (cudaHostAlloc) */
+int nnpm_host_alloc(void **ptr, uint64_t bytes);
+int nnpm_host_free(void *ptr);
+
+/* ---- particle state --------------------------------------------------------------------- */
+/* p["x"], p["v"], p["m"] (ParticleMesh.jl:122-124): n particles in Julia (rank,n) layout from
+ * this rank's host; any particles may be given to any rank -- nnpm_redistribute routes them to
+ * the owning slab.  first_id is the global index of x_aos[:,0] (original order is kept as an id
+ * so that download returns the reference's ordering). */
+int nnpm_upload_particles(nnpm_ctx *ctx, const double *x_aos, const double *v_aos, int64_t n,
+                          int64_t first_id, double m);
+/* Route every particle to the rank owning floor(x3*N3) (NCCL p2p); no-op when nranks == 1. */
+int nnpm_redistribute(nnpm_ctx *ctx);
+int64_t nnpm_local_count(const nnpm_ctx *ctx);
+/* Copy this rank's particles back: x_aos/v_aos (rank,n_local) and their global ids (may be
+ * NULL).  With ids_out == NULL and nranks == 1 the particles are written in ORIGINAL order. */
+int nnpm_download_particles(nnpm_ctx *ctx, double *x_aos, double *v_aos, int64_t *ids_out);
+/* Device-side synthetic ICs (lattice of ParticleMesh.jl:257-287, optionally displaced by a
+ * seeded plane-wave Zel'dovich field; oracle/pm_ref.py:synthetic_zeldovich is the checker).
+ * pdims = ParticleDimensions; v = vfac * displacement. */
+int nnpm_init_synthetic(nnpm_ctx *ctx, int kind, const int64_t pdims[3], uint64_t seed,
+                        int32_t nmodes, int32_t kmax, double disp_rms, double vfac, double m);
+/* Counting sort of the local particles by cell (new; K0 of the design). */
+int nnpm_sort(nnpm_ctx *ctx);
+
+/* ---- operator-granular entry points (un-fused; for field-level parity) -------------------- */
+int nnpm_make_periodic(nnpm_ctx *ctx);                 /* make_periodic  ParticleMesh.jl:409-415 */
+int nnpm_deposit(nnpm_ctx *ctx);                       /* deposit        ParticleMesh.jl:289-303,326-407 */
+int nnpm_solve(nnpm_ctx *ctx);                         /* compute_potential ParticleMesh.jl:417-505 (mean removal :768-769 folded into the zeroed DC bin) */
+int nnpm_accel(nnpm_ctx *ctx);                         /* compute_acceleration ParticleMesh.jl:631-637,507-573 (materialises acc) */
+int nnpm_interp(nnpm_ctx *ctx);                        /* interpVecToPoints ParticleMesh.jl:640-721 (materialises pa from acc) */
+int nnpm_drift(nnpm_ctx *ctx, double dt);              /* drift          ParticleMesh.jl:723-728 */
+int nnpm_kick(nnpm_ctx *ctx, double dt);               /* kick (static)  ParticleMesh.jl:731-736 */
+int nnpm_kick_comoving(nnpm_ctx *ctx, double dt, double a, double dadt); /* kick ParticleMesh.jl:800-807 */
+
+/* gd[1].d["ρD"], gd[1].d["Φ"], acc, pa -- Julia layout, local slab / local particles. */
+int nnpm_get_field(nnpm_ctx *ctx, int which, double *host_out);
+int nnpm_set_field(nnpm_ctx *ctx, int which, const double *host_in);
+
+/* ---- fused steps (the hot path) ----------------------------------------------------------- */
+/* Body of evolvePM's loop, src/ParticleMesh.jl:766-778, plus the reductions of :782. */
+int nnpm_step_static(nnpm_ctx *ctx, double dt, nnpm_stats *stats);
+/* Body of evolvePMCosmology's loop, src/ParticleMesh.jl:853-868, plus the reductions of
+ * :875-878.  a_d1 = a(t+dt/4), a_k = a(t+dt/2), adot_k = da/dt(t+dt/2), a_d2 = a(t+3dt/4)
+ * come from the host cosmology (src/cosmology.jl:19-42). */
+int nnpm_step_comoving(nnpm_ctx *ctx, double dt, double a_d1, double a_k, double adot_k,
+                       double a_d2, nnpm_stats *stats);
+/* Global (all-rank) maxima of the last step's stats: NCCL allreduce(max) when nranks > 1. */
+int nnpm_reduce_stats(nnpm_ctx *ctx, nnpm_stats *stats);
+
+/* Device bytes currently allocated by this context (for sizing reports). */
+int64_t nnpm_device_bytes(const nnpm_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNPM_H */
