@@ -80,6 +80,8 @@ enum {
   NNPM_MS_SORT = 3,    /* counting sort (when it ran this step) */
   NNPM_MS_EXCHANGE = 4,/* particle migration between slabs */
   NNPM_MS_COMM = 5,    /* of SOLVE: time inside the all-to-all transposes */
+  NNPM_MS_FFT_Z = 6,   /* of SOLVE: the z pass (z-FFT, Green multiply, z-iFFT) */
+  NNPM_MS_FFT_XY = 7,  /* of SOLVE: the two batched 2-D transforms */
   NNPM_MS_COUNT = 8
 };
 
@@ -89,7 +91,7 @@ typedef struct {
   double max_abs_v;   /* maximum(abs(v)) over this rank (the host adds 1e-30) */
   double max_v;       /* maximum(v), signed */
   double max_pa;      /* maximum(pa), signed */
-  double rho_sum;     /* sum of the local deposit (mass conservation check) */
+  int64_t n_halo_violations; /* particles whose half-drift left the slab's ghost region (must be 0) */
   int64_t npart_local;/* particles on this rank after the step */
   int64_t n_migrated; /* particles this rank sent away this step */
   float ms[NNPM_MS_COUNT]; /* CUDA-event milliseconds per phase (timing=1), else 0 */
@@ -163,6 +165,20 @@ int nnpm_reduce_stats(nnpm_ctx *ctx, nnpm_stats *stats);
 
 /* Device bytes currently allocated by this context (for sizing reports). */
 int64_t nnpm_device_bytes(const nnpm_ctx *ctx);
+
+/* powerSpectrum, src/ParticleMesh.jl:65-100 (+ fftfreq :202-206), on the device-resident
+ * particles: deposit -> delta = rho/mean - 1 -> |fft(delta)|^2 * prod(box)/prod(dims)^2 ->
+ * shell bins n = round(|k|/dk), dk = 2pi/max(dims).  karray_out/power_out have lenk =
+ * round(max(dims)/2) entries; with nranks > 1 every rank receives the global result.
+ * Overwrites the mesh (rho/phi).  box = (1,1,1), the only domain the reference tests. */
+int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, int32_t lenk);
+
+/* Runtime tuning knobs (new; no reference counterpart).  Unknown names -> NNPM_ERR_ARG.
+ *   "fft3d"        1 = single cuFFT 3-D plan instead of 2-D + fused z pass (nranks == 1 only)
+ *   "zfused"       1 = hand-written fused z-FFT * Green * z-iFFT kernel (default), 0 = cuFFT z
+ *   "tile_deposit" 1 = shared-memory tiled deposit on tile-sorted particles (default), 0 = global atomics
+ *   "tile_push"    1 = push gathers phi from a shared-memory tile on sorted particles, 0 = L2 gather */
+int nnpm_set_option(nnpm_ctx *ctx, const char *name, double value);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,671 @@
+// nnpm_kernels.cuh -- device kernels of the particle-mesh step (sm_100a).
+//
+// Arithmetic follows src/ParticleMesh.jl of the reference operation by operation; the
+// __dmul_rn/__dadd_rn/__dsub_rn/__ddiv_rn intrinsics pin the reference's evaluation order
+// (they are never contracted into FMAs), so every per-particle quantity is bit-identical to
+// the Julia/oracle value for the same inputs.  Only summation order (atomics) and the FFT
+// differ from the reference at rounding level.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef long long i64;
+typedef unsigned long long u64;
+
+struct Geom {
+  i64 N1, N2, N3;   // global mesh (TopgridDimensions); N3 == 1 for rank-2 runs
+  i64 rowp;         // padded row length in doubles = 2*(N1/2+1)  (in-place r2c layout)
+  i64 plane;        // N2*rowp doubles per k-plane
+  i64 kz0, nzl;     // first owned plane, number of owned planes (slab along k)
+  int glo;          // ghost planes kept below the slab (2 when nranks>1, else 0)
+  int nplanes;      // planes allocated = nzl + (nranks>1 ? 5 : 0)
+  double fN1, fN2, fN3;
+};
+
+// ------------------------------------------------------------------------------------------
+// reference-order scalar helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double wrap01(double x) {  // make_periodic, ParticleMesh.jl:409-415
+  if (x < 0.) x = __dadd_rn(x, 1.0);
+  if (x > 1.) x = __dsub_rn(x, 1.0);
+  return x;
+}
+
+// ii = floor(x*N)+1 ; d = x*N - ii + 1 ; ip1 = ii==N ? 1 : ii+1   (ParticleMesh.jl:386-388),
+// returned 0-based; index N (x == 1.0) and strays wrap periodically.
+__device__ __forceinline__ void cell_of(double x, double fN, i64 N, i64& i0, i64& ip, double& d) {
+  double t = __dmul_rn(x, fN);
+  double fl = floor(t);
+  d = __dadd_rn(__dsub_rn(t, fl + 1.0), 1.0);
+  i64 z = (i64)fl;
+  if (z >= N) z -= N;
+  if (z < 0) z += N;
+  if (z >= N || z < 0) z = ((z % N) + N) % N;
+  i0 = z;
+  ip = (z == N - 1) ? 0 : z + 1;
+}
+
+__device__ __forceinline__ i64 wrap_idx(i64 z, i64 N) {
+  if (z >= N) z -= N;
+  if (z < 0) z += N;
+  if (z >= N || z < 0) z = ((z % N) + N) % N;
+  return z;
+}
+
+// local plane of global plane k: p = k - kz0 + glo, unwrapped periodically into the slab's
+// ghost window.  Returns -1 when the plane is not held by this rank.
+__device__ __forceinline__ int local_plane(i64 k, const Geom& g) {
+  i64 d = k - g.kz0;
+  if (g.glo) {
+    if (d >= g.nzl + 3) d -= g.N3;
+    if (d < -2) d += g.N3;
+    if (d < -2 || d >= g.nzl + 3) return -1;
+  }
+  return (int)(d + g.glo);
+}
+
+__device__ __forceinline__ i64 ord_encode(double v) {  // monotone double -> int64
+  i64 k = __double_as_longlong(v);
+  return k >= 0 ? k : (k ^ 0x7FFFFFFFFFFFFFFFLL);
+}
+
+// warp+block max of three values, then one atomicMax each per block
+__device__ __forceinline__ void block_max3(double a, double b, double c, i64* out) {
+  __shared__ double s[3][32];
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a = fmax(a, __shfl_xor_sync(full, a, o));
+    b = fmax(b, __shfl_xor_sync(full, b, o));
+    c = fmax(c, __shfl_xor_sync(full, c, o));
+  }
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  if (l == 0) { s[0][w] = a; s[1][w] = b; s[2][w] = c; }
+  __syncthreads();
+  if (w == 0) {
+    a = l < nw ? s[0][l] : -INFINITY;
+    b = l < nw ? s[1][l] : -INFINITY;
+    c = l < nw ? s[2][l] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a = fmax(a, __shfl_xor_sync(full, a, o));
+      b = fmax(b, __shfl_xor_sync(full, b, o));
+      c = fmax(c, __shfl_xor_sync(full, c, o));
+    }
+    if (l == 0) {
+      atomicMax(&out[0], ord_encode(a));
+      atomicMax(&out[1], ord_encode(b));
+      atomicMax(&out[2], ord_encode(c));
+    }
+  }
+}
+
+struct PartPtrs {
+  double* x[3];
+  double* v[3];
+};
+
+// ------------------------------------------------------------------------------------------
+// host AoS (rank,n)  <->  device SoA
+// ------------------------------------------------------------------------------------------
+template <int RANK>
+__global__ void k_aos2soa(const double* __restrict__ aos, double* d0, double* d1, double* d2, i64 n) {
+  i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  d0[t] = aos[RANK * t + 0];
+  d1[t] = aos[RANK * t + 1];
+  if (RANK == 3) d2[t] = aos[RANK * t + 2];
+}
+template <int RANK>
+__global__ void k_soa2aos(double* __restrict__ aos, const double* d0, const double* d1, const double* d2,
+                          i64 n) {
+  i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  aos[RANK * t + 0] = d0[t];
+  aos[RANK * t + 1] = d1[t];
+  if (RANK == 3) aos[RANK * t + 2] = d2[t];
+}
+__global__ void k_iota_u32(uint32_t* ids, i64 n, u64 first) {
+  i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t < n) ids[t] = (uint32_t)(first + (u64)t);
+}
+__global__ void k_u32_to_i64(i64* out, const uint32_t* in, i64 n) {
+  i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t < n) out[t] = (i64)in[t];
+}
+
+// ------------------------------------------------------------------------------------------
+// un-fused particle operators
+// ------------------------------------------------------------------------------------------
+__global__ void k_make_periodic(double* a, i64 n) {  // ParticleMesh.jl:409-415
+  i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t < n) a[t] = wrap01(a[t]);
+}
+__global__ void k_axpy_rn(double* x, const double* v, double dt, i64 n) {  // drift :723-728, kick :731-736
+  i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t < n) x[t] = __dadd_rn(x[t], __dmul_rn(dt, v[t]));
+}
+// comoving kick, ParticleMesh.jl:800-807:  vmid = v + (pa*dt)/2 ; v += (-vmid*(adot/a) + pa/a)*dt
+__device__ __forceinline__ double kick_comoving_rn(double v, double pa, double dt, double a, double hub) {
+  double vmid = __dadd_rn(v, __dmul_rn(__dmul_rn(pa, dt), 0.5));
+  double t = __dadd_rn(__dmul_rn(-vmid, hub), __ddiv_rn(pa, a));
+  return __dadd_rn(v, __dmul_rn(t, dt));
+}
+__global__ void k_kick_comoving(double* v, const double* pa, double dt, double a, double hub, i64 n) {
+  i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t < n) v[t] = kick_comoving_rn(v[t], pa[t], dt, a, hub);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 deposit (global-atomic form).  ParticleMesh.jl:289-303, 326-407.
+//   PRE: apply the leading half-drift x + c0*v (comoving step, :854) without storing it.
+//   Always applies make_periodic (:766 / :856) on the fly.
+//   FIXED: accumulate llrint(w * 2^B) into the int64 view of the mesh (deterministic).
+// ------------------------------------------------------------------------------------------
+template <int RANK, int INTERP, bool FIXED, bool PRE>
+__global__ void __launch_bounds__(256)
+k_deposit(PartPtrs p, i64 np, double c0, Geom g, double* __restrict__ mesh, double m, double fscale,
+          u64* __restrict__ viol) {
+  i64 n = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (n >= np) return;
+  double x0 = p.x[0][n], x1 = p.x[1][n], x2 = (RANK == 3) ? p.x[2][n] : 0.0;
+  if (PRE) {
+    x0 = __dadd_rn(x0, __dmul_rn(c0, p.v[0][n]));
+    x1 = __dadd_rn(x1, __dmul_rn(c0, p.v[1][n]));
+    if (RANK == 3) x2 = __dadd_rn(x2, __dmul_rn(c0, p.v[2][n]));
+  }
+  x0 = wrap01(x0);
+  x1 = wrap01(x1);
+  if (RANK == 3) x2 = wrap01(x2);
+
+  auto add = [&](i64 idx, double w) {
+    if (FIXED) {
+      i64 q = __double2ll_rn(__dmul_rn(w, fscale));
+      atomicAdd((u64*)mesh + idx, (u64)q);
+    } else {
+      atomicAdd(mesh + idx, w);
+    }
+  };
+
+  if (INTERP == 0) {  // NGP, :326-353
+    i64 i, j, k = 0;
+    if (RANK == 2) {
+      i = (i64)floor(__dmul_rn(x0, g.fN1));
+      j = (i64)floor(__dmul_rn(x1, g.fN2));
+    } else {
+      i = (i64)floor(__dadd_rn(__dmul_rn(x0, g.fN1), 1.0)) - 1;
+      j = (i64)floor(__dadd_rn(__dmul_rn(x1, g.fN2), 1.0)) - 1;
+      k = wrap_idx((i64)floor(__dadd_rn(__dmul_rn(x2, g.fN3), 1.0)) - 1, g.N3);
+    }
+    i = wrap_idx(i, g.N1);
+    j = wrap_idx(j, g.N2);
+    int pl = (RANK == 3) ? local_plane(k, g) : g.glo;
+    if (pl < 0) { atomicAdd(viol, 1ull); return; }
+    add(i + g.rowp * j + g.plane * pl, FIXED ? 1.0 : m);
+    return;
+  }
+
+  i64 i, ip, j, jp;
+  double dx, dy;
+  cell_of(x0, g.fN1, g.N1, i, ip, dx);
+  cell_of(x1, g.fN2, g.N2, j, jp, dy);
+  const double mm = FIXED ? 1.0 : m;
+  const double wx0 = __dmul_rn(mm, __dsub_rn(1.0, dx)), wx1 = __dmul_rn(mm, dx);
+  const double ody = __dsub_rn(1.0, dy);
+  if (RANK == 2) {  // :376-379
+    double* base = mesh + g.plane * g.glo;
+    (void)base;
+    i64 off = g.plane * g.glo;
+    add(off + i + g.rowp * j, __dmul_rn(wx0, ody));
+    add(off + i + g.rowp * jp, __dmul_rn(wx0, dy));
+    add(off + ip + g.rowp * j, __dmul_rn(wx1, ody));
+    add(off + ip + g.rowp * jp, __dmul_rn(wx1, dy));
+    return;
+  }
+  i64 k, kp;
+  double dz;
+  cell_of(x2, g.fN3, g.N3, k, kp, dz);
+  int p0 = local_plane(k, g), p1 = local_plane(kp, g);
+  if (p0 < 0 || p1 < 0) { atomicAdd(viol, 1ull); return; }
+  const double odz = __dsub_rn(1.0, dz);
+  const i64 r0 = g.rowp * j, r1 = g.rowp * jp;
+  const i64 o0 = g.plane * p0, o1 = g.plane * p1;
+  // :395-402
+  add(o0 + r0 + i, __dmul_rn(__dmul_rn(wx0, ody), odz));
+  add(o0 + r1 + i, __dmul_rn(__dmul_rn(wx0, dy), odz));
+  add(o0 + r0 + ip, __dmul_rn(__dmul_rn(wx1, ody), odz));
+  add(o0 + r1 + ip, __dmul_rn(__dmul_rn(wx1, dy), odz));
+  add(o1 + r0 + i, __dmul_rn(__dmul_rn(wx0, ody), dz));
+  add(o1 + r1 + i, __dmul_rn(__dmul_rn(wx0, dy), dz));
+  add(o1 + r0 + ip, __dmul_rn(__dmul_rn(wx1, ody), dz));
+  add(o1 + r1 + ip, __dmul_rn(__dmul_rn(wx1, dy), dz));
+}
+
+// int64 fixed-point accumulations -> f64 density, in place: rho = m * (Q * 2^-B)
+__global__ void k_fixed_to_f64(double* mesh, i64 n, double inv_scale, double m) {
+  i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  i64 q = ((const i64*)mesh)[t];
+  mesh[t] = __dmul_rn(m, __dmul_rn((double)q, inv_scale));
+}
+
+// dst += src over n elements; FIXED adds the int64 views (ghost-plane fold)
+template <bool FIXED>
+__global__ void k_add_planes(double* dst, const double* src, i64 n) {
+  i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  if (FIXED) ((i64*)dst)[t] += ((const i64*)src)[t];
+  else dst[t] = __dadd_rn(dst[t], src[t]);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 (cuFFT-composed form): Green's function multiply in k space, ParticleMesh.jl:482-502 /
+// :451-466.  Spectrum layout [k][jl][ic] (k slowest), jl = local j range starting at j0
+// (slab-transposed when nranks > 1).  s1/s2/s3 = sin^2(k_d/2) tables built on the host with
+// the reference's expressions.  scale = 1/(N1*N2*N3) (unnormalised cuFFT inverse) * 1/N1^2.
+// ------------------------------------------------------------------------------------------
+__global__ void k_green(double2* __restrict__ rt, i64 icn, i64 njl, i64 j0, i64 nk, const double* __restrict__ s1,
+                        const double* __restrict__ s2, const double* __restrict__ s3, int rank3, double scale) {
+  i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  i64 jl = blockIdx.y;
+  if (i >= icn) return;
+  const double sxy = __dadd_rn(s1[i], s2[j0 + jl]);
+  for (i64 k = blockIdx.z; k < nk; k += gridDim.z) {
+    double ginv = rank3 ? __dmul_rn(-4.0, __dadd_rn(sxy, s3[k])) : __dmul_rn(-4.0, sxy);
+    i64 idx = i + icn * (jl + njl * k);
+    double2 val = rt[idx];
+    if (ginv != 0.0) {
+      val.x = __dmul_rn(__ddiv_rn(val.x, ginv), scale);
+      val.y = __dmul_rn(__ddiv_rn(val.y, ginv), scale);
+    } else {
+      val.x = __dmul_rn(val.x, scale);
+      val.y = __dmul_rn(val.y, scale);
+    }
+    if (i == 0 && j0 + jl == 0 && k == 0) { val.x = 0.0; val.y = 0.0; }  // rt[1,1,1] = 0, :501
+    rt[idx] = val;
+  }
+}
+
+// slab transpose helpers (nranks > 1).  A: [kl][j][ic] (local planes, all j);
+// S: [d][kl][jl][ic] (block d goes to rank d).
+__global__ void k_pack_fwd(const double2* __restrict__ A, double2* __restrict__ S, i64 icn, i64 N2, i64 njl,
+                           i64 nzl, i64 aplane_c) {
+  i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  i64 j = blockIdx.y, kl = blockIdx.z;
+  if (i >= icn) return;
+  i64 d = j / njl, jl = j - d * njl;
+  S[i + icn * (jl + njl * (kl + nzl * d))] = A[i + icn * j + aplane_c * kl];
+}
+__global__ void k_unpack_bwd(double2* __restrict__ A, const double2* __restrict__ S, i64 icn, i64 N2, i64 njl,
+                             i64 nzl, i64 aplane_c) {
+  i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  i64 j = blockIdx.y, kl = blockIdx.z;
+  if (i >= icn) return;
+  i64 d = j / njl, jl = j - d * njl;
+  A[i + icn * j + aplane_c * kl] = S[i + icn * (jl + njl * (kl + nzl * d))];
+}
+
+// ------------------------------------------------------------------------------------------
+// compute_acceleration materialised (parity path only), ParticleMesh.jl:631-637, 549-573:
+// acc[c,i,j,q] = -(N1 * ((phi[+1 along c] - phi[-1 along c]) / 2)), component-fastest.
+// q runs over nq planes starting at global plane kq0 (owned planes, +-1 when nranks > 1).
+// ------------------------------------------------------------------------------------------
+template <int RANK>
+__global__ void k_accel(double* __restrict__ acc, const double* __restrict__ phi, Geom g, i64 kq0, i64 nq) {
+  i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  i64 j = blockIdx.y, q = blockIdx.z;
+  if (i >= g.N1) return;
+  i64 k = wrap_idx(kq0 + q, g.N3);
+  i64 ip1 = (i == g.N1 - 1) ? 0 : i + 1, im1 = (i == 0) ? g.N1 - 1 : i - 1;
+  i64 jp1 = (j == g.N2 - 1) ? 0 : j + 1, jm1 = (j == 0) ? g.N2 - 1 : j - 1;
+  int pc = (RANK == 3) ? local_plane(k, g) : g.glo;
+  const double* P = phi + g.plane * pc;
+  double* o = acc + 3 * (i + g.N1 * (j + g.N2 * q));
+  o[0] = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(P[ip1 + g.rowp * j], P[im1 + g.rowp * j]), 0.5));
+  o[1] = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(P[i + g.rowp * jp1], P[i + g.rowp * jm1]), 0.5));
+  if (RANK == 3) {
+    i64 kp1 = (k == g.N3 - 1) ? 0 : k + 1, km1 = (k == 0) ? g.N3 - 1 : k - 1;
+    const double* Pp = phi + g.plane * local_plane(kp1, g);
+    const double* Pm = phi + g.plane * local_plane(km1, g);
+    o[2] = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(Pp[i + g.rowp * j], Pm[i + g.rowp * j]), 0.5));
+  } else {
+    o[2] = 0.0;  // third component stays as allocated (zeros), ParticleMesh.jl:754
+  }
+}
+
+// interpVecToPoints from a materialised acc (parity path only), ParticleMesh.jl:640-721.
+template <int RANK, int INTERP>
+__global__ void k_interp_acc(double* pa0, double* pa1, double* pa2, const double* __restrict__ acc, PartPtrs p,
+                             i64 np, Geom g, i64 kq0, i64 nq, int bugz) {
+  i64 n = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (n >= np) return;
+  double x0 = p.x[0][n], x1 = p.x[1][n], x2 = (RANK == 3) ? p.x[2][n] : 0.0;
+  auto A = [&](int m, i64 i, i64 j, i64 k) -> double {
+    i64 q = 0;
+    if (RANK == 3) {
+      q = k - kq0;
+      if (q < 0) q += g.N3;
+      if (q >= g.N3) q -= g.N3;
+      if (q >= nq) q = nq - 1;  // not held: clamp (halo violation is reported by the fused path)
+    }
+    return acc[m + 3 * (i + g.N1 * (j + g.N2 * q))];
+  };
+  if (INTERP == 0) {  // :642-652
+    i64 i = wrap_idx((i64)floor(__dmul_rn(x0, g.fN1)), g.N1);
+    i64 j = wrap_idx((i64)floor(__dmul_rn(x1, g.fN2)), g.N2);
+    i64 k = 0;
+    if (RANK == 3) k = bugz ? wrap_idx((i64)floor(x2) * g.N3, g.N3) : wrap_idx((i64)floor(__dmul_rn(x2, g.fN3)), g.N3);
+    pa0[n] = A(0, i, j, k);
+    pa1[n] = A(1, i, j, k);
+    if (RANK == 3) pa2[n] = A(2, i, j, k);
+    return;
+  }
+  i64 i, ip, j, jp;
+  double dx, dy;
+  cell_of(x0, g.fN1, g.N1, i, ip, dx);
+  cell_of(x1, g.fN2, g.N2, j, jp, dy);
+  const double odx = __dsub_rn(1.0, dx), ody = __dsub_rn(1.0, dy);
+  if (RANK == 2) {  // :686-689
+    double* out[2] = {pa0, pa1};
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+      double s = __dmul_rn(__dmul_rn(A(m, i, j, 0), odx), ody);
+      s = __dadd_rn(s, __dmul_rn(__dmul_rn(A(m, ip, j, 0), dx), ody));
+      s = __dadd_rn(s, __dmul_rn(__dmul_rn(A(m, i, jp, 0), odx), dy));
+      s = __dadd_rn(s, __dmul_rn(__dmul_rn(A(m, ip, jp, 0), dx), dy));
+      out[m][n] = s;
+    }
+    return;
+  }
+  i64 k, kp;
+  double dz;
+  if (bugz) {  // literal :706-708:  k = floor(x3)*Ng3 + 1 ; kp1 = k==Ng3 ? 1 : k+1 ; dz = x3*Ng3 - k + 1
+    i64 k1 = (i64)floor(x2) * g.N3 + 1;
+    dz = __dadd_rn(__dsub_rn(__dmul_rn(x2, g.fN3), (double)k1), 1.0);
+    k = wrap_idx(k1 - 1, g.N3);
+    kp = (k1 == g.N3) ? 0 : wrap_idx(k1, g.N3);
+  } else {
+    cell_of(x2, g.fN3, g.N3, k, kp, dz);
+  }
+  const double odz = __dsub_rn(1.0, dz);
+  double* out[3] = {pa0, pa1, pa2};
+#pragma unroll
+  for (int m = 0; m < 3; m++) {  // :710-717
+    double s = __dmul_rn(__dmul_rn(__dmul_rn(A(m, i, j, k), odx), ody), odz);
+    s = __dadd_rn(s, __dmul_rn(__dmul_rn(__dmul_rn(A(m, ip, j, k), dx), ody), odz));
+    s = __dadd_rn(s, __dmul_rn(__dmul_rn(__dmul_rn(A(m, i, jp, k), odx), dy), odz));
+    s = __dadd_rn(s, __dmul_rn(__dmul_rn(__dmul_rn(A(m, ip, jp, k), dx), dy), odz));
+    s = __dadd_rn(s, __dmul_rn(__dmul_rn(__dmul_rn(A(m, i, j, kp), odx), ody), dz));
+    s = __dadd_rn(s, __dmul_rn(__dmul_rn(__dmul_rn(A(m, ip, j, kp), dx), ody), dz));
+    s = __dadd_rn(s, __dmul_rn(__dmul_rn(__dmul_rn(A(m, i, jp, kp), odx), dy), dz));
+    s = __dadd_rn(s, __dmul_rn(__dmul_rn(__dmul_rn(A(m, ip, jp, kp), dx), dy), dz));
+    out[m][n] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5 fused push: [leading half-drift recomputed] -> make_periodic -> gradient of phi taken on
+// the fly (compute_acceleration, :631-637) -> back-interpolation (:640-721) -> kick (:731-736 or
+// :800-807) -> drift(s) (:723-728) -> make_periodic -> max reductions (:782, :875-878).
+// phi is read straight from the padded in-place FFT buffer; acc and pa are never materialised.
+//   COMOVING: x' = wrap(x + c0*v); v' = kick_comoving; x'' = wrap(x' + c2*v')
+//   static  : x' = wrap(x);        x1 = x' + c1*v; v' = v + dt*pa; x'' = x1 + c1*v'
+// ------------------------------------------------------------------------------------------
+struct PushParams {
+  double c0, c1, c2, dt, a, hub;  // hub = adot/a evaluated on the host as the reference does
+  int bugz;
+};
+
+#define PHI(ii, jj, pp) __ldg(phi + (ii) + g.rowp * (jj) + g.plane * (i64)(pp))
+
+template <int RANK, int INTERP, bool COMOVING>
+__global__ void __launch_bounds__(256)
+k_push(PartPtrs p, i64 np, Geom g, const double* __restrict__ phi, PushParams pp, i64* __restrict__ red,
+       u64* __restrict__ viol) {
+  i64 n = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  double mxa = -INFINITY, mxv = -INFINITY, mxp = -INFINITY;
+  if (n < np) {
+    double x[3], v[3], pa[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < RANK; d++) {
+      x[d] = p.x[d][n];
+      v[d] = p.v[d][n];
+      if (COMOVING) x[d] = __dadd_rn(x[d], __dmul_rn(pp.c0, v[d]));
+      x[d] = wrap01(x[d]);
+    }
+    bool ok = true;
+    if (INTERP == 0) {
+      i64 i = wrap_idx((i64)floor(__dmul_rn(x[0], g.fN1)), g.N1);
+      i64 j = wrap_idx((i64)floor(__dmul_rn(x[1], g.fN2)), g.N2);
+      i64 ip1 = (i == g.N1 - 1) ? 0 : i + 1, im1 = (i == 0) ? g.N1 - 1 : i - 1;
+      i64 jp1 = (j == g.N2 - 1) ? 0 : j + 1, jm1 = (j == 0) ? g.N2 - 1 : j - 1;
+      int pc = g.glo, pu = 0, pd = 0;
+      if (RANK == 3) {
+        i64 k = pp.bugz ? wrap_idx((i64)floor(x[2]) * g.N3, g.N3) : wrap_idx((i64)floor(__dmul_rn(x[2], g.fN3)), g.N3);
+        i64 kp1 = (k == g.N3 - 1) ? 0 : k + 1, km1 = (k == 0) ? g.N3 - 1 : k - 1;
+        pc = local_plane(k, g); pu = local_plane(kp1, g); pd = local_plane(km1, g);
+        ok = pc >= 0 && pu >= 0 && pd >= 0;
+      }
+      if (ok) {
+        pa[0] = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(PHI(ip1, j, pc), PHI(im1, j, pc)), 0.5));
+        pa[1] = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(PHI(i, jp1, pc), PHI(i, jm1, pc)), 0.5));
+        if (RANK == 3) pa[2] = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(PHI(i, j, pu), PHI(i, j, pd)), 0.5));
+      }
+    } else {
+      i64 ia[4], ja[4];
+      double dx, dy, dz = 0.0;
+      cell_of(x[0], g.fN1, g.N1, ia[1], ia[2], dx);
+      cell_of(x[1], g.fN2, g.N2, ja[1], ja[2], dy);
+      ia[0] = (ia[1] == 0) ? g.N1 - 1 : ia[1] - 1;
+      ia[3] = (ia[2] == g.N1 - 1) ? 0 : ia[2] + 1;
+      ja[0] = (ja[1] == 0) ? g.N2 - 1 : ja[1] - 1;
+      ja[3] = (ja[2] == g.N2 - 1) ? 0 : ja[2] + 1;
+      const double odx = __dsub_rn(1.0, dx), ody = __dsub_rn(1.0, dy);
+      const double wxs[2] = {odx, dx}, wys[2] = {ody, dy};
+      if (RANK == 2) {
+        const int pc = g.glo;
+        double c[2][4], ylo[2], yhi[2];
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+          for (int a = 0; a < 4; a++) c[b][a] = PHI(ia[a], ja[1 + b], pc);
+#pragma unroll
+        for (int a = 0; a < 2; a++) { ylo[a] = PHI(ia[1 + a], ja[0], pc); yhi[a] = PHI(ia[1 + a], ja[3], pc); }
+        double ax[2][2], ay[2][2];
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+#pragma unroll
+          for (int a = 0; a < 2; a++) {
+            ax[b][a] = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(c[b][a + 2], c[b][a]), 0.5));
+            double hi = b ? yhi[a] : c[1][a + 1], lo = b ? c[0][a + 1] : ylo[a];
+            ay[b][a] = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(hi, lo), 0.5));
+          }
+        // order :687-688  (i,j) (ip,j) (i,jp) (ip,jp)
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+          double s = 0.0;
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            int a = t & 1, b = t >> 1;
+            double val = m ? ay[b][a] : ax[b][a];
+            double term = __dmul_rn(__dmul_rn(val, wxs[a]), wys[b]);
+            s = t ? __dadd_rn(s, term) : term;
+          }
+          pa[m] = s;
+        }
+      } else {
+        i64 k, kp;
+        if (pp.bugz) {
+          i64 k1 = (i64)floor(x[2]) * g.N3 + 1;
+          dz = __dadd_rn(__dsub_rn(__dmul_rn(x[2], g.fN3), (double)k1), 1.0);
+          k = wrap_idx(k1 - 1, g.N3);
+          kp = (k1 == g.N3) ? 0 : wrap_idx(k1, g.N3);
+        } else {
+          cell_of(x[2], g.fN3, g.N3, k, kp, dz);
+        }
+        i64 km1 = (k == 0) ? g.N3 - 1 : k - 1, kp2 = (kp == g.N3 - 1) ? 0 : kp + 1;
+        int pl[4] = {local_plane(km1, g), local_plane(k, g), local_plane(kp, g), local_plane(kp2, g)};
+        ok = pl[0] >= 0 && pl[1] >= 0 && pl[2] >= 0 && pl[3] >= 0;
+        if (ok) {
+          const double odz = __dsub_rn(1.0, dz);
+          const double wzs[2] = {odz, dz};
+          double c[2][2][4], ylo[2][2], yhi[2][2], zlo[2][2], zhi[2][2];
+#pragma unroll
+          for (int cz = 0; cz < 2; cz++)
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+#pragma unroll
+              for (int a = 0; a < 4; a++) c[cz][b][a] = PHI(ia[a], ja[1 + b], pl[1 + cz]);
+#pragma unroll
+          for (int cz = 0; cz < 2; cz++)
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+              ylo[cz][a] = PHI(ia[1 + a], ja[0], pl[1 + cz]);
+              yhi[cz][a] = PHI(ia[1 + a], ja[3], pl[1 + cz]);
+            }
+#pragma unroll
+          for (int b = 0; b < 2; b++)
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+              zlo[b][a] = PHI(ia[1 + a], ja[1 + b], pl[0]);
+              zhi[b][a] = PHI(ia[1 + a], ja[1 + b], pl[3]);
+            }
+          // order :710-717: (i,j,k)(ip,j,k)(i,jp,k)(ip,jp,k) then the kp four
+          double s[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+          for (int t = 0; t < 8; t++) {
+            const int a = t & 1, b = (t >> 1) & 1, cz = t >> 2;
+            double gx = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(c[cz][b][a + 2], c[cz][b][a]), 0.5));
+            double yh = b ? yhi[cz][a] : c[cz][1][a + 1], yl = b ? c[cz][0][a + 1] : ylo[cz][a];
+            double gy = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(yh, yl), 0.5));
+            double zh = cz ? zhi[b][a] : c[1][b][a + 1], zl = cz ? c[0][b][a + 1] : zlo[b][a];
+            double gz = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(zh, zl), 0.5));
+            double tx = __dmul_rn(__dmul_rn(__dmul_rn(gx, wxs[a]), wys[b]), wzs[cz]);
+            double ty = __dmul_rn(__dmul_rn(__dmul_rn(gy, wxs[a]), wys[b]), wzs[cz]);
+            double tz = __dmul_rn(__dmul_rn(__dmul_rn(gz, wxs[a]), wys[b]), wzs[cz]);
+            s[0] = t ? __dadd_rn(s[0], tx) : tx;
+            s[1] = t ? __dadd_rn(s[1], ty) : ty;
+            s[2] = t ? __dadd_rn(s[2], tz) : tz;
+          }
+          pa[0] = s[0]; pa[1] = s[1]; pa[2] = s[2];
+        }
+      }
+    }
+    if (!ok) atomicAdd(viol, 1ull);
+#pragma unroll
+    for (int d = 0; d < RANK; d++) {
+      double vn, xn;
+      if (COMOVING) {
+        vn = kick_comoving_rn(v[d], pa[d], pp.dt, pp.a, pp.hub);
+        xn = wrap01(__dadd_rn(x[d], __dmul_rn(pp.c2, vn)));
+      } else {
+        double x1 = __dadd_rn(x[d], __dmul_rn(pp.c1, v[d]));
+        vn = __dadd_rn(v[d], __dmul_rn(pp.dt, pa[d]));
+        xn = __dadd_rn(x1, __dmul_rn(pp.c1, vn));
+      }
+      p.x[d][n] = xn;
+      p.v[d][n] = vn;
+      mxa = fmax(mxa, fabs(vn));
+      mxv = fmax(mxv, vn);
+      mxp = fmax(mxp, pa[d]);
+    }
+  }
+  block_max3(mxa, mxv, mxp, red);
+}
+#undef PHI
+
+// ------------------------------------------------------------------------------------------
+// K0 counting sort by 8x8x8-cell tile (histogram -> scan -> scatter)
+// ------------------------------------------------------------------------------------------
+#define NNPM_TILE 8
+struct TileGeom {
+  i64 ntx, nty, ntz;
+};
+
+template <int RANK>
+__global__ void k_sort_count(PartPtrs p, i64 np, Geom g, TileGeom tg, uint32_t* __restrict__ hist,
+                             uint32_t* __restrict__ key, uint32_t* __restrict__ rnk) {
+  i64 n = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (n >= np) return;
+  i64 i = wrap_idx((i64)floor(wrap01(p.x[0][n]) * g.fN1), g.N1);
+  i64 j = wrap_idx((i64)floor(wrap01(p.x[1][n]) * g.fN2), g.N2);
+  i64 kl = 0;
+  if (RANK == 3) {
+    i64 k = wrap_idx((i64)floor(wrap01(p.x[2][n]) * g.fN3), g.N3);
+    kl = k - g.kz0;
+    if (kl < 0) kl = 0;              // strays (not yet migrated) sort into the boundary tiles
+    if (kl >= g.nzl) kl = g.nzl - 1;
+  }
+  uint32_t t = (uint32_t)((i / NNPM_TILE) + tg.ntx * ((j / NNPM_TILE) + tg.nty * (kl / NNPM_TILE)));
+  key[n] = t;
+  rnk[n] = atomicAdd(&hist[t], 1u);
+}
+
+// exclusive scan of uint32 in three launches (block sums -> scan of sums -> add back)
+#define SCAN_BLOCK 1024
+__global__ void k_scan_block(uint32_t* data, uint32_t* bsum, i64 n) {
+  __shared__ uint32_t s[SCAN_BLOCK];
+  i64 t = blockIdx.x * (i64)SCAN_BLOCK + threadIdx.x;
+  uint32_t v = t < n ? data[t] : 0u;
+  s[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
+    uint32_t a = threadIdx.x >= o ? s[threadIdx.x - o] : 0u;
+    __syncthreads();
+    s[threadIdx.x] += a;
+    __syncthreads();
+  }
+  if (t < n) data[t] = s[threadIdx.x] - v;  // exclusive
+  if (threadIdx.x == SCAN_BLOCK - 1) bsum[blockIdx.x] = s[threadIdx.x];
+}
+__global__ void k_scan_add(uint32_t* data, const uint32_t* bsum, i64 n) {
+  i64 t = blockIdx.x * (i64)SCAN_BLOCK + threadIdx.x;
+  if (t < n) data[t] += bsum[blockIdx.x];
+}
+__global__ void k_sort_dest(uint32_t* __restrict__ key, const uint32_t* __restrict__ rnk,
+                            const uint32_t* __restrict__ off, i64 np) {
+  i64 n = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (n < np) key[n] = off[key[n]] + rnk[n];
+}
+template <typename T>
+__global__ void k_permute(T* __restrict__ out, const T* __restrict__ in, const uint32_t* __restrict__ dest, i64 np) {
+  i64 n = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (n < np) out[dest[n]] = in[n];
+}
+
+// ------------------------------------------------------------------------------------------
+// device-side synthetic ICs: lattice (ParticleMesh.jl:257-287) + plane-wave Zel'dovich field
+// ------------------------------------------------------------------------------------------
+struct ICModes {
+  int n;
+  double amp;
+  int kx[64], ky[64], kz[64];
+  double ph[64];
+};
+template <int RANK>
+__global__ void k_init_synth(PartPtrs p, uint32_t* ids, i64 nloc, i64 first, i64 P1, i64 P2, i64 P3, ICModes M,
+                             double vfac) {
+  i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t >= nloc) return;
+  i64 gidx = first + t;
+  i64 i = gidx % P1, j = (gidx / P1) % P2, k = gidx / (P1 * P2);
+  double q[3];
+  q[0] = __ddiv_rn(__dsub_rn((double)(i + 1), 0.5), (double)P1);
+  q[1] = __ddiv_rn(__dsub_rn((double)(j + 1), 0.5), (double)P2);
+  q[2] = (RANK == 3) ? __ddiv_rn(__dsub_rn((double)(k + 1), 0.5), (double)P3) : 0.0;
+  double psi[3] = {0.0, 0.0, 0.0};
+  for (int mIdx = 0; mIdx < M.n; mIdx++) {
+    double k2 = (double)(M.kx[mIdx] * M.kx[mIdx] + M.ky[mIdx] * M.ky[mIdx] + M.kz[mIdx] * M.kz[mIdx]);
+    double arg = M.kx[mIdx] * q[0] + M.ky[mIdx] * q[1] + M.kz[mIdx] * q[2] + M.ph[mIdx];
+    double s = sinpi(2.0 * arg);
+    psi[0] += (M.amp * M.kx[mIdx] / k2) * s;
+    psi[1] += (M.amp * M.ky[mIdx] / k2) * s;
+    psi[2] += (M.amp * M.kz[mIdx] / k2) * s;
+  }
+#pragma unroll
+  for (int d = 0; d < RANK; d++) {
+    p.x[d][t] = wrap01(q[d] + psi[d]);
+    p.v[d][t] = vfac * psi[d];
+  }
+  ids[t] = (uint32_t)gidx;
+}

@@ -1,0 +1,297 @@
+"""Parity of the CUDA path (through the C ABI, via the reference-named host functions) against
+the CPU oracle on identical seeded inputs.  Tolerances: per-particle / per-cell arithmetic follows
+the reference's evaluation order and is bit-exact where no summation order or FFT is involved;
+density and everything downstream of the FFT is held to 1e-12 normalised L-infinity (the north
+star's single-step bound)."""
+import numpy as np
+import pytest
+
+from conftest import nlinf, make_particles
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def PM(lib_built):
+    from noname_b200 import ParticleMesh
+    yield ParticleMesh
+    ParticleMesh.clear_cache()
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import pm_ref
+    return pm_ref
+
+
+DIMS = [((16, 16, 1), 2), ((12, 20, 1), 2), ((16, 16, 16), 3), ((8, 12, 20), 3), ((32, 32, 32), 3)]
+
+
+@pytest.mark.parametrize("dims,rank", DIMS)
+@pytest.mark.parametrize("interp", ["cic", "none"])
+def test_deposit(PM, O, dims, rank, interp):
+    x, _ = make_particles(1, 5000, rank, clustered=True)
+    m = 0.37
+    shape = (dims[2], dims[1], dims[0])
+    ref = np.ones(shape)
+    O.deposit(ref, x.copy(), m, interpolation=interp)
+    got = np.ones(shape)
+    PM.deposit(got, x, m, interpolation=interp)
+    assert nlinf(got, ref) < TOL
+    assert abs(got.sum() - m * x.shape[0]) < 1e-9 * m * x.shape[0]      # mass conservation
+
+
+@pytest.mark.parametrize("dims,rank", [((16, 16, 1), 2), ((16, 16, 16), 3)])
+def test_deposit_fixedpoint_bitexact_run_to_run(PM, O, dims, rank):
+    x, _ = make_particles(2, 20000, rank, clustered=True)
+    shape = (dims[2], dims[1], dims[0])
+    PM.options["deposit_mode"] = "fixedpoint"
+    try:
+        outs = []
+        for rep in range(3):
+            perm = np.random.default_rng(rep).permutation(x.shape[0])     # order must not matter either
+            got = np.empty(shape)
+            PM.deposit(got, np.ascontiguousarray(x[perm]), 0.5, interpolation="cic")
+            outs.append(got)
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+        ref = np.empty(shape)
+        O.deposit(ref, x.copy(), 0.5, interpolation="cic")
+        assert nlinf(outs[0], ref) < 1e-11      # 2^-44 quantisation per contribution
+    finally:
+        PM.options["deposit_mode"] = "atomic"
+
+
+@pytest.mark.parametrize("dims,rank", DIMS)
+def test_potential(PM, O, dims, rank):
+    rng = np.random.default_rng(3)
+    shape = (dims[2], dims[1], dims[0])
+    rho = rng.random(shape)
+    rho -= rho.mean()
+    ref = np.empty(shape)
+    O.compute_potential(ref, rho, np.zeros((shape[0], shape[1], shape[2] // 2 + 1), dtype=np.complex128))
+    got = np.empty(shape)
+    PM.compute_potential(got, rho, None)
+    assert nlinf(got, ref) < TOL
+
+
+def test_potential_ignores_mean(PM, O):
+    """evolvePM subtracts mean(rho) (:768-769); the DC bin is zeroed (:501) so it must not matter."""
+    rng = np.random.default_rng(4)
+    rho = rng.random((16, 16, 16))
+    a = np.empty_like(rho)
+    b = np.empty_like(rho)
+    PM.compute_potential(a, rho, None)
+    PM.compute_potential(b, rho - rho.mean(), None)
+    assert nlinf(a, b) < TOL
+
+
+@pytest.mark.parametrize("dims,rank", DIMS)
+def test_acceleration_bitexact(PM, O, dims, rank):
+    rng = np.random.default_rng(5)
+    shape = (dims[2], dims[1], dims[0])
+    phi = rng.standard_normal(shape)
+    ref = np.zeros(shape + (3,))
+    O.compute_acceleration(ref, phi)
+    got = np.full(shape + (3,), 7.0)
+    PM.compute_acceleration(got, phi)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("dims,rank", DIMS)
+@pytest.mark.parametrize("interp", ["cic", "none"])
+def test_interp_bitexact(PM, O, dims, rank, interp):
+    rng = np.random.default_rng(6)
+    shape = (dims[2], dims[1], dims[0])
+    acc = rng.standard_normal(shape + (3,))
+    x, _ = make_particles(7, 3000, rank)
+    ref = np.zeros((x.shape[0], rank))
+    O.interpVecToPoints(ref, acc, x, interpolation=interp)
+    got = np.zeros_like(ref)
+    PM.interpVecToPoints(got, acc, x, interpolation=interp)
+    assert np.array_equal(got, ref)
+
+
+def test_interp_bugcompat_literal(PM, O):
+    """ParticleMesh.jl:706 literally (k = floor(x3)*Ng3 + 1), SURVEY.md F7."""
+    rng = np.random.default_rng(8)
+    acc = rng.standard_normal((8, 8, 8, 3))
+    x = rng.random((500, 3)) * 0.999
+    ref = np.zeros((500, 3))
+    O.interpVecToPoints(ref, acc, x, interpolation="cic", bugcompat=True)
+    PM.options["bugcompat_interp_z"] = True
+    try:
+        got = np.zeros_like(ref)
+        PM.interpVecToPoints(got, acc, x, interpolation="cic")
+    finally:
+        PM.options["bugcompat_interp_z"] = False
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("rank", [2, 3])
+def test_drift_kick_periodic_bitexact(PM, O, rank):
+    x, v = make_particles(9, 4000, rank)
+    pa = np.random.default_rng(10).standard_normal(x.shape)
+    x[10] = -0.25
+    x[11] = 1.25
+    xr, vr = x.copy(), v.copy()
+    O.drift(xr, vr, 0.013)
+    O.make_periodic(xr)
+    O.kick(vr, pa, 0.02)
+    O.kick(vr, pa, 0.02, 1.3, 0.7)
+    xg, vg = x.copy(), v.copy()
+    PM.drift(xg, vg, 0.013)
+    PM.make_periodic(xg)
+    PM.kick(vg, pa, 0.02)
+    PM.kick(vg, pa, 0.02, 1.3, 0.7)
+    assert np.array_equal(xg, xr)
+    assert np.array_equal(vg, vr)
+
+
+def _one_step(dev_kw, O, dims, rank, npart, comoving, seed=11, sort=False):
+    from noname_b200 import DevicePM
+    x, v = make_particles(seed, npart, rank, clustered=True)
+    m = float(np.prod(dims)) / npart
+    f = O.Fields(dims, npart, rank)
+    xr, vr = x.copy(), v.copy()
+    dt = 0.01
+    sc = (1.01, 1.02, 0.9, 1.03)
+    if comoving:
+        O.step_comoving(f, xr, vr, m, dt, *sc)
+    else:
+        O.step_static(f, xr, vr, m, dt)
+    with DevicePM(dims, npart, rank=rank, **dev_kw) as dev:
+        dev.upload(x, v, m)
+        if sort:
+            dev.sort()
+        st = dev.step_comoving(dt, *sc) if comoving else dev.step_static(dt)
+        phi = dev.get_field("phi")
+        xg, vg = dev.download()
+    return (xr, vr, f), (xg, vg, phi, st)
+
+
+@pytest.mark.parametrize("dims,rank", [((16, 16, 1), 2), ((16, 16, 16), 3), ((8, 12, 20), 3)])
+@pytest.mark.parametrize("comoving", [False, True])
+@pytest.mark.parametrize("sort", [False, True])
+def test_fused_step_matches_oracle(lib_built, O, dims, rank, comoving, sort):
+    (xr, vr, f), (xg, vg, phi, st) = _one_step({}, O, dims, rank, 6000, comoving, sort=sort)
+    assert nlinf(phi, f.phi) < TOL
+    assert nlinf(vg, vr) < TOL
+    assert np.max(np.abs(xg - xr)) < 1e-13
+    assert abs(st.max_abs_v - np.max(np.abs(vr))) <= 1e-12 * np.max(np.abs(vr))
+    assert abs(st.max_v - np.max(vr)) <= 1e-12 * abs(np.max(vr))
+    assert abs(st.max_pa - np.max(f.pa)) <= 1e-10 * abs(np.max(f.pa))
+    assert st.kernel_launches > 0 and st.n_halo_violations == 0
+
+
+def test_fused_step_single_step_fields_rho_acc(lib_built, O):
+    """north star: single-step density and acceleration fields within 1e-12 relative."""
+    from noname_b200 import DevicePM
+    dims, rank, npart = (32, 32, 32), 3, 32 ** 3
+    x, v = O.synthetic_zeldovich((32, 32, 32), 3, 12345, 16, 4, 0.3 / 32, 0.1)
+    m = 1.0
+    f = O.Fields(dims, npart, rank)
+    xr = x.copy()
+    O.make_periodic(xr)
+    O.deposit(f.rho, xr, m, "cic")
+    O.compute_potential(f.phi, f.rho - f.rho.mean(), f.rt)
+    O.compute_acceleration(f.acc, f.phi)
+    with DevicePM(dims, npart, rank=rank) as dev:
+        dev.upload(x, v, m)
+        dev.make_periodic()
+        dev.deposit()
+        rho = dev.get_field("rho")
+        dev.solve()
+        dev.accel()
+        acc = dev.get_field("acc")
+    assert nlinf(rho, f.rho) < TOL
+    assert nlinf(acc, f.acc) < TOL
+
+
+def test_synthetic_ics_match_oracle(lib_built, O):
+    from noname_b200 import DevicePM
+    for pdims, dims, rank in (((16, 16, 16), (16, 16, 16), 3), ((24, 24, 1), (16, 16, 1), 2)):
+        npart = int(np.prod(pdims))
+        xr, vr = O.synthetic_zeldovich(pdims, rank, 777, 12, 3, 0.02, 0.5)
+        with DevicePM(dims, npart, rank=rank) as dev:
+            dev.init_synthetic(pdims, seed=777, nmodes=12, kmax=3, disp_rms=0.02, vfac=0.5, m=1.0)
+            xg, vg = dev.download()
+        assert np.max(np.abs(xg - xr)) < 1e-13
+        assert np.max(np.abs(vg - vr)) < 1e-13
+
+
+def test_sort_keeps_particles_and_restores_order(lib_built):
+    from noname_b200 import DevicePM
+    x, v = make_particles(21, 10000, 3)
+    with DevicePM((16, 16, 16), 10000, rank=3) as dev:
+        dev.upload(x, v, 1.0)
+        dev.sort()
+        xs, vs, ids = dev.download(ids=True)
+        assert sorted(ids.tolist()) == list(range(10000))
+        assert np.array_equal(xs, x[ids]) and np.array_equal(vs, v[ids])
+        xo, vo = dev.download()
+        assert np.array_equal(xo, x) and np.array_equal(vo, v)
+
+
+@pytest.mark.parametrize("dims,rank", [((16, 16, 1), 2), ((16, 16, 16), 3), ((8, 12, 20), 3)])
+def test_power_spectrum(lib_built, O, dims, rank):
+    from noname_b200 import DevicePM
+    x, v = make_particles(31, 20000, rank, clustered=True)
+    kr, pr = O.powerSpectrum(x.copy(), 1.0, dims, "cic")
+    with DevicePM(dims, x.shape[0], rank=rank) as dev:
+        dev.upload(x, v, 1.0)
+        kg, pg = dev.power_spectrum()
+    assert np.allclose(kg, kr, rtol=1e-15)
+    ok = np.isfinite(pr)
+    assert np.array_equal(ok, np.isfinite(pg))
+    assert np.max(np.abs(pg[ok] / pr[ok] - 1.0)) < 1e-10
+
+
+def test_nstep_evolution_pk_within_1e6(lib_built, O):
+    """north star: final P(k) after N steps within 1e-6 (comoving loop, dt control included)."""
+    from noname_b200 import ParticleMesh as PM, cosmology as cos
+    dims, pdims, rank = (16, 16, 16), (16, 16, 16), 3
+    cosmo_kw = dict(h=0.7, OmegaM=0.3, OmegaR=0.0)
+    oc = O.Cosmo(**cosmo_kw)
+    zi, zf = 50.0, 20.0
+    ts, te = O.start_stop_times(oc, zi, zf)
+    a0 = O.a_from_t_internal(oc, ts, zi, zwherea1=zi)
+    ad0 = O.dadt_from_t_internal(oc, ts, zi)
+    x0, v0 = O.synthetic_zeldovich(pdims, rank, 5, 16, 3, 0.4 / 16, ad0 / a0)
+    m = 0.3
+    conf = dict(StartTime=ts, StopTime=te, StartCycle=0, StopCycle=12, InitialDt=1e-4, CourantFactor=0.5,
+                MaximumDt=1.0, DtFractionOfTime=0.1, InitialRedshift=zi)
+    xr, vr = x0.copy(), v0.copy()
+    logr = []
+    O.evolvePMCosmology(xr, vr, m, dims, dict(conf), oc, log=logr)
+    kr, pr = O.powerSpectrum(xr.copy(), m, dims, "cic")
+
+    from noname_b200.GridTypes import GridPatch, GridData
+    gp = {1: GridPatch([0, 0, 0], [1, 1, 1], 1, 1, dims)}
+    gd = {1: GridData({"ρD": np.ones(dims[::-1]), "Φ": np.ones(dims[::-1])})}
+    p = {"x": x0.copy(), "v": v0.copy(), "m": m}
+    c = dict(conf, ParticleDimensions=list(pdims), ParticleDepositInterpolation="cic", ParticleBackInterpolation="cic",
+             OutputEveryNCycle=0, OutputDtDataDump=0.0, LastOutputTime=0.0, OutputDisabled=True, _rank=3,
+             _cosmo=cos.Cosmology(**cosmo_kw))
+    logg = []
+    PM.evolvePMCosmology(gp, gd, p, c, log=logg)
+    assert len(logg) == len(logr) == 12
+    assert abs(logg[-1][0] - logr[-1][0]) < 1e-12 * logr[-1][0]
+    kg, pg = PM.powerSpectrum(gp, gd, p, c)
+    ok = np.isfinite(pr)
+    assert np.max(np.abs(pg[ok] / pr[ok] - 1.0)) < 1e-6
+    assert np.max(np.abs(p["x"] - xr)) < 1e-9
+
+
+def test_error_behaviour(PM):
+    import noname_b200 as nb
+    with pytest.raises(ValueError):
+        PM.deposit(np.zeros((4, 4, 4)), np.zeros((3, 3)), 1.0, interpolation="tsc")
+    with pytest.raises(TypeError):
+        PM.deposit(np.zeros((4, 4, 4), dtype=np.float32), np.zeros((3, 3)), 1.0, interpolation="cic")
+    with nb.DevicePM((8, 8, 8), 10) as dev:
+        with pytest.raises(nb.NNPMError):
+            dev.solve()                     # nothing deposited yet
+        with pytest.raises(nb.NNPMError):
+            dev.upload(np.zeros((11, 3)), None, 1.0)   # over capacity
