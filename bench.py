@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/s of one comoving PM step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 1024] [--mesh 1024]
+
+N = 1: the configuration the metric is quoted on, 1024^3 particles on a 1024^3 mesh (configs[3] of
+BASELINE.json fits one 180 GB B200), seeded synthetic Zel'dovich ICs generated on the device.
+N > 1 (under torchrun): the same global problem slab-decomposed over N ranks ("strong" scaling --
+the metric names a fixed 1024^3/1024^3 problem at 1/2/4/8 GPUs).
+
+One JSON line on stdout (rank 0).  `value`: device-resident steps (state in HBM before the timed
+region), CUDA events on the launching stream, max over ranks.  `e2e`: the same step through the
+C ABI with HOST buffers -- upload x,v (pinned) -> step -> download x,v + stats inside the timed
+region.  `roofline`: the dominant kernel (fused gather+push), algorithmic bytes / CUDA-event time.
+`cpu_baseline` / `--impl reference`: the C restatement of the reference's loops (oracle/pm_ref.c;
+the Julia reference cannot run in this image) on the host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-updates/sec per PM step (1024³ part, 1024³ mesh) at 1/2/4/8 B200; % HBM roofline"
+UNIT = "particle-updates/s"
+B_P_COMOVING = 144.0   # algorithmic bytes / particle / step
+B_C = 96.0             # algorithmic bytes / mesh cell / step
+PUSH_BYTES_PER_PARTICLE = 96.0   # R x,v (48) + W x,v (48)
+DEPOSIT_BYTES_PER_PARTICLE = 48.0
+COSMO = dict(h=0.7, OmegaM=0.3, OmegaR=0.0)
+ZINIT = 50.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, r in self.rows:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [q.strip() for q in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def scalars(t, dt):
+    """a(t+dt/4), a(t+dt/2), adot(t+dt/2), a(t+3dt/4) -- host cosmology, as evolvePMCosmology does."""
+    from noname_b200 import cosmology as cos
+    c = scalars.cosmo
+    a1 = cos.a_from_t_internal(c, t + dt / 2 / 2, ZINIT, zwherea1=ZINIT)
+    ak = cos.a_from_t_internal(c, t + dt / 2, ZINIT, zwherea1=ZINIT)
+    adk = cos.dadt(c, ak, zwherea1=ZINIT)
+    a2 = cos.a_from_t_internal(c, t + 3.0 * dt / 2 / 2, ZINIT, zwherea1=ZINIT)
+    return a1, ak, adk, a2
+
+
+def run_cpu(n, mesh, steps, warmup, threads):
+    """The reference's loops (C restatement + pocketfft) on the host: comoving steps on an n^3 / mesh^3
+    sample of the same synthetic workload.  Returns (pu/s, seconds per step)."""
+    import numpy as np
+    from oracle import pm_ref as O
+    from oracle.pm_ref_c import PMRefC
+    from noname_b200 import cosmology as cos
+    scalars.cosmo = cos.Cosmology(**COSMO)
+    ref = PMRefC(threads=threads)
+    oc = O.Cosmo(**COSMO)
+    ts, _ = O.start_stop_times(oc, ZINIT, 0.0)
+    a0 = O.a_from_t_internal(oc, ts, ZINIT, zwherea1=ZINIT)
+    ad0 = O.dadt_from_t_internal(oc, ts, ZINIT)
+    x, v = O.synthetic_zeldovich((n, n, n), 3, 12345, 32, 8, 0.3 / mesh, ad0 / a0)
+    m = (mesh ** 3) / float(n ** 3) * COSMO["OmegaM"]
+    f = O.Fields((mesh, mesh, mesh), n ** 3, 3)
+    t, dt = ts, 1e-4
+    el = []
+    for it in range(warmup + steps):
+        sc = scalars(t, dt)
+        t0 = time.perf_counter()
+        mabs, _ = ref.step_comoving(f, x, v, m, dt, *sc)
+        el.append(time.perf_counter() - t0)
+        t += dt
+        dt = min(0.5 * (1.0 / mesh) / mabs, 0.1 * t, 1.0)
+    sec = sum(el[warmup:]) / steps
+    return n ** 3 / sec, sec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--n", type=int, default=1024, help="particles per dimension")
+    ap.add_argument("--mesh", type=int, default=1024, help="mesh cells per dimension")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample", type=int, default=192, help="n of the n^3/n^3 CPU-baseline sample (0 = skip)")
+    ap.add_argument("--sort-every", type=int, default=0)
+    ap.add_argument("--deposit-mode", default="atomic")
+    ap.add_argument("--opt", action="append", default=[], help="name=value passed to nnpm_set_option")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(args.warmup, 3)
+    K = args.steps
+    n, mesh = args.n, args.mesh
+    workload = f"{n}^3 particles / {mesh}^3 mesh comoving PM step (LCDM Om=0.3 h=0.7), synthetic Zel'dovich ICs"
+    config = {"workload": workload, "particles": n ** 3, "mesh_cells": mesh ** 3, "interpolation": "cic/cic",
+              "l2": "inputs (>= 48 B/particle resident state) exceed the 126 MB L2 for n >= 256; no flush needed",
+              "parallelism": f"slab{world}" if world > 1 else "single"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = os.cpu_count() or 1
+        cs = args.cpu_sample or 192
+        val, sec = run_cpu(cs, cs, K, min(W, 1), threads)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+                "warmup": min(W, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                 "sample": f"{cs}^3 particles / {cs}^3 mesh comoving steps of the same synthetic workload; "
+                                           "C restatement of ParticleMesh.jl loops + pocketfft (the Julia reference cannot run here)"},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from noname_b200 import DevicePM, cosmology as cos, pinned_empty, pinned_free
+    scalars.cosmo = cos.Cosmology(**COSMO)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.current_stream()
+    peak, peak_src = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dev = DevicePM((mesh, mesh, mesh), n ** 3, rank=3, device=local_rank, nranks=world, rank_id=rank, timing=True,
+                   sort_every=args.sort_every, deposit_mode=args.deposit_mode, stream=stream.cuda_stream)
+    for kv in args.opt:
+        k, _, v = kv.partition("=")
+        dev.set_option(k, float(v))
+    if world > 1:
+        uid = [DevicePM.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        dev.comm_init(uid[0])
+    ts = scalars.cosmo.age_gyr(ZINIT) * (cos.gyr_in_s / cos.get_units(scalars.cosmo, ZINIT, zinit=ZINIT).T)
+    a0 = cos.a_from_t_internal(scalars.cosmo, ts, ZINIT, zwherea1=ZINIT)
+    ad0 = cos.dadt(scalars.cosmo, a0, zwherea1=ZINIT)
+    m = (mesh ** 3) / float(n ** 3) * COSMO["OmegaM"]
+    dev.init_synthetic((n, n, n), seed=12345, nmodes=32, kmax=8, disp_rms=0.3 / mesh, vfac=ad0 / a0, m=m)
+
+    state = {"t": ts, "dt": 1e-4}
+
+    def one_step():
+        sc = scalars(state["t"], state["dt"])
+        st = dev.step_comoving(state["dt"], *sc)
+        if world > 1:
+            dev.reduce_stats(st)
+        state["t"] += state["dt"]
+        state["dt"] = min(0.5 * (1.0 / mesh) / (st.max_abs_v + 1e-30), 0.1 * state["t"], 1.0)
+        return st
+
+    for _ in range(W):
+        one_step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    e0.record(stream)
+    launches = 0
+    ms_phase = {}
+    for _ in range(K):
+        st = one_step()
+        launches += st.kernel_launches
+        for k, v in st.as_dict()["ms"].items():
+            ms_phase[k] = ms_phase.get(k, 0.0) + v
+    e1.record(stream)
+    barrier()
+    wall1 = time.time()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    ms_step = ms_total / K
+    value = n ** 3 / (ms_step * 1e-3)
+    ms_phase = {k: v / K for k, v in ms_phase.items()}
+    np_local = dev.local_count
+
+    # roofline of the dominant kernel (fused gather + kick + drift push): algorithmic bytes / event time
+    push_ms = max_over_ranks(ms_phase["push"])
+    push_bytes = PUSH_BYTES_PER_PARTICLE * np_local
+    ach = push_bytes / (push_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "push_traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                tj = json.load(f)
+            if tj.get("particles") == np_local:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "kernel": "k_push (gradient + CIC gather + comoving kick + drift + wrap + max reductions)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": push_bytes,
+                "kernel_ms": push_ms, "phase_ms": ms_phase}
+    t_roof = ((n ** 3) * B_P_COMOVING + (mesh ** 3) * B_C) / world / (peak * 1e9)
+    if world > 1:
+        nvl = 2 * 16.0 * (mesh // 2 + 1) * mesh * mesh * (world - 1) / world ** 2
+        t_roof += nvl / 770e9
+    roofline["step_roofline_ms"] = t_roof * 1e3
+    roofline["step_frac"] = t_roof * 1e3 / ms_step
+
+    # e2e: host buffers through the C ABI: upload -> step -> download, every step
+    e2e = None
+    try:
+        nl = dev.local_count
+        hx, hv = pinned_empty((nl, 3)), pinned_empty((nl, 3))
+        dev.download(hx, hv)
+        barrier()
+        tE = []
+        for it in range(1 + args.e2e_steps):
+            barrier()
+            t0 = time.perf_counter()
+            dev.upload(hx, hv, m)
+            sc = scalars(state["t"], state["dt"])
+            st = dev.step_comoving(state["dt"], *sc)
+            if world > 1:
+                dev.reduce_stats(st)
+                dev2 = dev.local_count
+                if dev2 != nl:       # migration changed the local count: re-size the host buffers
+                    pinned_free(hx), pinned_free(hv)
+                    nl = dev2
+                    hx, hv = pinned_empty((nl, 3)), pinned_empty((nl, 3))
+            dev.download(hx, hv)
+            torch.cuda.synchronize()
+            tE.append(max_over_ranks(time.perf_counter() - t0))
+            launches_e = st.kernel_launches
+        sec = sum(tE[1:]) / len(tE[1:])
+        e2e = {"value": n ** 3 / sec, "unit": UNIT, "h2d_bytes_per_step": int(2 * nl * 3 * 8 * world),
+               "d2h_bytes_per_step": int(2 * nl * 3 * 8 * world + 32), "ms_per_step": sec * 1e3,
+               "steps": len(tE) - 1, "api": "nnpm_upload_particles -> nnpm_step_comoving -> nnpm_download_particles (pinned host buffers)"}
+        pinned_free(hx), pinned_free(hv)
+    except Exception as ex:  # report, do not hide
+        e2e = {"value": None, "unit": UNIT, "error": repr(ex)}
+    dev.close()
+
+    cpu = None
+    if rank == 0 and args.cpu_sample:
+        cs = args.cpu_sample
+        val, sec = run_cpu(cs, cs, 2, 1, 1)
+        cpu = {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"2 comoving steps of a {cs}^3 / {cs}^3 sample of the same synthetic workload ({sec:.2f} s/step); "
+                         "C restatement of ParticleMesh.jl + pocketfft, 1 thread like the reference (Readme.md:53); "
+                         "the Julia reference itself cannot run in this image"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

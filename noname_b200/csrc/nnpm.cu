@@ -74,7 +74,7 @@ struct nnpm_ctx {
   // cuFFT
   cufftHandle plan2f, plan2b, planz, plan3f, plan3b;
   bool have2, havez, have3;
-  int opt_fft3d, opt_zfused, opt_tile_deposit, opt_tile_push;
+  int opt_fft3d, opt_zfused, opt_tile_deposit, opt_tile_push, opt_push_minb;
   void* fftwork;
   size_t fftwork_bytes;
 
@@ -91,6 +91,9 @@ struct nnpm_ctx {
   double* mig_recv;
   i64 mig_cap;
   uint32_t* mig_holes;
+  uint32_t* mig_lo;
+  double* ghost_rx;
+  double* red_buf;
   i64* mig_cnt;    // device counters
   i64* h_cnt;      // pinned
   i64 last_migrated;
@@ -259,6 +262,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   if (cfg->rank == 3 && N3 < 2) return fail(ctx, NNPM_ERR_ARG, "rank 3 needs ngrid[2] >= 2");
   const int P = cfg->nranks < 1 ? 1 : cfg->nranks;
   if (cfg->rank_id < 0 || cfg->rank_id >= P) return fail(ctx, NNPM_ERR_ARG, "rank_id out of range");
+  if (P > 64) return fail(ctx, NNPM_ERR_ARG, "nranks must be <= 64");
   if (P > 1 && (cfg->rank != 3 || N3 % P || N2 % P || N3 / P < 4))
     return fail(ctx, NNPM_ERR_ARG, "nranks>1 needs rank 3, N3 %% P == 0, N2 %% P == 0 and N3/P >= 4");
   if (cfg->npart_total < 0 || cfg->npart_total >= (1ll << 32))
@@ -302,13 +306,14 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->stage = nullptr; c->stage_elems = 0;
   c->hist = c->bsum = c->bsum2 = c->skey = c->srnk = nullptr;
   c->have2 = c->havez = c->have3 = false;
-  c->opt_fft3d = 0; c->opt_zfused = 1; c->opt_tile_deposit = 1; c->opt_tile_push = 1;
+  c->opt_fft3d = 0; c->opt_zfused = 1; c->opt_tile_deposit = 1; c->opt_tile_push = 1; c->opt_push_minb = 3;
   c->fftwork = nullptr; c->fftwork_bytes = 0;
   c->step_count = 0; c->launches = 0;
   c->nccl = nullptr; c->comm = nullptr;
   c->mig_send = c->mig_recv = nullptr; c->mig_cap = 0; c->mig_holes = nullptr; c->mig_cnt = nullptr; c->h_cnt = nullptr;
   c->last_migrated = 0;
   c->pk_buf = nullptr;
+  c->mig_lo = nullptr; c->ghost_rx = nullptr; c->red_buf = nullptr;
   c->np = 0; c->m = 0.0; c->ids_dirty = false; c->field_state = 0;
   c->own_stream = false;
   c->h_red = nullptr;
@@ -340,7 +345,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   CKB(CKR(dalloc(c, &c->ids, (size_t)c->cap)));
   CKB(CKR(dalloc(c, &c->d_red, 8)));
   CKB(CK(cudaHostAlloc((void**)&c->h_red, 8 * sizeof(i64), cudaHostAllocDefault)));
-  CKB(CK(cudaHostAlloc((void**)&c->h_cnt, 64 * sizeof(i64), cudaHostAllocDefault)));
+  CKB(CK(cudaHostAlloc((void**)&c->h_cnt, 24 * 64 * sizeof(i64), cudaHostAllocDefault)));
   {
     std::vector<double> t1, t2, t3;
     sin2_table(t1, N1, false, false);
@@ -902,8 +907,11 @@ template <int RANK, int INTERP>
 static void launch_push(nnpm_ctx* ctx, bool comoving, const PushParams& pp) {
   const i64 np = ctx->np;
   u64* viol = (u64*)(ctx->d_red + 3);
-  if (comoving) k_push<RANK, INTERP, true><<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->pp, np, ctx->g, ctx->mesh, pp, ctx->d_red, viol);
-  else k_push<RANK, INTERP, false><<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->pp, np, ctx->g, ctx->mesh, pp, ctx->d_red, viol);
+#define LP(CM, MB) k_push<RANK, INTERP, CM, MB><<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->pp, np, ctx->g, ctx->mesh, pp, ctx->d_red, viol)
+  if (ctx->opt_push_minb >= 4) { if (comoving) LP(true, 4); else LP(false, 4); }
+  else if (ctx->opt_push_minb == 3) { if (comoving) LP(true, 3); else LP(false, 3); }
+  else { if (comoving) LP(true, 2); else LP(false, 2); }
+#undef LP
 }
 
 static int do_step(nnpm_ctx* ctx, bool comoving, double dt, double a_d1, double a_k, double adot_k, double a_d2,
@@ -1009,6 +1017,7 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   } else if (!strcmp(name, "zfused")) ctx->opt_zfused = v;
   else if (!strcmp(name, "tile_deposit")) ctx->opt_tile_deposit = v;
   else if (!strcmp(name, "tile_push")) ctx->opt_tile_push = v;
+  else if (!strcmp(name, "push_minb")) ctx->opt_push_minb = v;
   else return fail(ctx, NNPM_ERR_ARG, "unknown option '%s'", name);
   return NNPM_OK;
 }

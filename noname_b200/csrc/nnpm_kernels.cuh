@@ -52,6 +52,30 @@ __device__ __forceinline__ i64 wrap_idx(i64 z, i64 N) {
   return z;
 }
 
+
+// 32-bit variants for the hot kernels (N < 2^30; in-plane offsets rowp*N2 < 2^31):
+// fl = floor(x*N) kept as a double for the offset, index from F2I.
+__device__ __forceinline__ void cell_of32(double x, double fN, int N, int& i0, int& ip, double& d) {
+  const double t = __dmul_rn(x, fN);
+  const double fl = floor(t);
+  d = __dadd_rn(__dsub_rn(t, fl + 1.0), 1.0);
+  int z = __double2int_rz(fl);
+  if (z >= N) z -= N;   // x == 1.0 (make_periodic leaves it, ParticleMesh.jl:411) -> index N -> 0
+  if (z < 0) z += N;
+  if ((unsigned)z >= (unsigned)N) z = ((z % N) + N) % N;  // strays (never taken after make_periodic)
+  i0 = z;
+  ip = (z == N - 1) ? 0 : z + 1;
+}
+__device__ __forceinline__ int local_plane32(int k, const Geom& g) {
+  int d = k - (int)g.kz0;
+  if (g.glo) {
+    if (d >= (int)g.nzl + 3) d -= (int)g.N3;
+    if (d < -2) d += (int)g.N3;
+    if (d < -2 || d >= (int)g.nzl + 3) return -1;
+  }
+  return d + g.glo;
+}
+
 // local plane of global plane k: p = k - kz0 + glo, unwrapped periodically into the slab's
 // ghost window.  Returns -1 when the plane is not held by this rank.
 __device__ __forceinline__ int local_plane(i64 k, const Geom& g) {
@@ -69,35 +93,29 @@ __device__ __forceinline__ i64 ord_encode(double v) {  // monotone double -> int
   return k >= 0 ? k : (k ^ 0x7FFFFFFFFFFFFFFFLL);
 }
 
-// warp+block max of three values, then one atomicMax each per block
-__device__ __forceinline__ void block_max3(double a, double b, double c, i64* out) {
-  __shared__ double s[3][32];
+// max of three values over the block, then one global atomicMax each.  The doubles are compared
+// through their monotone int64 encoding so the warp step is two 32-bit REDUX ops per value
+// (hi word signed, then lo word unsigned among the lanes holding the max hi word).
+__device__ __forceinline__ i64 warp_max_key(i64 key) {
   const unsigned full = 0xffffffffu;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a = fmax(a, __shfl_xor_sync(full, a, o));
-    b = fmax(b, __shfl_xor_sync(full, b, o));
-    c = fmax(c, __shfl_xor_sync(full, c, o));
-  }
-  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
-  if (l == 0) { s[0][w] = a; s[1][w] = b; s[2][w] = c; }
+  const int hi = (int)(key >> 32);
+  const int mhi = __reduce_max_sync(full, hi);
+  const unsigned lo = (hi == mhi) ? (unsigned)key : 0u;
+  const unsigned mlo = __reduce_max_sync(full, lo);
+  return ((i64)mhi << 32) | (i64)mlo;
+}
+__device__ __forceinline__ void block_max3(double a, double b, double c, i64* out) {
+  __shared__ i64 s[3];
+  if (threadIdx.x < 3) s[threadIdx.x] = (i64)0x8000000000000000ull;
   __syncthreads();
-  if (w == 0) {
-    a = l < nw ? s[0][l] : -INFINITY;
-    b = l < nw ? s[1][l] : -INFINITY;
-    c = l < nw ? s[2][l] : -INFINITY;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a = fmax(a, __shfl_xor_sync(full, a, o));
-      b = fmax(b, __shfl_xor_sync(full, b, o));
-      c = fmax(c, __shfl_xor_sync(full, c, o));
-    }
-    if (l == 0) {
-      atomicMax(&out[0], ord_encode(a));
-      atomicMax(&out[1], ord_encode(b));
-      atomicMax(&out[2], ord_encode(c));
-    }
+  const i64 ka = warp_max_key(ord_encode(a)), kb = warp_max_key(ord_encode(b)), kc = warp_max_key(ord_encode(c));
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&s[0], ka);
+    atomicMax(&s[1], kb);
+    atomicMax(&s[2], kc);
   }
+  __syncthreads();
+  if (threadIdx.x < 3) atomicMax(&out[threadIdx.x], s[threadIdx.x]);
 }
 
 struct PartPtrs {
@@ -205,40 +223,38 @@ k_deposit(PartPtrs p, i64 np, double c0, Geom g, double* __restrict__ mesh, doub
     return;
   }
 
-  i64 i, ip, j, jp;
+  int i, ip, j, jp;
   double dx, dy;
-  cell_of(x0, g.fN1, g.N1, i, ip, dx);
-  cell_of(x1, g.fN2, g.N2, j, jp, dy);
+  cell_of32(x0, g.fN1, (int)g.N1, i, ip, dx);
+  cell_of32(x1, g.fN2, (int)g.N2, j, jp, dy);
   const double mm = FIXED ? 1.0 : m;
   const double wx0 = __dmul_rn(mm, __dsub_rn(1.0, dx)), wx1 = __dmul_rn(mm, dx);
   const double ody = __dsub_rn(1.0, dy);
+  const unsigned r0 = (unsigned)((int)g.rowp * j), r1 = (unsigned)((int)g.rowp * jp);
   if (RANK == 2) {  // :376-379
-    double* base = mesh + g.plane * g.glo;
-    (void)base;
-    i64 off = g.plane * g.glo;
-    add(off + i + g.rowp * j, __dmul_rn(wx0, ody));
-    add(off + i + g.rowp * jp, __dmul_rn(wx0, dy));
-    add(off + ip + g.rowp * j, __dmul_rn(wx1, ody));
-    add(off + ip + g.rowp * jp, __dmul_rn(wx1, dy));
+    const i64 off = g.plane * g.glo;
+    add(off + (r0 + i), __dmul_rn(wx0, ody));
+    add(off + (r1 + i), __dmul_rn(wx0, dy));
+    add(off + (r0 + ip), __dmul_rn(wx1, ody));
+    add(off + (r1 + ip), __dmul_rn(wx1, dy));
     return;
   }
-  i64 k, kp;
+  int k, kp;
   double dz;
-  cell_of(x2, g.fN3, g.N3, k, kp, dz);
-  int p0 = local_plane(k, g), p1 = local_plane(kp, g);
-  if (p0 < 0 || p1 < 0) { atomicAdd(viol, 1ull); return; }
+  cell_of32(x2, g.fN3, (int)g.N3, k, kp, dz);
+  const int p0 = local_plane32(k, g), p1 = local_plane32(kp, g);
+  if ((p0 | p1) < 0) { atomicAdd(viol, 1ull); return; }
   const double odz = __dsub_rn(1.0, dz);
-  const i64 r0 = g.rowp * j, r1 = g.rowp * jp;
-  const i64 o0 = g.plane * p0, o1 = g.plane * p1;
+  const i64 o0 = g.plane * (i64)p0, o1 = g.plane * (i64)p1;
   // :395-402
-  add(o0 + r0 + i, __dmul_rn(__dmul_rn(wx0, ody), odz));
-  add(o0 + r1 + i, __dmul_rn(__dmul_rn(wx0, dy), odz));
-  add(o0 + r0 + ip, __dmul_rn(__dmul_rn(wx1, ody), odz));
-  add(o0 + r1 + ip, __dmul_rn(__dmul_rn(wx1, dy), odz));
-  add(o1 + r0 + i, __dmul_rn(__dmul_rn(wx0, ody), dz));
-  add(o1 + r1 + i, __dmul_rn(__dmul_rn(wx0, dy), dz));
-  add(o1 + r0 + ip, __dmul_rn(__dmul_rn(wx1, ody), dz));
-  add(o1 + r1 + ip, __dmul_rn(__dmul_rn(wx1, dy), dz));
+  add(o0 + (r0 + i), __dmul_rn(__dmul_rn(wx0, ody), odz));
+  add(o0 + (r1 + i), __dmul_rn(__dmul_rn(wx0, dy), odz));
+  add(o0 + (r0 + ip), __dmul_rn(__dmul_rn(wx1, ody), odz));
+  add(o0 + (r1 + ip), __dmul_rn(__dmul_rn(wx1, dy), odz));
+  add(o1 + (r0 + i), __dmul_rn(__dmul_rn(wx0, ody), dz));
+  add(o1 + (r1 + i), __dmul_rn(__dmul_rn(wx0, dy), dz));
+  add(o1 + (r0 + ip), __dmul_rn(__dmul_rn(wx1, ody), dz));
+  add(o1 + (r1 + ip), __dmul_rn(__dmul_rn(wx1, dy), dz));
 }
 
 // int64 fixed-point accumulations -> f64 density, in place: rho = m * (Q * 2^-B)
@@ -418,8 +434,8 @@ struct PushParams {
 
 #define PHI(ii, jj, pp) __ldg(phi + (ii) + g.rowp * (jj) + g.plane * (i64)(pp))
 
-template <int RANK, int INTERP, bool COMOVING>
-__global__ void __launch_bounds__(256)
+template <int RANK, int INTERP, bool COMOVING, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_push(PartPtrs p, i64 np, Geom g, const double* __restrict__ phi, PushParams pp, i64* __restrict__ red,
        u64* __restrict__ viol) {
   i64 n = blockIdx.x * (i64)blockDim.x + threadIdx.x;
@@ -452,102 +468,108 @@ k_push(PartPtrs p, i64 np, Geom g, const double* __restrict__ phi, PushParams pp
         if (RANK == 3) pa[2] = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(PHI(i, j, pu), PHI(i, j, pd)), 0.5));
       }
     } else {
-      i64 ia[4], ja[4];
+      const int N1 = (int)g.N1, N2 = (int)g.N2, rowp = (int)g.rowp;
+      int ia[4], ro[4];  // i-1, i, ip, ip+1 ; row offsets rowp*(j-1, j, jp, jp+1)
       double dx, dy, dz = 0.0;
-      cell_of(x[0], g.fN1, g.N1, ia[1], ia[2], dx);
-      cell_of(x[1], g.fN2, g.N2, ja[1], ja[2], dy);
-      ia[0] = (ia[1] == 0) ? g.N1 - 1 : ia[1] - 1;
-      ia[3] = (ia[2] == g.N1 - 1) ? 0 : ia[2] + 1;
-      ja[0] = (ja[1] == 0) ? g.N2 - 1 : ja[1] - 1;
-      ja[3] = (ja[2] == g.N2 - 1) ? 0 : ja[2] + 1;
+      {
+        int j1, j2;
+        cell_of32(x[0], g.fN1, N1, ia[1], ia[2], dx);
+        cell_of32(x[1], g.fN2, N2, j1, j2, dy);
+        ia[0] = (ia[1] == 0) ? N1 - 1 : ia[1] - 1;
+        ia[3] = (ia[2] == N1 - 1) ? 0 : ia[2] + 1;
+        ro[0] = rowp * ((j1 == 0) ? N2 - 1 : j1 - 1);
+        ro[1] = rowp * j1;
+        ro[2] = rowp * j2;
+        ro[3] = rowp * ((j2 == N2 - 1) ? 0 : j2 + 1);
+      }
       const double odx = __dsub_rn(1.0, dx), ody = __dsub_rn(1.0, dy);
       const double wxs[2] = {odx, dx}, wys[2] = {ody, dy};
+      // -(N1*((hi-lo)/2)) == (hi-lo) * (-N1/2) bit for bit: the halving and the negation are exact
+      const double gfac = -0.5 * g.fN1;
       if (RANK == 2) {
-        const int pc = g.glo;
+        const double* P = phi + g.plane * (i64)g.glo;
         double c[2][4], ylo[2], yhi[2];
 #pragma unroll
         for (int b = 0; b < 2; b++)
 #pragma unroll
-          for (int a = 0; a < 4; a++) c[b][a] = PHI(ia[a], ja[1 + b], pc);
+          for (int a = 0; a < 4; a++) c[b][a] = __ldg(P + (unsigned)(ro[1 + b] + ia[a]));
 #pragma unroll
-        for (int a = 0; a < 2; a++) { ylo[a] = PHI(ia[1 + a], ja[0], pc); yhi[a] = PHI(ia[1 + a], ja[3], pc); }
-        double ax[2][2], ay[2][2];
-#pragma unroll
-        for (int b = 0; b < 2; b++)
-#pragma unroll
-          for (int a = 0; a < 2; a++) {
-            ax[b][a] = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(c[b][a + 2], c[b][a]), 0.5));
-            double hi = b ? yhi[a] : c[1][a + 1], lo = b ? c[0][a + 1] : ylo[a];
-            ay[b][a] = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(hi, lo), 0.5));
-          }
+        for (int a = 0; a < 2; a++) { ylo[a] = __ldg(P + (unsigned)(ro[0] + ia[1 + a])); yhi[a] = __ldg(P + (unsigned)(ro[3] + ia[1 + a])); }
         // order :687-688  (i,j) (ip,j) (i,jp) (ip,jp)
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-        for (int m = 0; m < 2; m++) {
-          double s = 0.0;
-#pragma unroll
-          for (int t = 0; t < 4; t++) {
-            int a = t & 1, b = t >> 1;
-            double val = m ? ay[b][a] : ax[b][a];
-            double term = __dmul_rn(__dmul_rn(val, wxs[a]), wys[b]);
-            s = t ? __dadd_rn(s, term) : term;
-          }
-          pa[m] = s;
+        for (int t = 0; t < 4; t++) {
+          const int a = t & 1, b = t >> 1;
+          const double gx = __dmul_rn(__dsub_rn(c[b][a + 2], c[b][a]), gfac);
+          const double hi = b ? yhi[a] : c[1][a + 1], lo = b ? c[0][a + 1] : ylo[a];
+          const double gy = __dmul_rn(__dsub_rn(hi, lo), gfac);
+          const double tx = __dmul_rn(__dmul_rn(gx, wxs[a]), wys[b]);
+          const double ty = __dmul_rn(__dmul_rn(gy, wxs[a]), wys[b]);
+          s0 = t ? __dadd_rn(s0, tx) : tx;
+          s1 = t ? __dadd_rn(s1, ty) : ty;
         }
+        pa[0] = s0; pa[1] = s1;
       } else {
-        i64 k, kp;
-        if (pp.bugz) {
+        const int N3 = (int)g.N3;
+        int k, kp;
+        if (pp.bugz) {  // literal :706-708
           i64 k1 = (i64)floor(x[2]) * g.N3 + 1;
           dz = __dadd_rn(__dsub_rn(__dmul_rn(x[2], g.fN3), (double)k1), 1.0);
-          k = wrap_idx(k1 - 1, g.N3);
-          kp = (k1 == g.N3) ? 0 : wrap_idx(k1, g.N3);
+          k = (int)wrap_idx(k1 - 1, g.N3);
+          kp = (k1 == g.N3) ? 0 : (int)wrap_idx(k1, g.N3);
         } else {
-          cell_of(x[2], g.fN3, g.N3, k, kp, dz);
+          cell_of32(x[2], g.fN3, N3, k, kp, dz);
         }
-        i64 km1 = (k == 0) ? g.N3 - 1 : k - 1, kp2 = (kp == g.N3 - 1) ? 0 : kp + 1;
-        int pl[4] = {local_plane(km1, g), local_plane(k, g), local_plane(kp, g), local_plane(kp2, g)};
-        ok = pl[0] >= 0 && pl[1] >= 0 && pl[2] >= 0 && pl[3] >= 0;
+        const int km1 = (k == 0) ? N3 - 1 : k - 1, kp2 = (kp == N3 - 1) ? 0 : kp + 1;
+        const int pl[4] = {local_plane32(km1, g), local_plane32(k, g), local_plane32(kp, g), local_plane32(kp2, g)};
+        ok = (pl[0] | pl[1] | pl[2] | pl[3]) >= 0;
         if (ok) {
+          const double* P0 = phi + g.plane * (i64)pl[0];
+          const double* P1 = phi + g.plane * (i64)pl[1];
+          const double* P2 = phi + g.plane * (i64)pl[2];
+          const double* P3 = phi + g.plane * (i64)pl[3];
           const double odz = __dsub_rn(1.0, dz);
           const double wzs[2] = {odz, dz};
           double c[2][2][4], ylo[2][2], yhi[2][2], zlo[2][2], zhi[2][2];
 #pragma unroll
-          for (int cz = 0; cz < 2; cz++)
+          for (int b = 0; b < 2; b++)
 #pragma unroll
-            for (int b = 0; b < 2; b++)
-#pragma unroll
-              for (int a = 0; a < 4; a++) c[cz][b][a] = PHI(ia[a], ja[1 + b], pl[1 + cz]);
-#pragma unroll
-          for (int cz = 0; cz < 2; cz++)
-#pragma unroll
-            for (int a = 0; a < 2; a++) {
-              ylo[cz][a] = PHI(ia[1 + a], ja[0], pl[1 + cz]);
-              yhi[cz][a] = PHI(ia[1 + a], ja[3], pl[1 + cz]);
+            for (int a = 0; a < 4; a++) {
+              c[0][b][a] = __ldg(P1 + (unsigned)(ro[1 + b] + ia[a]));
+              c[1][b][a] = __ldg(P2 + (unsigned)(ro[1 + b] + ia[a]));
             }
+#pragma unroll
+          for (int a = 0; a < 2; a++) {
+            ylo[0][a] = __ldg(P1 + (unsigned)(ro[0] + ia[1 + a]));
+            yhi[0][a] = __ldg(P1 + (unsigned)(ro[3] + ia[1 + a]));
+            ylo[1][a] = __ldg(P2 + (unsigned)(ro[0] + ia[1 + a]));
+            yhi[1][a] = __ldg(P2 + (unsigned)(ro[3] + ia[1 + a]));
+          }
 #pragma unroll
           for (int b = 0; b < 2; b++)
 #pragma unroll
             for (int a = 0; a < 2; a++) {
-              zlo[b][a] = PHI(ia[1 + a], ja[1 + b], pl[0]);
-              zhi[b][a] = PHI(ia[1 + a], ja[1 + b], pl[3]);
+              zlo[b][a] = __ldg(P0 + (unsigned)(ro[1 + b] + ia[1 + a]));
+              zhi[b][a] = __ldg(P3 + (unsigned)(ro[1 + b] + ia[1 + a]));
             }
           // order :710-717: (i,j,k)(ip,j,k)(i,jp,k)(ip,jp,k) then the kp four
-          double s[3] = {0.0, 0.0, 0.0};
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
           for (int t = 0; t < 8; t++) {
             const int a = t & 1, b = (t >> 1) & 1, cz = t >> 2;
-            double gx = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(c[cz][b][a + 2], c[cz][b][a]), 0.5));
-            double yh = b ? yhi[cz][a] : c[cz][1][a + 1], yl = b ? c[cz][0][a + 1] : ylo[cz][a];
-            double gy = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(yh, yl), 0.5));
-            double zh = cz ? zhi[b][a] : c[1][b][a + 1], zl = cz ? c[0][b][a + 1] : zlo[b][a];
-            double gz = -__dmul_rn(g.fN1, __dmul_rn(__dsub_rn(zh, zl), 0.5));
-            double tx = __dmul_rn(__dmul_rn(__dmul_rn(gx, wxs[a]), wys[b]), wzs[cz]);
-            double ty = __dmul_rn(__dmul_rn(__dmul_rn(gy, wxs[a]), wys[b]), wzs[cz]);
-            double tz = __dmul_rn(__dmul_rn(__dmul_rn(gz, wxs[a]), wys[b]), wzs[cz]);
-            s[0] = t ? __dadd_rn(s[0], tx) : tx;
-            s[1] = t ? __dadd_rn(s[1], ty) : ty;
-            s[2] = t ? __dadd_rn(s[2], tz) : tz;
+            const double gx = __dmul_rn(__dsub_rn(c[cz][b][a + 2], c[cz][b][a]), gfac);
+            const double yh = b ? yhi[cz][a] : c[cz][1][a + 1], yl = b ? c[cz][0][a + 1] : ylo[cz][a];
+            const double gy = __dmul_rn(__dsub_rn(yh, yl), gfac);
+            const double zh = cz ? zhi[b][a] : c[1][b][a + 1], zl = cz ? c[0][b][a + 1] : zlo[b][a];
+            const double gz = __dmul_rn(__dsub_rn(zh, zl), gfac);
+            const double tx = __dmul_rn(__dmul_rn(__dmul_rn(gx, wxs[a]), wys[b]), wzs[cz]);
+            const double ty = __dmul_rn(__dmul_rn(__dmul_rn(gy, wxs[a]), wys[b]), wzs[cz]);
+            const double tz = __dmul_rn(__dmul_rn(__dmul_rn(gz, wxs[a]), wys[b]), wzs[cz]);
+            s0 = t ? __dadd_rn(s0, tx) : tx;
+            s1 = t ? __dadd_rn(s1, ty) : ty;
+            s2 = t ? __dadd_rn(s2, tz) : tz;
           }
-          pa[0] = s[0]; pa[1] = s[1]; pa[2] = s[2];
+          pa[0] = s0; pa[1] = s1; pa[2] = s2;
         }
       }
     }
