@@ -94,6 +94,7 @@ typedef struct {
   int64_t n_halo_violations; /* particles whose half-drift left the slab's ghost region (must be 0) */
   int64_t npart_local;/* particles on this rank after the step */
   int64_t n_migrated; /* particles this rank sent away this step */
+  int64_t n_untiled;  /* particles the tiled kernels handed to the global-memory path (strayed > 1 cell from their tile since the sort) */
   float ms[NNPM_MS_COUNT]; /* CUDA-event milliseconds per phase (timing=1), else 0 */
   int32_t kernel_launches; /* kernels + cuFFT execs + NCCL ops launched by this call */
   int32_t pad;

@@ -53,12 +53,13 @@ class Stats(C.Structure):
     _fields_ = [
         ("max_abs_v", C.c_double), ("max_v", C.c_double), ("max_pa", C.c_double),
         ("n_halo_violations", C.c_int64), ("npart_local", C.c_int64), ("n_migrated", C.c_int64),
+        ("n_untiled", C.c_int64),
         ("ms", C.c_float * NNPM_MS_COUNT), ("kernel_launches", C.c_int32), ("pad", C.c_int32),
     ]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k in ("max_abs_v", "max_v", "max_pa", "n_halo_violations",
-                                           "npart_local", "n_migrated", "kernel_launches")}
+                                           "npart_local", "n_migrated", "n_untiled", "kernel_launches")}
         d["ms"] = {n: float(self.ms[i]) for i, n in enumerate(MS_NAMES)}
         return d
 

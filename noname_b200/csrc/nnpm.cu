@@ -66,6 +66,8 @@ struct nnpm_ctx {
   uint32_t *hist, *bsum, *bsum2, *skey, *srnk;
   TileGeom tg;
   i64 ntiles;
+  i64 sorted_np;     // particles [0, sorted_np) are covered by the tile offsets in `hist` (0 = not sorted)
+  i64 last_untiled;  // stragglers of the last tiled push
 
   // reductions
   i64* d_red;  // [0..2] encoded maxima, [3] violation counter
@@ -306,7 +308,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->stage = nullptr; c->stage_elems = 0;
   c->hist = c->bsum = c->bsum2 = c->skey = c->srnk = nullptr;
   c->have2 = c->havez = c->have3 = false;
-  c->opt_fft3d = 0; c->opt_zfused = 1; c->opt_tile_deposit = 1; c->opt_tile_push = 1; c->opt_push_minb = 3;
+  c->opt_fft3d = 0; c->opt_zfused = 1; c->opt_tile_deposit = 1; c->opt_tile_push = 1; c->opt_push_minb = 2;
   c->fftwork = nullptr; c->fftwork_bytes = 0;
   c->step_count = 0; c->launches = 0;
   c->nccl = nullptr; c->comm = nullptr;
@@ -360,10 +362,15 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   }
   CKB(CKR(make_plans(c)));
   for (int i = 0; i < 16; i++) CKB(CK(cudaEventCreate(&c->ev[i])));
-  c->tg.ntx = (N1 + NNPM_TILE - 1) / NNPM_TILE;
-  c->tg.nty = (N2 + NNPM_TILE - 1) / NNPM_TILE;
-  c->tg.ntz = (g.nzl + NNPM_TILE - 1) / NNPM_TILE;
-  c->ntiles = c->tg.ntx * c->tg.nty * c->tg.ntz;
+  c->tg.tx = (int)(N1 < NNPM_TX ? N1 : NNPM_TX);
+  c->tg.ty = (int)(N2 < NNPM_TY ? N2 : NNPM_TY);
+  c->tg.tz = c->R == 3 ? (int)(g.nzl < NNPM_TZ ? g.nzl : NNPM_TZ) : 1;
+  c->tg.ntx = (int)((N1 + c->tg.tx - 1) / c->tg.tx);
+  c->tg.nty = (int)((N2 + c->tg.ty - 1) / c->tg.ty);
+  c->tg.ntz = (int)((g.nzl + c->tg.tz - 1) / c->tg.tz);
+  c->ntiles = (i64)c->tg.ntx * c->tg.nty * c->tg.ntz;
+  c->sorted_np = 0;
+  c->last_untiled = 0;
   CKB(CK(cudaMemsetAsync(c->mesh, 0, (size_t)g.plane * g.nplanes * 8, c->st)));
   CKB(CK(cudaStreamSynchronize(c->st)));
 #undef CKB
@@ -456,6 +463,7 @@ extern "C" int nnpm_upload_particles(nnpm_ctx* ctx, const double* x_aos, const d
   if (n) { k_iota_u32<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->ids, n, (u64)first_id); LAUNCHED(ctx); KCHECK(); }
   ctx->np = n;
   ctx->m = m;
+  ctx->sorted_np = 0;
   ctx->ids_dirty = false;
   ctx->acc_valid = ctx->pa_valid = false;
   CK(cudaStreamSynchronize(ctx->st));
@@ -502,6 +510,7 @@ extern "C" int nnpm_download_particles(nnpm_ctx* ctx, double* x_aos, double* v_a
     CK(cudaMemcpyAsync(ctx->skey, dest, (size_t)np * 4, cudaMemcpyDeviceToDevice, ctx->st));
     CKR(permute_all(ctx, ctx->skey));
     ctx->ids_dirty = false;
+    ctx->sorted_np = 0;
   }
   if (x_aos) CKR(download_aos(ctx, x_aos, ctx->pp.x[0], ctx->pp.x[1], ctx->pp.x[2], np));
   if (v_aos) CKR(download_aos(ctx, v_aos, ctx->pp.v[0], ctx->pp.v[1], ctx->pp.v[2], np));
@@ -572,6 +581,7 @@ extern "C" int nnpm_init_synthetic(nnpm_ctx* ctx, int kind, const int64_t pdims[
   }
   ctx->np = per;
   ctx->m = m;
+  ctx->sorted_np = 0;
   ctx->ids_dirty = ctx->P > 1;
   ctx->acc_valid = ctx->pa_valid = false;
   CK(cudaStreamSynchronize(ctx->st));
@@ -621,6 +631,7 @@ extern "C" int nnpm_sort(nnpm_ctx* ctx) {
   CKR(permute_all(ctx, ctx->skey));
   ctx->ids_dirty = true;
   ctx->pa_valid = false;
+  ctx->sorted_np = np;
   return NNPM_OK;
 }
 
@@ -893,7 +904,7 @@ extern "C" int nnpm_set_field(nnpm_ctx* ctx, int which, const double* host_in) {
 // ------------------------------------------------------------------------------------------
 __global__ void k_reset_red(i64* red) {
   if (threadIdx.x < 3) red[threadIdx.x] = (i64)0x8000000000000000ull;
-  if (threadIdx.x == 3) red[3] = 0;
+  if (threadIdx.x == 3 || threadIdx.x == 4) red[threadIdx.x] = 0;
 }
 
 static inline double ord_decode(i64 k) {
@@ -904,14 +915,40 @@ static inline double ord_decode(i64 k) {
 }
 
 template <int RANK, int INTERP>
-static void launch_push(nnpm_ctx* ctx, bool comoving, const PushParams& pp) {
+static int launch_push(nnpm_ctx* ctx, bool comoving, const PushParams& pp) {
   const i64 np = ctx->np;
   u64* viol = (u64*)(ctx->d_red + 3);
-#define LP(CM, MB) k_push<RANK, INTERP, CM, MB><<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->pp, np, ctx->g, ctx->mesh, pp, ctx->d_red, viol)
-  if (ctx->opt_push_minb >= 4) { if (comoving) LP(true, 4); else LP(false, 4); }
-  else if (ctx->opt_push_minb == 3) { if (comoving) LP(true, 3); else LP(false, 3); }
-  else { if (comoving) LP(true, 2); else LP(false, 2); }
+  u64* slow_count = (u64*)(ctx->d_red + 4);
+  auto global_push = [&](i64 base, i64 count, const uint32_t* list, unsigned grid) {
+#define LP(CM, MB) k_push<RANK, INTERP, CM, MB><<<grid, 256, 0, ctx->st>>>(ctx->pp, base, count, list, slow_count, ctx->g, ctx->mesh, pp, ctx->d_red, viol)
+    if (ctx->opt_push_minb >= 4) { if (comoving) LP(true, 4); else LP(false, 4); }
+    else if (ctx->opt_push_minb == 3) { if (comoving) LP(true, 3); else LP(false, 3); }
+    else { if (comoving) LP(true, 2); else LP(false, 2); }
 #undef LP
+    LAUNCHED(ctx);
+  };
+  const bool tiled = INTERP == 1 && ctx->opt_tile_push && ctx->sorted_np > 0 && !ctx->cfg.bugcompat_interp_z;
+  if (!tiled) {
+    global_push(0, np, nullptr, nblk(np, 256));
+    KCHECK();
+    return NNPM_OK;
+  }
+  const size_t smem = (size_t)NNPM_BX * NNPM_BY * (RANK == 3 ? NNPM_BZ : 1) * sizeof(double);
+  const i64 covered = ctx->sorted_np < np ? ctx->sorted_np : np;
+#define LT(CM, MB)                                                                                                  \
+  do {                                                                                                              \
+    CK(cudaFuncSetAttribute(k_push_tile<RANK, CM, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    k_push_tile<RANK, CM, MB><<<(unsigned)ctx->ntiles, 256, smem, ctx->st>>>(ctx->pp, covered, ctx->g, ctx->tg, ctx->hist, \
+                                                                             ctx->mesh, pp, ctx->d_red, ctx->srnk, slow_count); \
+  } while (0)
+  if (ctx->opt_push_minb >= 3) { if (comoving) LT(true, 3); else LT(false, 3); }
+  else { if (comoving) LT(true, 2); else LT(false, 2); }
+#undef LT
+  LAUNCHED(ctx);
+  global_push(0, 0, ctx->srnk, 148 * 4);                       // stragglers (device-side count)
+  if (np > covered) global_push(covered, np - covered, nullptr, nblk(np - covered, 256));  // arrivals since the sort
+  KCHECK();
+  return NNPM_OK;
 }
 
 static int do_step(nnpm_ctx* ctx, bool comoving, double dt, double a_d1, double a_k, double adot_k, double a_d2,
@@ -920,7 +957,9 @@ static int do_step(nnpm_ctx* ctx, bool comoving, double dt, double a_d1, double 
   const bool tim = ctx->cfg.timing != 0;
   const int launches0 = ctx->launches;
   cudaEvent_t* ev = ctx->ev;
-  const bool do_sort = ctx->cfg.sort_every > 0 && (ctx->step_count % ctx->cfg.sort_every) == 0;
+  // counting sort on the configured cadence, or early when > 1/16 of the particles left their tile box
+  const bool do_sort = ctx->cfg.sort_every > 0 && ctx->np > 0 &&
+                       ((ctx->step_count % ctx->cfg.sort_every) == 0 || ctx->last_untiled * 16 > ctx->np);
   if (tim) CK(cudaEventRecord(ev[0], ctx->st));
   if (do_sort) CKR(nnpm_sort(ctx));
   if (tim) CK(cudaEventRecord(ev[1], ctx->st));
@@ -948,20 +987,19 @@ static int do_step(nnpm_ctx* ctx, bool comoving, double dt, double a_d1, double 
   CKR(do_solve(ctx, tim ? ev + 8 : nullptr));
   if (tim) CK(cudaEventRecord(ev[3], ctx->st));
   if (ctx->np) {
-#define PSH(RK, IT) launch_push<RK, IT>(ctx, comoving, pp)
+#define PSH(RK, IT) CKR((launch_push<RK, IT>(ctx, comoving, pp)))
     if (ctx->R == 3) { if (ctx->cfg.backinterp) PSH(3, 1); else PSH(3, 0); }
     else { if (ctx->cfg.backinterp) PSH(2, 1); else PSH(2, 0); }
 #undef PSH
-    LAUNCHED(ctx);
-    KCHECK();
   }
   if (tim) CK(cudaEventRecord(ev[4], ctx->st));
   ctx->last_migrated = 0;
   if (ctx->P > 1) CKR(comm_migrate(ctx));
   if (tim) CK(cudaEventRecord(ev[5], ctx->st));
-  CK(cudaMemcpyAsync(ctx->h_red, ctx->d_red, 4 * sizeof(i64), cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaMemcpyAsync(ctx->h_red, ctx->d_red, 5 * sizeof(i64), cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
   ctx->step_count++;
+  ctx->last_untiled = ctx->h_red[4] + (ctx->sorted_np > 0 && ctx->np > ctx->sorted_np ? ctx->np - ctx->sorted_np : 0);
   ctx->ids_dirty = ctx->ids_dirty || ctx->P > 1;
   ctx->pa_valid = false;
   if (stats) {
@@ -970,6 +1008,7 @@ static int do_step(nnpm_ctx* ctx, bool comoving, double dt, double a_d1, double 
     stats->max_v = ctx->np ? ord_decode(ctx->h_red[1]) : -INFINITY;
     stats->max_pa = ctx->np ? ord_decode(ctx->h_red[2]) : -INFINITY;
     stats->n_halo_violations = ctx->h_red[3];
+    stats->n_untiled = ctx->h_red[4];
     stats->npart_local = ctx->np;
     stats->n_migrated = ctx->last_migrated;
     stats->kernel_launches = ctx->launches - launches0;

@@ -6,6 +6,7 @@
 // the Julia/oracle value for the same inputs.  Only summation order (atomics) and the FFT
 // differ from the reference at rounding level.
 #pragma once
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -420,6 +421,78 @@ __global__ void k_interp_acc(double* pa0, double* pa1, double* pa2, const double
 }
 
 // ------------------------------------------------------------------------------------------
+// compute_acceleration (:631-637) + cic_interp (:676-721) fused: the finite-difference gradient is
+// evaluated at the 4 / 8 CIC corners from phi values delivered by ld(a, b, c), a/b/c in 0..3
+// indexing cells (i-1, i, ip, ip+1) x (j-1, j, jp, jp+1) x (k-1, k, kp, kp+1).
+//   -(N1*((hi-lo)/2)) == (hi-lo) * (-N1/2) bit for bit (the halving and negation are exact), so
+//   gfac = -N1/2; weights multiply left to right, corners add in the reference's order.
+// ------------------------------------------------------------------------------------------
+template <int RANK, class LD>
+__device__ __forceinline__ void cic_grad_gather(const LD& ld, double dx, double dy, double dz, double gfac, double* pa) {
+  const double odx = __dsub_rn(1.0, dx), ody = __dsub_rn(1.0, dy);
+  const double wxs[2] = {odx, dx}, wys[2] = {ody, dy};
+  if (RANK == 2) {
+    double c[2][4], ylo[2], yhi[2];
+#pragma unroll
+    for (int b = 0; b < 2; b++)
+#pragma unroll
+      for (int a = 0; a < 4; a++) c[b][a] = ld(a, 1 + b, 0);
+#pragma unroll
+    for (int a = 0; a < 2; a++) { ylo[a] = ld(1 + a, 0, 0); yhi[a] = ld(1 + a, 3, 0); }
+    // order :687-688  (i,j) (ip,j) (i,jp) (ip,jp)
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int a = t & 1, b = t >> 1;
+      const double gx = __dmul_rn(__dsub_rn(c[b][a + 2], c[b][a]), gfac);
+      const double hi = b ? yhi[a] : c[1][a + 1], lo = b ? c[0][a + 1] : ylo[a];
+      const double gy = __dmul_rn(__dsub_rn(hi, lo), gfac);
+      const double tx = __dmul_rn(__dmul_rn(gx, wxs[a]), wys[b]);
+      const double ty = __dmul_rn(__dmul_rn(gy, wxs[a]), wys[b]);
+      s0 = t ? __dadd_rn(s0, tx) : tx;
+      s1 = t ? __dadd_rn(s1, ty) : ty;
+    }
+    pa[0] = s0; pa[1] = s1;
+  } else {
+    const double odz = __dsub_rn(1.0, dz);
+    const double wzs[2] = {odz, dz};
+    double c[2][2][4], ylo[2][2], yhi[2][2], zlo[2][2], zhi[2][2];
+#pragma unroll
+    for (int cz = 0; cz < 2; cz++)
+#pragma unroll
+      for (int b = 0; b < 2; b++)
+#pragma unroll
+        for (int a = 0; a < 4; a++) c[cz][b][a] = ld(a, 1 + b, 1 + cz);
+#pragma unroll
+    for (int cz = 0; cz < 2; cz++)
+#pragma unroll
+      for (int a = 0; a < 2; a++) { ylo[cz][a] = ld(1 + a, 0, 1 + cz); yhi[cz][a] = ld(1 + a, 3, 1 + cz); }
+#pragma unroll
+    for (int b = 0; b < 2; b++)
+#pragma unroll
+      for (int a = 0; a < 2; a++) { zlo[b][a] = ld(1 + a, 1 + b, 0); zhi[b][a] = ld(1 + a, 1 + b, 3); }
+    // order :710-717: (i,j,k)(ip,j,k)(i,jp,k)(ip,jp,k) then the kp four
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      const int a = t & 1, b = (t >> 1) & 1, cz = t >> 2;
+      const double gx = __dmul_rn(__dsub_rn(c[cz][b][a + 2], c[cz][b][a]), gfac);
+      const double yh = b ? yhi[cz][a] : c[cz][1][a + 1], yl = b ? c[cz][0][a + 1] : ylo[cz][a];
+      const double gy = __dmul_rn(__dsub_rn(yh, yl), gfac);
+      const double zh = cz ? zhi[b][a] : c[1][b][a + 1], zl = cz ? c[0][b][a + 1] : zlo[b][a];
+      const double gz = __dmul_rn(__dsub_rn(zh, zl), gfac);
+      const double tx = __dmul_rn(__dmul_rn(__dmul_rn(gx, wxs[a]), wys[b]), wzs[cz]);
+      const double ty = __dmul_rn(__dmul_rn(__dmul_rn(gy, wxs[a]), wys[b]), wzs[cz]);
+      const double tz = __dmul_rn(__dmul_rn(__dmul_rn(gz, wxs[a]), wys[b]), wzs[cz]);
+      s0 = t ? __dadd_rn(s0, tx) : tx;
+      s1 = t ? __dadd_rn(s1, ty) : ty;
+      s2 = t ? __dadd_rn(s2, tz) : tz;
+    }
+    pa[0] = s0; pa[1] = s1; pa[2] = s2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K5 fused push: [leading half-drift recomputed] -> make_periodic -> gradient of phi taken on
 // the fly (compute_acceleration, :631-637) -> back-interpolation (:640-721) -> kick (:731-736 or
 // :800-807) -> drift(s) (:723-728) -> make_periodic -> max reductions (:782, :875-878).
@@ -434,13 +507,39 @@ struct PushParams {
 
 #define PHI(ii, jj, pp) __ldg(phi + (ii) + g.rowp * (jj) + g.plane * (i64)(pp))
 
+// kick + drift(s) + wrap of one particle, shared by the global and the tiled push
+template <int RANK, bool COMOVING>
+__device__ __forceinline__ void push_finish(const PartPtrs& p, i64 n, const double* x, const double* v, const double* pa,
+                                            const PushParams& pp, double& mxa, double& mxv, double& mxp) {
+#pragma unroll
+  for (int d = 0; d < RANK; d++) {
+    double vn, xn;
+    if (COMOVING) {
+      vn = kick_comoving_rn(v[d], pa[d], pp.dt, pp.a, pp.hub);
+      xn = wrap01(__dadd_rn(x[d], __dmul_rn(pp.c2, vn)));
+    } else {
+      double x1 = __dadd_rn(x[d], __dmul_rn(pp.c1, v[d]));
+      vn = __dadd_rn(v[d], __dmul_rn(pp.dt, pa[d]));
+      xn = __dadd_rn(x1, __dmul_rn(pp.c1, vn));
+    }
+    p.x[d][n] = xn;
+    p.v[d][n] = vn;
+    mxa = fmax(mxa, fabs(vn));
+    mxv = fmax(mxv, vn);
+    mxp = fmax(mxp, pa[d]);
+  }
+}
+
+// Global-gather push.  Work items: particles [base, base+count) or, when list != nullptr, the
+// particle indices list[0 .. *list_count) (the tiled push's stragglers).
 template <int RANK, int INTERP, bool COMOVING, int MINB>
 __global__ void __launch_bounds__(256, MINB)
-k_push(PartPtrs p, i64 np, Geom g, const double* __restrict__ phi, PushParams pp, i64* __restrict__ red,
-       u64* __restrict__ viol) {
-  i64 n = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+k_push(PartPtrs p, i64 base, i64 count, const uint32_t* __restrict__ list, const u64* __restrict__ list_count, Geom g,
+       const double* __restrict__ phi, PushParams pp, i64* __restrict__ red, u64* __restrict__ viol) {
   double mxa = -INFINITY, mxv = -INFINITY, mxp = -INFINITY;
-  if (n < np) {
+  const i64 total = list ? (i64)*list_count : count;
+  for (i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+    const i64 n = list ? (i64)list[t] : base + t;
     double x[3], v[3], pa[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int d = 0; d < RANK; d++) {
@@ -482,33 +581,10 @@ k_push(PartPtrs p, i64 np, Geom g, const double* __restrict__ phi, PushParams pp
         ro[2] = rowp * j2;
         ro[3] = rowp * ((j2 == N2 - 1) ? 0 : j2 + 1);
       }
-      const double odx = __dsub_rn(1.0, dx), ody = __dsub_rn(1.0, dy);
-      const double wxs[2] = {odx, dx}, wys[2] = {ody, dy};
-      // -(N1*((hi-lo)/2)) == (hi-lo) * (-N1/2) bit for bit: the halving and the negation are exact
       const double gfac = -0.5 * g.fN1;
       if (RANK == 2) {
         const double* P = phi + g.plane * (i64)g.glo;
-        double c[2][4], ylo[2], yhi[2];
-#pragma unroll
-        for (int b = 0; b < 2; b++)
-#pragma unroll
-          for (int a = 0; a < 4; a++) c[b][a] = __ldg(P + (unsigned)(ro[1 + b] + ia[a]));
-#pragma unroll
-        for (int a = 0; a < 2; a++) { ylo[a] = __ldg(P + (unsigned)(ro[0] + ia[1 + a])); yhi[a] = __ldg(P + (unsigned)(ro[3] + ia[1 + a])); }
-        // order :687-688  (i,j) (ip,j) (i,jp) (ip,jp)
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-          const int a = t & 1, b = t >> 1;
-          const double gx = __dmul_rn(__dsub_rn(c[b][a + 2], c[b][a]), gfac);
-          const double hi = b ? yhi[a] : c[1][a + 1], lo = b ? c[0][a + 1] : ylo[a];
-          const double gy = __dmul_rn(__dsub_rn(hi, lo), gfac);
-          const double tx = __dmul_rn(__dmul_rn(gx, wxs[a]), wys[b]);
-          const double ty = __dmul_rn(__dmul_rn(gy, wxs[a]), wys[b]);
-          s0 = t ? __dadd_rn(s0, tx) : tx;
-          s1 = t ? __dadd_rn(s1, ty) : ty;
-        }
-        pa[0] = s0; pa[1] = s1;
+        cic_grad_gather<2>([&](int a, int b, int) { return __ldg(P + (unsigned)(ro[b] + ia[a])); }, dx, dy, 0.0, gfac, pa);
       } else {
         const int N3 = (int)g.N3;
         int k, kp;
@@ -524,101 +600,253 @@ k_push(PartPtrs p, i64 np, Geom g, const double* __restrict__ phi, PushParams pp
         const int pl[4] = {local_plane32(km1, g), local_plane32(k, g), local_plane32(kp, g), local_plane32(kp2, g)};
         ok = (pl[0] | pl[1] | pl[2] | pl[3]) >= 0;
         if (ok) {
-          const double* P0 = phi + g.plane * (i64)pl[0];
-          const double* P1 = phi + g.plane * (i64)pl[1];
-          const double* P2 = phi + g.plane * (i64)pl[2];
-          const double* P3 = phi + g.plane * (i64)pl[3];
-          const double odz = __dsub_rn(1.0, dz);
-          const double wzs[2] = {odz, dz};
-          double c[2][2][4], ylo[2][2], yhi[2][2], zlo[2][2], zhi[2][2];
-#pragma unroll
-          for (int b = 0; b < 2; b++)
-#pragma unroll
-            for (int a = 0; a < 4; a++) {
-              c[0][b][a] = __ldg(P1 + (unsigned)(ro[1 + b] + ia[a]));
-              c[1][b][a] = __ldg(P2 + (unsigned)(ro[1 + b] + ia[a]));
-            }
-#pragma unroll
-          for (int a = 0; a < 2; a++) {
-            ylo[0][a] = __ldg(P1 + (unsigned)(ro[0] + ia[1 + a]));
-            yhi[0][a] = __ldg(P1 + (unsigned)(ro[3] + ia[1 + a]));
-            ylo[1][a] = __ldg(P2 + (unsigned)(ro[0] + ia[1 + a]));
-            yhi[1][a] = __ldg(P2 + (unsigned)(ro[3] + ia[1 + a]));
-          }
-#pragma unroll
-          for (int b = 0; b < 2; b++)
-#pragma unroll
-            for (int a = 0; a < 2; a++) {
-              zlo[b][a] = __ldg(P0 + (unsigned)(ro[1 + b] + ia[1 + a]));
-              zhi[b][a] = __ldg(P3 + (unsigned)(ro[1 + b] + ia[1 + a]));
-            }
-          // order :710-717: (i,j,k)(ip,j,k)(i,jp,k)(ip,jp,k) then the kp four
-          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-          for (int t = 0; t < 8; t++) {
-            const int a = t & 1, b = (t >> 1) & 1, cz = t >> 2;
-            const double gx = __dmul_rn(__dsub_rn(c[cz][b][a + 2], c[cz][b][a]), gfac);
-            const double yh = b ? yhi[cz][a] : c[cz][1][a + 1], yl = b ? c[cz][0][a + 1] : ylo[cz][a];
-            const double gy = __dmul_rn(__dsub_rn(yh, yl), gfac);
-            const double zh = cz ? zhi[b][a] : c[1][b][a + 1], zl = cz ? c[0][b][a + 1] : zlo[b][a];
-            const double gz = __dmul_rn(__dsub_rn(zh, zl), gfac);
-            const double tx = __dmul_rn(__dmul_rn(__dmul_rn(gx, wxs[a]), wys[b]), wzs[cz]);
-            const double ty = __dmul_rn(__dmul_rn(__dmul_rn(gy, wxs[a]), wys[b]), wzs[cz]);
-            const double tz = __dmul_rn(__dmul_rn(__dmul_rn(gz, wxs[a]), wys[b]), wzs[cz]);
-            s0 = t ? __dadd_rn(s0, tx) : tx;
-            s1 = t ? __dadd_rn(s1, ty) : ty;
-            s2 = t ? __dadd_rn(s2, tz) : tz;
-          }
-          pa[0] = s0; pa[1] = s1; pa[2] = s2;
+          const double* P[4] = {phi + g.plane * (i64)pl[0], phi + g.plane * (i64)pl[1], phi + g.plane * (i64)pl[2],
+                                phi + g.plane * (i64)pl[3]};
+          cic_grad_gather<3>([&](int a, int b, int c) { return __ldg(P[c] + (unsigned)(ro[b] + ia[a])); }, dx, dy, dz, gfac, pa);
         }
       }
     }
     if (!ok) atomicAdd(viol, 1ull);
+    push_finish<RANK, COMOVING>(p, n, x, v, pa, pp, mxa, mxv, mxp);
+  }
+  block_max3(mxa, mxv, mxp, red);
+}
+
+// ------------------------------------------------------------------------------------------
+// Tiled push (CIC): one CTA per tile of TX x TY x TZ cells of tile-sorted particles.  The phi box
+// the tile's particles can touch -- cells [-H-1, T+H+2) around the tile, H = cells a particle may
+// have strayed since the sort -- is staged in shared memory once; every particle then takes its 32
+// (16 in 2-D) stencil values from shared memory.  Particles outside the box go to `slow_list` and
+// are pushed afterwards by k_push's global-gather path.  Arithmetic is cic_grad_gather in both.
+// ------------------------------------------------------------------------------------------
+#define NNPM_TX 32
+#define NNPM_TY 8
+#define NNPM_TZ 8
+#define NNPM_TH 1
+struct TileGeom {
+  int ntx, nty, ntz;   // tiles per axis (z: over the slab's owned planes)
+  int tx, ty, tz;      // tile extent in cells (clamped to the mesh)
+};
+
+// Fast-path gather: same operator as cic_grad_gather with the products re-associated so that the
+// FP64 pipe (16 lanes per SM sub-partition -- a co-limit of this kernel next to HBM) sees 72
+// instead of 141 operations: corner weights w = wx*wy*wz*(-N1/2) are formed once and shared by
+// the three components, and the corner sums use fused multiply-adds.  Differences from the
+// reference's evaluation order are a few ulp of the largest term (parity budget: 1e-12).
+template <int RANK, class LD>
+__device__ __forceinline__ void cic_grad_gather_fma(const LD& ld, double dx, double dy, double dz, double gfac, double* pa) {
+  const double odx = 1.0 - dx, ody = 1.0 - dy;
+  const double wx[2] = {odx * gfac, dx * gfac}, wy[2] = {ody, dy};
+  if (RANK == 2) {
+    double c[2][4], ylo[2], yhi[2];
+#pragma unroll
+    for (int b = 0; b < 2; b++)
+#pragma unroll
+      for (int a = 0; a < 4; a++) c[b][a] = ld(a, 1 + b, 0);
+#pragma unroll
+    for (int a = 0; a < 2; a++) { ylo[a] = ld(1 + a, 0, 0); yhi[a] = ld(1 + a, 3, 0); }
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int a = t & 1, b = t >> 1;
+      const double w = wx[a] * wy[b];
+      const double hi = b ? yhi[a] : c[1][a + 1], lo = b ? c[0][a + 1] : ylo[a];
+      s0 = fma(c[b][a + 2] - c[b][a], w, s0);
+      s1 = fma(hi - lo, w, s1);
+    }
+    pa[0] = s0; pa[1] = s1;
+  } else {
+    const double wz[2] = {1.0 - dz, dz};
+    double c[2][2][4], ylo[2][2], yhi[2][2], zlo[2][2], zhi[2][2];
+#pragma unroll
+    for (int cz = 0; cz < 2; cz++)
+#pragma unroll
+      for (int b = 0; b < 2; b++)
+#pragma unroll
+        for (int a = 0; a < 4; a++) c[cz][b][a] = ld(a, 1 + b, 1 + cz);
+#pragma unroll
+    for (int cz = 0; cz < 2; cz++)
+#pragma unroll
+      for (int a = 0; a < 2; a++) { ylo[cz][a] = ld(1 + a, 0, 1 + cz); yhi[cz][a] = ld(1 + a, 3, 1 + cz); }
+#pragma unroll
+    for (int b = 0; b < 2; b++)
+#pragma unroll
+      for (int a = 0; a < 2; a++) { zlo[b][a] = ld(1 + a, 1 + b, 0); zhi[b][a] = ld(1 + a, 1 + b, 3); }
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      const int a = t & 1, b = (t >> 1) & 1, cz = t >> 2;
+      const double w = wx[a] * wy[b] * wz[cz];
+      const double yh = b ? yhi[cz][a] : c[cz][1][a + 1], yl = b ? c[cz][0][a + 1] : ylo[cz][a];
+      const double zh = cz ? zhi[b][a] : c[1][b][a + 1], zl = cz ? c[0][b][a + 1] : zlo[b][a];
+      s0 = fma(c[cz][b][a + 2] - c[cz][b][a], w, s0);
+      s1 = fma(yh - yl, w, s1);
+      s2 = fma(zh - zl, w, s2);
+    }
+    pa[0] = s0; pa[1] = s1; pa[2] = s2;
+  }
+}
+
+// correctly rounded p/a from the correctly rounded reciprocal ra = RN(1/a) (Markstein): three
+// operations instead of the ~12 of a full division; equals __ddiv_rn(p, a) for every a whose
+// significand is not all ones.
+__device__ __forceinline__ double div_by_scalar(double p, double a, double ra) {
+  const double q = p * ra;
+  const double r = fma(-q, a, p);
+  return fma(r, ra, q);
+}
+
+template <int RANK, bool COMOVING>
+__device__ __forceinline__ void push_finish_fast(const PartPtrs& p, i64 n, const double* x, const double* v, const double* pa,
+                                                 const PushParams& pp, double ra, double& mxa, double& mxv, double& mxp) {
+#pragma unroll
+  for (int d = 0; d < RANK; d++) {
+    double vn, xn;
+    if (COMOVING) {  // ParticleMesh.jl:800-807 in the reference's operation order; only pa/a is restructured
+      const double vmid = __dadd_rn(v[d], __dmul_rn(__dmul_rn(pa[d], pp.dt), 0.5));
+      const double t = __dadd_rn(__dmul_rn(-vmid, pp.hub), div_by_scalar(pa[d], pp.a, ra));
+      vn = __dadd_rn(v[d], __dmul_rn(t, pp.dt));
+      xn = wrap01(__dadd_rn(x[d], __dmul_rn(pp.c2, vn)));
+    } else {
+      double x1 = __dadd_rn(x[d], __dmul_rn(pp.c1, v[d]));
+      vn = __dadd_rn(v[d], __dmul_rn(pp.dt, pa[d]));
+      xn = __dadd_rn(x1, __dmul_rn(pp.c1, vn));
+    }
+    p.x[d][n] = xn;
+    p.v[d][n] = vn;
+    mxa = fmax(mxa, fabs(vn));
+    mxv = fmax(mxv, vn);
+    mxp = fmax(mxp, pa[d]);
+  }
+}
+
+#define NNPM_BX (NNPM_TX + 2 * NNPM_TH + 3)
+#define NNPM_BY (NNPM_TY + 2 * NNPM_TH + 3)
+#define NNPM_BZ (NNPM_TZ + 2 * NNPM_TH + 3)
+
+__device__ __forceinline__ int wrap_small(int z, int N) {  // z within a few periods of [0, N)
+  if (z < 0) { z += N; if (z < 0) z = ((z % N) + N) % N; }
+  else if (z >= N) { z -= N; if (z >= N) z %= N; }
+  return z;
+}
+
+template <int RANK, bool COMOVING, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_push_tile(PartPtrs p, i64 np, Geom g, TileGeom tg, const uint32_t* __restrict__ tile_off, const double* __restrict__ phi,
+            PushParams pp, i64* __restrict__ red, uint32_t* __restrict__ slow_list, u64* __restrict__ slow_count) {
+  extern __shared__ double box[];  // [BZ][BY][BX]
+  constexpr int BX = NNPM_BX, BY = NNPM_BY, BZ = (RANK == 3) ? NNPM_BZ : 1, BXY = BX * BY;
+  const int t = blockIdx.x;
+  i64 n0 = tile_off[t], n1 = tile_off[t + 1];
+  if (n1 > np) n1 = np;
+  if (n0 >= n1) return;  // uniform across the block
+  const int N1 = (int)g.N1, N2 = (int)g.N2, N3 = (int)g.N3;
+  const int ttx = t % tg.ntx, tty = (t / tg.ntx) % tg.nty, ttz = t / (tg.ntx * tg.nty);
+  const int ti0 = ttx * tg.tx, tj0 = tty * tg.ty, tk0 = ttz * tg.tz;  // tk0: plane within the slab
+  // first particle's loads go out before the box is staged
+  i64 n = n0 + threadIdx.x;
+  double cx[3], cv[3];
+  if (n < n1) {
+#pragma unroll
+    for (int d = 0; d < RANK; d++) { cx[d] = p.x[d][n]; cv[d] = p.v[d][n]; }
+  }
+  {  // stage the phi box: one warp per (by, bz) row, lanes along x
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int gi0 = wrap_small(ti0 - NNPM_TH - 1 + lane, N1);
+    int gi1 = wrap_small(ti0 - NNPM_TH - 1 + lane + 32, N1);
+    for (int row = warp; row < BY * BZ; row += 8) {
+      const int byi = row % BY, bzi = row / BY;  // compile-time divisors
+      const int gj = wrap_small(tj0 - NNPM_TH - 1 + byi, N2);
+      int lp = g.glo;
+      bool valid = true;
+      if (RANK == 3) {
+        lp = tk0 - NNPM_TH - 1 + bzi;
+        if (g.glo) { lp += g.glo; valid = lp >= 0 && lp < g.nplanes; }
+        else lp = wrap_small(lp, N3);
+      }
+      const double* src = phi + g.plane * (i64)lp + (unsigned)((int)g.rowp * gj);
+      double* dst = box + row * BX;
+      // cp.async (LDGSTS): all rows of the box are in flight at once, no register staging
+      if (valid) {
+        __pipeline_memcpy_async(dst + lane, src + gi0, 8);
+        if (lane + 32 < BX) __pipeline_memcpy_async(dst + lane + 32, src + gi1, 8);
+      } else {
+        dst[lane] = 0.0;
+        if (lane + 32 < BX) dst[lane + 32] = 0.0;
+      }
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+  }
+  __syncthreads();
+  const double gfac = -0.5 * g.fN1;
+  const double ra = 1.0 / pp.a;
+  const int k0g = (int)g.kz0 + tk0;  // global plane of the tile origin
+  const int fx = tg.tx + 2 * NNPM_TH, fy = tg.ty + 2 * NNPM_TH, fz = tg.tz + 2 * NNPM_TH;
+  double mxa = -INFINITY, mxv = -INFINITY, mxp = -INFINITY;
+  while (n < n1) {
+    double x[3], v[3], pa[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < RANK; d++) { x[d] = cx[d]; v[d] = cv[d]; }
+    const i64 nn = n + 256;
+    if (nn < n1) {  // prefetch the next particle of this thread
+#pragma unroll
+      for (int d = 0; d < RANK; d++) { cx[d] = p.x[d][nn]; cv[d] = p.v[d][nn]; }
+    }
 #pragma unroll
     for (int d = 0; d < RANK; d++) {
-      double vn, xn;
-      if (COMOVING) {
-        vn = kick_comoving_rn(v[d], pa[d], pp.dt, pp.a, pp.hub);
-        xn = wrap01(__dadd_rn(x[d], __dmul_rn(pp.c2, vn)));
-      } else {
-        double x1 = __dadd_rn(x[d], __dmul_rn(pp.c1, v[d]));
-        vn = __dadd_rn(v[d], __dmul_rn(pp.dt, pa[d]));
-        xn = __dadd_rn(x1, __dmul_rn(pp.c1, vn));
-      }
-      p.x[d][n] = xn;
-      p.v[d][n] = vn;
-      mxa = fmax(mxa, fabs(vn));
-      mxv = fmax(mxv, vn);
-      mxp = fmax(mxp, pa[d]);
+      if (COMOVING) x[d] = __dadd_rn(x[d], __dmul_rn(pp.c0, v[d]));
+      x[d] = wrap01(x[d]);
     }
+    int i, j, k = 0, dummy;
+    double dx, dy, dz = 0.0;
+    cell_of32(x[0], g.fN1, N1, i, dummy, dx);
+    cell_of32(x[1], g.fN2, N2, j, dummy, dy);
+    int ri = i - ti0 + NNPM_TH, rj = j - tj0 + NNPM_TH, rk = 0;
+    ri = ri < 0 ? ri + N1 : (ri >= N1 ? ri - N1 : ri);
+    rj = rj < 0 ? rj + N2 : (rj >= N2 ? rj - N2 : rj);
+    bool fast = ri < fx && rj < fy;
+    if (RANK == 3) {
+      cell_of32(x[2], g.fN3, N3, k, dummy, dz);
+      rk = k - k0g + NNPM_TH;
+      rk = rk < 0 ? rk + N3 : (rk >= N3 ? rk - N3 : rk);
+      fast = fast && rk < fz;
+    }
+    if (!fast) {
+      slow_list[atomicAdd(slow_count, 1ull)] = (uint32_t)n;
+    } else {
+      const double* b0 = box + (rk * BXY + rj * BX + ri);
+      if (RANK == 2) cic_grad_gather_fma<2>([&](int a, int b, int) { return b0[b * BX + a]; }, dx, dy, 0.0, gfac, pa);
+      else cic_grad_gather_fma<3>([&](int a, int b, int c) { return b0[c * BXY + b * BX + a]; }, dx, dy, dz, gfac, pa);
+      push_finish_fast<RANK, COMOVING>(p, n, x, v, pa, pp, ra, mxa, mxv, mxp);
+    }
+    n = nn;
   }
   block_max3(mxa, mxv, mxp, red);
 }
 #undef PHI
 
 // ------------------------------------------------------------------------------------------
-// K0 counting sort by 8x8x8-cell tile (histogram -> scan -> scatter)
+// K0 counting sort by tile of NNPM_TX x NNPM_TY x NNPM_TZ cells (histogram -> scan -> scatter).
+// After the scan `hist` holds the tile offsets the tiled deposit / push kernels index by.
 // ------------------------------------------------------------------------------------------
-#define NNPM_TILE 8
-struct TileGeom {
-  i64 ntx, nty, ntz;
-};
-
 template <int RANK>
 __global__ void k_sort_count(PartPtrs p, i64 np, Geom g, TileGeom tg, uint32_t* __restrict__ hist,
                              uint32_t* __restrict__ key, uint32_t* __restrict__ rnk) {
   i64 n = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (n >= np) return;
-  i64 i = wrap_idx((i64)floor(wrap01(p.x[0][n]) * g.fN1), g.N1);
-  i64 j = wrap_idx((i64)floor(wrap01(p.x[1][n]) * g.fN2), g.N2);
-  i64 kl = 0;
+  int i, j, k, dummy;
+  double d;
+  cell_of32(wrap01(p.x[0][n]), g.fN1, (int)g.N1, i, dummy, d);
+  cell_of32(wrap01(p.x[1][n]), g.fN2, (int)g.N2, j, dummy, d);
+  int kl = 0;
   if (RANK == 3) {
-    i64 k = wrap_idx((i64)floor(wrap01(p.x[2][n]) * g.fN3), g.N3);
-    kl = k - g.kz0;
+    cell_of32(wrap01(p.x[2][n]), g.fN3, (int)g.N3, k, dummy, d);
+    kl = k - (int)g.kz0;
     if (kl < 0) kl = 0;              // strays (not yet migrated) sort into the boundary tiles
-    if (kl >= g.nzl) kl = g.nzl - 1;
+    if (kl >= (int)g.nzl) kl = (int)g.nzl - 1;
   }
-  uint32_t t = (uint32_t)((i / NNPM_TILE) + tg.ntx * ((j / NNPM_TILE) + tg.nty * (kl / NNPM_TILE)));
+  uint32_t t = (uint32_t)((i / tg.tx) + tg.ntx * ((j / tg.ty) + tg.nty * (kl / tg.tz)));
   key[n] = t;
   rnk[n] = atomicAdd(&hist[t], 1u);
 }

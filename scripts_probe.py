@@ -5,7 +5,7 @@ sys.path.insert(0, '.')
 from noname_b200 import DevicePM
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 opts = dict(kv.split('=') for kv in sys.argv[2:])
-dev = DevicePM((n, n, n), n ** 3, rank=3, timing=True, sort_every=int(opts.pop('sort_every', 0)),
+dev = DevicePM((n, n, n), n ** 3, rank=3, timing=True, part_capacity=int(opts.pop('cap_extra', 0)) + n ** 3, sort_every=int(opts.pop('sort_every', 0)),
                deposit_mode=opts.pop('deposit_mode', 'atomic'))
 for k, v in opts.items():
     dev.set_option(k, float(v))
