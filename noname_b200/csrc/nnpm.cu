@@ -69,6 +69,9 @@ struct nnpm_ctx {
   i64 sorted_np;     // particles [0, sorted_np) are covered by the tile offsets in `hist` (0 = not sorted)
   i64 last_untiled;  // stragglers of the last tiled push
 
+  CUtensorMap tmap_phi;  // 3-D tiled tensor map over the mesh (rowp x N2 x nplanes doubles), box = push tile box
+  bool have_tmap;
+
   // reductions
   i64* d_red;  // [0..2] encoded maxima, [3] violation counter
   i64* h_red;  // pinned
@@ -250,6 +253,29 @@ static void sin2_table(std::vector<double>& t, i64 N, bool wrapneg, bool round_h
   }
 }
 
+// TMA descriptor of the mesh for the tiled push: doubles, dims (N1, N2, nplanes) with the padded
+// strides of the in-place FFT layout, box = (NNPM_BX, NNPM_BY, NNPM_BZ|1), no swizzle, OOB -> 0.
+static int make_tensor_map(nnpm_ctx* ctx) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) return fail(ctx, NNPM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  const Geom& g = ctx->g;
+  cuuint64_t dims[3] = {(cuuint64_t)g.N1, (cuuint64_t)g.N2, (cuuint64_t)g.nplanes};
+  cuuint64_t strides[2] = {(cuuint64_t)g.rowp * 8, (cuuint64_t)g.plane * 8};
+  cuuint32_t box[3] = {NNPM_BX, NNPM_BY, (cuuint32_t)(ctx->R == 3 ? NNPM_BZ : 1)};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = ((encode_fn)fn)(&ctx->tmap_phi, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ctx->mesh, dims, strides, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, NNPM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  ctx->have_tmap = true;
+  return NNPM_OK;
+}
+
 extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   nnpm_ctx* ctx = nullptr;
   if (!out || !cfg) return fail(ctx, NNPM_ERR_ARG, "null argument");
@@ -308,6 +334,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->stage = nullptr; c->stage_elems = 0;
   c->hist = c->bsum = c->bsum2 = c->skey = c->srnk = nullptr;
   c->have2 = c->havez = c->have3 = false;
+  c->have_tmap = false;
   c->opt_fft3d = 0; c->opt_zfused = 1; c->opt_tile_deposit = 1; c->opt_tile_push = 1; c->opt_push_minb = 2;
   c->fftwork = nullptr; c->fftwork_bytes = 0;
   c->step_count = 0; c->launches = 0;
@@ -360,6 +387,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
     CKB(CK(cudaMemcpy(c->s2, t2.data(), N2 * 8, cudaMemcpyHostToDevice)));
     CKB(CK(cudaMemcpy(c->s3, t3.data(), N3 * 8, cudaMemcpyHostToDevice)));
   }
+  CKB(CKR(make_tensor_map(c)));
   CKB(CKR(make_plans(c)));
   for (int i = 0; i < 16; i++) CKB(CK(cudaEventCreate(&c->ev[i])));
   c->tg.tx = (int)(N1 < NNPM_TX ? N1 : NNPM_TX);
@@ -938,7 +966,7 @@ static int launch_push(nnpm_ctx* ctx, bool comoving, const PushParams& pp) {
 #define LT(CM, MB)                                                                                                  \
   do {                                                                                                              \
     CK(cudaFuncSetAttribute(k_push_tile<RANK, CM, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    k_push_tile<RANK, CM, MB><<<(unsigned)ctx->ntiles, 256, smem, ctx->st>>>(ctx->pp, covered, ctx->g, ctx->tg, ctx->hist, \
+    k_push_tile<RANK, CM, MB><<<(unsigned)ctx->ntiles, 256, smem, ctx->st>>>(ctx->tmap_phi, ctx->pp, covered, ctx->g, ctx->tg, ctx->hist, \
                                                                              ctx->mesh, pp, ctx->d_red, ctx->srnk, slow_count); \
   } while (0)
   if (ctx->opt_push_minb >= 3) { if (comoving) LT(true, 3); else LT(false, 3); }

@@ -6,6 +6,7 @@
 // the Julia/oracle value for the same inputs.  Only summation order (atomics) and the FFT
 // differ from the reference at rounding level.
 #pragma once
+#include <cuda.h>
 #include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -720,7 +721,7 @@ __device__ __forceinline__ void push_finish_fast(const PartPtrs& p, i64 n, const
   }
 }
 
-#define NNPM_BX (NNPM_TX + 2 * NNPM_TH + 3)
+#define NNPM_BX (NNPM_TX + 2 * NNPM_TH + 4)  // 37 used + 1: the TMA inner box extent must be a multiple of 16 B
 #define NNPM_BY (NNPM_TY + 2 * NNPM_TH + 3)
 #define NNPM_BZ (NNPM_TZ + 2 * NNPM_TH + 3)
 
@@ -730,11 +731,43 @@ __device__ __forceinline__ int wrap_small(int z, int N) {  // z within a few per
   return z;
 }
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier primitives, sm_90+/sm_100a PTX ---------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "NNPM_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra NNPM_DONE;\n"
+      "bra NNPM_WAIT;\n"
+      "NNPM_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
 template <int RANK, bool COMOVING, int MINB>
 __global__ void __launch_bounds__(256, MINB)
-k_push_tile(PartPtrs p, i64 np, Geom g, TileGeom tg, const uint32_t* __restrict__ tile_off, const double* __restrict__ phi,
-            PushParams pp, i64* __restrict__ red, uint32_t* __restrict__ slow_list, u64* __restrict__ slow_count) {
-  extern __shared__ double box[];  // [BZ][BY][BX]
+k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g, TileGeom tg,
+            const uint32_t* __restrict__ tile_off, const double* __restrict__ phi, PushParams pp, i64* __restrict__ red,
+            uint32_t* __restrict__ slow_list, u64* __restrict__ slow_count) {
+  extern __shared__ __align__(128) double box[];  // [BZ][BY][BX]
+  __shared__ __align__(8) unsigned long long mbar;
   constexpr int BX = NNPM_BX, BY = NNPM_BY, BZ = (RANK == 3) ? NNPM_BZ : 1, BXY = BX * BY;
   const int t = blockIdx.x;
   i64 n0 = tile_off[t], n1 = tile_off[t + 1];
@@ -750,29 +783,42 @@ k_push_tile(PartPtrs p, i64 np, Geom g, TileGeom tg, const uint32_t* __restrict_
 #pragma unroll
     for (int d = 0; d < RANK; d++) { cx[d] = p.x[d][n]; cv[d] = p.v[d][n]; }
   }
-  {  // stage the phi box: one warp per (by, bz) row, lanes along x
+  // Stage the phi box.  Interior tiles (box inside the mesh, no periodic wrap): ONE TMA tensor copy
+  // issued by one thread, completion on an mbarrier.  Tiles whose box wraps: cp.async row by row.
+  const int bx0 = ti0 - NNPM_TH - 1, by0 = tj0 - NNPM_TH - 1;
+  const int bz0 = (RANK == 3) ? tk0 - NNPM_TH - 1 + g.glo : g.glo;  // local plane of the box origin
+  const bool interior = bx0 >= 0 && bx0 + BX - 1 <= N1 && by0 >= 0 && by0 + BY <= N2 &&
+                        (RANK == 2 || g.glo != 0 || (bz0 >= 0 && bz0 + BZ <= N3));
+  if (interior) {
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&mbar, (unsigned)(BX * BY * BZ * sizeof(double)));
+      tma_load_3d(box, &tmap, bx0, by0, bz0, &mbar);
+    }
+    mbar_wait(&mbar, 0);
+  } else {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int gi0 = wrap_small(ti0 - NNPM_TH - 1 + lane, N1);
-    int gi1 = wrap_small(ti0 - NNPM_TH - 1 + lane + 32, N1);
+    int gi0 = wrap_small(bx0 + lane, N1);
+    int gi1 = wrap_small(bx0 + lane + 32, N1);
     for (int row = warp; row < BY * BZ; row += 8) {
       const int byi = row % BY, bzi = row / BY;  // compile-time divisors
-      const int gj = wrap_small(tj0 - NNPM_TH - 1 + byi, N2);
+      const int gj = wrap_small(by0 + byi, N2);
       int lp = g.glo;
       bool valid = true;
       if (RANK == 3) {
-        lp = tk0 - NNPM_TH - 1 + bzi;
-        if (g.glo) { lp += g.glo; valid = lp >= 0 && lp < g.nplanes; }
+        lp = bz0 + bzi;
+        if (g.glo) valid = lp >= 0 && lp < g.nplanes;
         else lp = wrap_small(lp, N3);
       }
       const double* src = phi + g.plane * (i64)lp + (unsigned)((int)g.rowp * gj);
       double* dst = box + row * BX;
-      // cp.async (LDGSTS): all rows of the box are in flight at once, no register staging
       if (valid) {
         __pipeline_memcpy_async(dst + lane, src + gi0, 8);
-        if (lane + 32 < BX) __pipeline_memcpy_async(dst + lane + 32, src + gi1, 8);
+        if (lane + 32 < BX - 1) __pipeline_memcpy_async(dst + lane + 32, src + gi1, 8);
       } else {
         dst[lane] = 0.0;
-        if (lane + 32 < BX) dst[lane + 32] = 0.0;
+        if (lane + 32 < BX - 1) dst[lane + 32] = 0.0;
       }
     }
     __pipeline_commit();
