@@ -103,6 +103,8 @@ struct nnpm_ctx {
   i64* h_cnt;      // pinned
   i64 last_migrated;
   double* pk_buf;
+  double2* ztw;  // z-FFT twiddles W_N3^m
+  int opt_zcols;
 };
 
 static thread_local std::string g_create_err;
@@ -342,6 +344,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->mig_send = c->mig_recv = nullptr; c->mig_cap = 0; c->mig_holes = nullptr; c->mig_cnt = nullptr; c->h_cnt = nullptr;
   c->last_migrated = 0;
   c->pk_buf = nullptr;
+  c->ztw = nullptr; c->opt_zcols = 8;
   c->mig_lo = nullptr; c->ghost_rx = nullptr; c->red_buf = nullptr;
   c->np = 0; c->m = 0.0; c->ids_dirty = false; c->field_state = 0;
   c->own_stream = false;
@@ -1085,6 +1088,7 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   else if (!strcmp(name, "tile_deposit")) ctx->opt_tile_deposit = v;
   else if (!strcmp(name, "tile_push")) ctx->opt_tile_push = v;
   else if (!strcmp(name, "push_minb")) ctx->opt_push_minb = v;
+  else if (!strcmp(name, "zcols")) ctx->opt_zcols = v;
   else return fail(ctx, NNPM_ERR_ARG, "unknown option '%s'", name);
   return NNPM_OK;
 }

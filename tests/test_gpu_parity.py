@@ -76,6 +76,28 @@ def test_potential(PM, O, dims, rank):
     assert nlinf(got, ref) < TOL
 
 
+@pytest.mark.parametrize("dims", [(16, 8, 64), (12, 10, 128), (32, 16, 256), (8, 8, 512), (8, 4, 1024)])
+def test_potential_fused_z_pass(lib_built, O, dims):
+    """the hand-written fused z-FFT * Green * z-iFFT kernel (N3 = 64 .. 1024) against the oracle and
+    against the cuFFT-composed z path."""
+    from noname_b200 import DevicePM
+    rng = np.random.default_rng(33)
+    shape = (dims[2], dims[1], dims[0])
+    rho = rng.random(shape)
+    ref = np.empty(shape)
+    O.compute_potential(ref, rho - rho.mean(), np.zeros((shape[0], shape[1], shape[2] // 2 + 1), dtype=np.complex128))
+    out = {}
+    for zf in (1, 0):
+        with DevicePM(dims, 1, rank=3) as dev:
+            dev.set_option("zfused", zf)
+            dev.set_field("rho", rho)
+            dev.solve()
+            out[zf] = dev.get_field("phi")
+    assert nlinf(out[1], ref) < TOL
+    assert nlinf(out[0], ref) < TOL
+    assert nlinf(out[1], out[0]) < TOL
+
+
 def test_potential_ignores_mean(PM, O):
     """evolvePM subtracts mean(rho) (:768-769); the DC bin is zeroed (:501) so it must not matter."""
     rng = np.random.default_rng(4)
