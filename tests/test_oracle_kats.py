@@ -1,0 +1,258 @@
+"""CPU tests of the oracle (oracle/pm_ref.py, oracle/pm_ref.c).
+
+The reference ships no tests or golden vectors -> "parity unpinned"; these are the
+pins this repo creates instead: (a) the vectorised oracle equals a literal loop transcription of
+the Julia source bit for bit, (b) the independent C restatement equals the numpy one, (c) the
+analytic known answers derivable from the reference's formulas.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import make_particles, nlinf
+from oracle import pm_ref as O
+from oracle.pm_ref_c import PMRefC
+
+
+@pytest.fixture(scope="module")
+def CR():
+    return PMRefC(threads=1)
+
+
+# ---------------------------------------------------------------- (a) vectorised == literal loops
+@pytest.mark.parametrize("dims,rank", [((8, 6, 1), 2), ((6, 5, 7), 3)])
+def test_cic_deposit_equals_literal_loops(dims, rank):
+    x, _ = make_particles(3, 300, rank, clustered=True)
+    shape = (dims[2], dims[1], dims[0])
+    a, b = np.zeros(shape), np.zeros(shape)
+    O.cicdensity(a, x, 0.37)
+    O.cicdensity_loops(b, x, 0.37)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("dims", [(8, 6, 1), (6, 4, 8)])
+def test_potential_equals_literal_loops(dims):
+    rng = np.random.default_rng(5)
+    shape = (dims[2], dims[1], dims[0])
+    rho = rng.random(shape)
+    rho -= rho.mean()
+    rt = np.zeros((shape[0], shape[1], shape[2] // 2 + 1), dtype=np.complex128)
+    a, b = np.empty(shape), np.empty(shape)
+    O.compute_potential(a, rho, rt)
+    O.potential_loops(b, rho, rt.copy())
+    assert nlinf(a, b) < 4e-16      # per-element sin vs tables: identical expressions, same libm
+
+
+@pytest.mark.parametrize("dims", [(8, 6, 1), (6, 4, 8)])
+def test_gradient_equals_literal_loops(dims):
+    rng = np.random.default_rng(6)
+    shape = (dims[2], dims[1], dims[0])
+    phi = rng.standard_normal(shape)
+    a, b = np.zeros(shape + (3,)), np.zeros(shape + (3,))
+    O.deriv1(a, phi)
+    O.deriv1_loops(b, phi)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("dims,rank", [((8, 6, 1), 2), ((6, 5, 7), 3)])
+def test_cic_interp_equals_literal_loops(dims, rank):
+    rng = np.random.default_rng(7)
+    x, _ = make_particles(8, 200, rank)
+    acc = rng.standard_normal((dims[2], dims[1], dims[0], 3))
+    a, b = np.zeros((200, rank)), np.zeros((200, rank))
+    O.interpVecToPoints(a, acc, x, interpolation="cic")
+    O.cic_interp_loops(b, acc, x)
+    assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------- (b) C restatement == numpy
+@pytest.mark.parametrize("dims,rank", [((16, 12, 1), 2), ((8, 12, 10), 3)])
+@pytest.mark.parametrize("comoving", [False, True])
+def test_c_restatement_step_equals_numpy(CR, dims, rank, comoving):
+    npart = 2000
+    x, v = make_particles(11, npart, rank, clustered=True)
+    v *= 0.05
+    m = 0.8
+    fa, fb = O.Fields(dims, npart, rank), O.Fields(dims, npart, rank)
+    xa, va, xb, vb = x.copy(), v.copy(), x.copy(), v.copy()
+    if comoving:
+        sc = (1.01, 1.02, 0.8, 1.03)
+        O.step_comoving(fa, xa, va, m, 0.01, *sc)
+        CR.step_comoving(fb, xb, vb, m, 0.01, *sc)
+    else:
+        O.step_static(fa, xa, va, m, 0.01)
+        CR.step_static(fb, xb, vb, m, 0.01)
+    assert np.array_equal(fa.rho, fb.rho)            # same summation order
+    assert nlinf(fb.phi, fa.phi) < 1e-14
+    assert nlinf(vb, va) < 1e-14 and np.max(np.abs(xb - xa)) < 1e-15
+
+
+# ---------------------------------------------------------------- (c) analytic known answers
+def test_kat1_single_particle_weights_and_mass():
+    """ParticleMesh.jl:395-402: the 8 CIC weights m(1-d|d)... at cells (i|ip, j|jp, k|kp)."""
+    n = 8
+    x = np.array([[(2 + 0.25) / n, (5 + 0.5) / n, (7 + 0.75) / n]])
+    rho = np.zeros((n, n, n))
+    O.deposit(rho, x, 2.0, interpolation="cic")
+    dx, dy, dz = 0.25, 0.5, 0.75
+    for (kk, wz) in ((7, 1 - dz), (0, dz)):          # kp1 wraps to plane 0
+        for (jj, wy) in ((5, 1 - dy), (6, dy)):
+            for (ii, wx) in ((2, 1 - dx), (3, dx)):
+                assert rho[kk, jj, ii] == pytest.approx(2.0 * wx * wy * wz, rel=1e-15)
+    assert np.count_nonzero(rho) == 8
+    assert rho.sum() == pytest.approx(2.0, rel=1e-15)
+
+
+@pytest.mark.parametrize("rank", [2, 3])
+def test_kat1b_mass_conservation(rank):
+    dims = (16, 12, 1) if rank == 2 else (8, 12, 10)
+    x, _ = make_particles(2, 5000, rank, clustered=True)
+    rho = np.zeros((dims[2], dims[1], dims[0]))
+    for interp in ("cic", "none"):
+        O.deposit(rho, x.copy(), 0.4, interpolation=interp)
+        assert rho.sum() == pytest.approx(0.4 * 5000, rel=1e-13)
+
+
+def test_kat2_lattice_gives_uniform_density_and_zero_force():
+    """Lattice (i-1/2)/Npd with Npart == Ncell -> rho == m everywhere, phi == 0, acc == 0 (:257-287)."""
+    n = 8
+    x = O.initialize_particles_uniform((n, n, n), 3)
+    f = O.Fields((n, n, n), n ** 3, 3)
+    O.deposit(f.rho, x, 1.5, interpolation="cic")
+    assert np.allclose(f.rho, 1.5, rtol=0, atol=1e-15)
+    O.compute_potential(f.phi, f.rho - f.rho.mean(), f.rt)
+    O.compute_acceleration(f.acc, f.phi)
+    assert np.max(np.abs(f.phi)) < 1e-16 and np.max(np.abs(f.acc)) < 1e-14
+
+
+def test_kat3_single_fourier_mode_is_an_eigenfunction():
+    """rho = cos(2pi n.i/N): phi = rho / (-4 N^2 sum sin^2(pi n_d/N)) (:494-502);
+    acc_d = -N * (phi[+1]-phi[-1])/2 = phi-amplitude * N sin(2pi n_d/N) sin(phase)."""
+    N = 16
+    nx, ny, nz = 2, 3, 1
+    k, j, i = np.meshgrid(np.arange(N), np.arange(N), np.arange(N), indexing="ij")
+    phase = 2 * math.pi * (nx * i + ny * j + nz * k) / N
+    rho = np.cos(phase)
+    phi = np.empty_like(rho)
+    O.compute_potential(phi, rho, np.zeros((N, N, N // 2 + 1), dtype=np.complex128))
+    eig = -4.0 * N ** 2 * sum(math.sin(math.pi * q / N) ** 2 for q in (nx, ny, nz))
+    assert nlinf(phi, rho / eig) < 1e-13
+    acc = np.zeros((N, N, N, 3))
+    O.compute_acceleration(acc, phi)
+    for d, q in enumerate((nx, ny, nz)):
+        want = (1.0 / eig) * N * math.sin(2 * math.pi * q / N) * np.sin(phase)
+        assert nlinf(acc[..., d], want) < 1e-12
+
+
+def test_kat4_discrete_laplacian_of_phi_is_rho():
+    """The solve inverts the 7-point Laplacian times N^2 (deriv2_3d of the reference, :576-628)."""
+    rng = np.random.default_rng(9)
+    N = 16
+    rho = rng.random((N, N, N))
+    rho -= rho.mean()
+    phi = np.empty_like(rho)
+    O.compute_potential(phi, rho, np.zeros((N, N, N // 2 + 1), dtype=np.complex128))
+    lap = sum(np.roll(phi, 1, ax) + np.roll(phi, -1, ax) - 2 * phi for ax in range(3)) * N ** 2
+    assert nlinf(lap, rho) < 1e-12
+
+
+def test_kat5_fd_gradient_equals_spectral_sin_operator():
+    """central difference == multiplication by i sin(k_d) N in k space."""
+    rng = np.random.default_rng(10)
+    N = 12
+    phi = rng.standard_normal((N, N, N))
+    acc = np.zeros((N, N, N, 3))
+    O.compute_acceleration(acc, phi)
+    pk = np.fft.fftn(phi)
+    kk = 2 * math.pi * np.arange(N) / N
+    for d, ax in enumerate((2, 1, 0)):
+        shp = [1, 1, 1]
+        shp[ax] = N
+        want = -np.real(np.fft.ifftn(1j * np.sin(kk).reshape(shp) * N * pk))
+        assert nlinf(acc[..., d], want) < 1e-13
+
+
+def test_kat6_cic_cic_momentum_conservation():
+    """sum_n pa_n ~ 0 for the intended (bug-fixed) back-interpolation with CIC deposit."""
+    npart = 4000
+    x, _ = make_particles(12, npart, 3, clustered=True)
+    O.make_periodic(x)
+    f = O.Fields((16, 16, 16), npart, 3)
+    O.deposit(f.rho, x, 1.0, interpolation="cic")
+    O.compute_potential(f.phi, f.rho - f.rho.mean(), f.rt)
+    O.compute_acceleration(f.acc, f.phi)
+    O.interpVecToPoints(f.pa, f.acc, x, interpolation="cic")
+    assert np.max(np.abs(f.pa.sum(axis=0))) < 1e-10 * np.abs(f.pa).sum()
+
+
+def test_kat7_comoving_kick_without_force():
+    """pa = 0: v_new = v (1 - adot/a dt) (:803-806)."""
+    v = np.array([[0.3, -0.2, 0.1]])
+    v0 = v.copy()
+    O.kick(v, np.zeros_like(v), 0.01, 1.25, 0.7)
+    assert np.allclose(v, v0 * (1 - 0.7 / 1.25 * 0.01), rtol=1e-15, atol=0)
+
+
+def test_kat8_einstein_de_sitter_scalars():
+    """cosmology(h=1,OmegaM=1,OmegaR=0): StartTime = sqrt(2/3), a ~ t^(2/3), adot = sqrt(2/(3a))
+    (cosmology.jl:33,69; the numerical constants of the Enzo unit system agree to ~1e-4)."""
+    c = O.Cosmo(h=1.0, OmegaM=1.0, OmegaR=0.0)
+    zi = 400.0
+    ts, te = O.start_stop_times(c, zi, 9.0)
+    assert ts == pytest.approx(math.sqrt(2.0 / 3.0), rel=2e-4)
+    a1 = O.a_from_t_internal(c, ts, zi, zwherea1=zi)
+    assert a1 == pytest.approx(1.0, rel=1e-10)
+    a2 = O.a_from_t_internal(c, 8 * ts, zi, zwherea1=zi)
+    assert a2 == pytest.approx(4.0, rel=1e-9)
+    assert O.dadt(c, a2, zwherea1=zi) == pytest.approx(math.sqrt(2.0 / (3.0 * a2)), rel=1e-14)
+
+
+def test_make_periodic_single_wrap_and_exact_one():
+    """:409-415 -- single wrap, x == 1.0 untouched, and -1e-17 + 1 creates exactly 1.0."""
+    x = np.array([-0.25, 1.25, 1.0, 0.0, -1e-17, 2.5])
+    O.make_periodic(x)
+    assert x.tolist() == [0.75, 0.25, 1.0, 0.0, 1.0, 1.5]
+
+
+def test_x_equal_one_deposits_into_cell_zero():
+    """index N -> 0 (the documented deviation from the reference's out-of-bounds access)."""
+    rho = np.zeros((4, 4, 4))
+    O.deposit(rho, np.array([[1.0, 1.0, 1.0]]), 1.0, interpolation="cic")
+    assert rho[0, 0, 0] == 1.0 and rho.sum() == 1.0
+
+
+def test_backinterp_bugcompat_differs_from_intended():
+    """F7: the literal :706 index gives k = 0 and dz = x3*N for every x3 in [0,1)."""
+    rng = np.random.default_rng(13)
+    acc = rng.standard_normal((8, 8, 8, 3))
+    x = rng.random((50, 3))
+    a, b = np.zeros((50, 3)), np.zeros((50, 3))
+    O.interpVecToPoints(a, acc, x, interpolation="cic")
+    O.interpVecToPoints(b, acc, x, interpolation="cic", bugcompat=True)
+    assert not np.allclose(a, b)
+    lowz = x.copy()
+    lowz[:, 2] *= 1.0 / 8                     # inside plane 0: both formulas coincide
+    O.interpVecToPoints(a, acc, lowz, interpolation="cic")
+    O.interpVecToPoints(b, acc, lowz, interpolation="cic", bugcompat=True)
+    assert np.allclose(a, b, rtol=1e-14)
+
+
+def test_power_spectrum_of_single_mode():
+    """:65-100 -- delta = A cos(2pi n x): |delta_k|^2 = A^2/4 in the two bins +-n, shell average."""
+    N = 16
+    x = O.initialize_particles_uniform((N, N, N), 3)
+    amp = 0.01 / N
+    x[:, 0] += amp * np.sin(2 * math.pi * 2 * x[:, 0])
+    k, p = O.powerSpectrum(x, 1.0, (N, N, N))
+    assert len(k) == N // 2 and k[0] == pytest.approx(2 * math.pi / N)
+    assert np.nanargmax(p) == 1                 # shell n = round(|k|/dk) = 2 -> index 1
+
+
+def test_evolve_loops_run_and_clamp_final_step():
+    conf = dict(StartTime=0.0, StopTime=0.02, InitialDt=1e-3, CourantFactor=0.5, MaximumDt=5e-3)
+    x, v = O.synthetic_zeldovich((8, 8, 8), 3, 7, 8, 2, 0.2 / 8, 0.5)
+    log = []
+    t, cyc, _ = O.evolvePM(x, v, 1.0, (8, 8, 8), conf, log=log)
+    assert t >= conf["StopTime"] and t == pytest.approx(conf["StopTime"], rel=1e-12)
+    assert cyc == len(log) and all(dt <= 5e-3 * (1 + 1e-12) for (_, dt, _, _) in log)
