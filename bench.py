@@ -134,14 +134,15 @@ def run_cpu(n, mesh, steps, warmup, threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--n", type=int, default=1024, help="particles per dimension")
     ap.add_argument("--mesh", type=int, default=1024, help="mesh cells per dimension")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=192, help="n of the n^3/n^3 CPU-baseline sample (0 = skip)")
-    ap.add_argument("--sort-every", type=int, default=0)
+    ap.add_argument("--sort-every", type=int, default=16,
+                    help="counting-sort cadence in steps; the default K = 16 timed steps contain exactly one sort")
     ap.add_argument("--deposit-mode", default="atomic")
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to nnpm_set_option")
     args = ap.parse_args()
@@ -154,6 +155,7 @@ def main():
     workload = f"{n}^3 particles / {mesh}^3 mesh comoving PM step (LCDM Om=0.3 h=0.7), synthetic Zel'dovich ICs"
     config = {"workload": workload, "particles": n ** 3, "mesh_cells": mesh ** 3, "interpolation": "cic/cic",
               "l2": "inputs (>= 48 B/particle resident state) exceed the 126 MB L2 for n >= 256; no flush needed",
+              "sort_every": args.sort_every, "deposit_mode": args.deposit_mode,
               "parallelism": f"slab{world}" if world > 1 else "single"}
 
     if args.impl == "reference":
@@ -262,7 +264,7 @@ def main():
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             pass
-    roofline = {"bound": "hbm", "kernel": "k_push (gradient + CIC gather + comoving kick + drift + wrap + max reductions)",
+    roofline = {"bound": "hbm", "kernel": "k_push_tile (TMA-staged phi box; gradient + CIC gather + comoving kick + drift + wrap + max reductions)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": push_bytes,
                 "kernel_ms": push_ms, "phase_ms": ms_phase}

@@ -702,11 +702,13 @@ extern "C" int nnpm_kick_comoving(nnpm_ctx* ctx, double dt, double a, double dad
 }
 
 template <int RANK, int INTERP, bool FIXED>
-static void launch_deposit(nnpm_ctx* ctx, bool pre, double c0, u64* viol) {
-  const i64 np = ctx->np;
+static void launch_deposit(nnpm_ctx* ctx, bool pre, double c0, u64* viol, i64 base) {
+  const i64 cnt = ctx->np - base;
   const double fscale = ldexp(1.0, ctx->cfg.fixed_bits);
-  if (pre) k_deposit<RANK, INTERP, FIXED, true><<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->pp, np, c0, ctx->g, ctx->mesh, ctx->m, fscale, viol);
-  else k_deposit<RANK, INTERP, FIXED, false><<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->pp, np, c0, ctx->g, ctx->mesh, ctx->m, fscale, viol);
+  PartPtrs q = ctx->pp;
+  for (int d = 0; d < ctx->R; d++) { q.x[d] += base; q.v[d] += base; }
+  if (pre) k_deposit<RANK, INTERP, FIXED, true><<<nblk(cnt, 256), 256, 0, ctx->st>>>(q, cnt, c0, ctx->g, ctx->mesh, ctx->m, fscale, viol);
+  else k_deposit<RANK, INTERP, FIXED, false><<<nblk(cnt, 256), 256, 0, ctx->st>>>(q, cnt, c0, ctx->g, ctx->mesh, ctx->m, fscale, viol);
 }
 
 // zero + scatter + ghost fold (+ fixed -> f64).  pre: apply x + c0*v on the fly.
@@ -717,11 +719,23 @@ static int do_deposit(nnpm_ctx* ctx, bool pre, double c0) {
   CK(cudaMemsetAsync(ctx->mesh, 0, (size_t)g.plane * g.nplanes * 8, ctx->st));
   LAUNCHED(ctx);
   u64* viol = (u64*)(ctx->d_red + 3);
-  if (ctx->np) {
+  const double fscale = ldexp(1.0, ctx->cfg.fixed_bits);
+  // tile-sorted particles [0, covered): shared-memory tiled scatter; the rest: global atomics
+  i64 covered = 0;
+  if (interp == NNPM_INTERP_CIC && ctx->opt_tile_deposit && ctx->sorted_np > 0 && ctx->np > 0) {
+    covered = ctx->sorted_np < ctx->np ? ctx->sorted_np : ctx->np;
+#define DT(RK, FX, PR) k_deposit_tile<RK, FX, PR><<<(unsigned)ctx->ntiles, 256, 0, ctx->st>>>(ctx->pp, covered, c0, ctx->g, ctx->tg, ctx->hist, ctx->mesh, ctx->m, fscale, viol)
+    if (ctx->R == 3) { if (fixed) { if (pre) DT(3, true, true); else DT(3, true, false); } else { if (pre) DT(3, false, true); else DT(3, false, false); } }
+    else { if (fixed) { if (pre) DT(2, true, true); else DT(2, true, false); } else { if (pre) DT(2, false, true); else DT(2, false, false); } }
+#undef DT
+    LAUNCHED(ctx);
+    KCHECK();
+  }
+  if (ctx->np > covered) {
 #define DEP(RK, IT)                                                                     \
   do {                                                                                  \
-    if (fixed) launch_deposit<RK, IT, true>(ctx, pre, c0, viol);                         \
-    else launch_deposit<RK, IT, false>(ctx, pre, c0, viol);                              \
+    if (fixed) launch_deposit<RK, IT, true>(ctx, pre, c0, viol, covered);                \
+    else launch_deposit<RK, IT, false>(ctx, pre, c0, viol, covered);                     \
   } while (0)
     if (ctx->R == 3) { if (interp) DEP(3, 1); else DEP(3, 0); }
     else { if (interp) DEP(2, 1); else DEP(2, 0); }

@@ -873,28 +873,164 @@ k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g
 #undef PHI
 
 // ------------------------------------------------------------------------------------------
+// K1 tiled deposit (CIC): one CTA per tile of tile-sorted particles.  The tile's particles scatter
+// into a shared-memory box covering cells [-H, T+H+1) around the tile (H = NNPM_TH cells a particle
+// may have strayed since the sort, +1 for the CIC upper neighbour); the box is then flushed to the
+// mesh with one global reduction per box cell -- (T+3)^3/T^3 ~ 2 global atomics per cell instead of
+// 8 per particle.  64-bit shared-memory atomics are compare-and-swap loops on sm_100 (ATOMS.CAST.SPIN
+// for f64 and u64 alike); the box is private to the CTA so contention is limited to particles of one
+// tile that share a cell.  FIXED accumulates llrint(w * 2^B) as integers (order-independent, hence
+// bit-exact run to run); particles outside the box take the global-atomic path directly.
+// ------------------------------------------------------------------------------------------
+#define NNPM_DX (NNPM_TX + 2 * NNPM_TH + 1)
+#define NNPM_DY (NNPM_TY + 2 * NNPM_TH + 1)
+#define NNPM_DZ (NNPM_TZ + 2 * NNPM_TH + 1)
+
+template <int RANK, bool FIXED, bool PRE>
+__global__ void __launch_bounds__(256)
+k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, const uint32_t* __restrict__ tile_off,
+               double* __restrict__ mesh, double m, double fscale, u64* __restrict__ viol) {
+  constexpr int DX = NNPM_DX, DY = NNPM_DY, DZ = (RANK == 3) ? NNPM_DZ : 1, DXY = DX * DY, NBOX = DXY * DZ;
+  __shared__ __align__(16) double box[NBOX];
+  const int t = blockIdx.x;
+  i64 n0 = tile_off[t], n1 = tile_off[t + 1];
+  if (n1 > np) n1 = np;
+  if (n0 >= n1) return;  // uniform across the block
+  for (int c = threadIdx.x; c < NBOX; c += 256) box[c] = 0.0;
+  const int N1 = (int)g.N1, N2 = (int)g.N2, N3 = (int)g.N3;
+  const int ttx = t % tg.ntx, tty = (t / tg.ntx) % tg.nty, ttz = t / (tg.ntx * tg.nty);
+  const int ti0 = ttx * tg.tx, tj0 = tty * tg.ty, tk0 = ttz * tg.tz;
+  const int k0g = (int)g.kz0 + tk0;
+  const int fx = tg.tx + 2 * NNPM_TH, fy = tg.ty + 2 * NNPM_TH, fz = tg.tz + 2 * NNPM_TH;
+  const double mm = FIXED ? 1.0 : m;
+  __syncthreads();
+  auto sadd = [&](int idx, double w) {
+    if (FIXED) atomicAdd((u64*)box + idx, (u64)__double2ll_rn(__dmul_rn(w, fscale)));
+    else atomicAdd(box + idx, w);
+  };
+  auto gadd = [&](i64 idx, double w) {
+    if (FIXED) atomicAdd((u64*)mesh + idx, (u64)__double2ll_rn(__dmul_rn(w, fscale)));
+    else atomicAdd(mesh + idx, w);
+  };
+  for (i64 n = n0 + threadIdx.x; n < n1; n += 256) {
+    double x0 = p.x[0][n], x1 = p.x[1][n], x2 = (RANK == 3) ? p.x[2][n] : 0.0;
+    if (PRE) {
+      x0 = __dadd_rn(x0, __dmul_rn(c0, p.v[0][n]));
+      x1 = __dadd_rn(x1, __dmul_rn(c0, p.v[1][n]));
+      if (RANK == 3) x2 = __dadd_rn(x2, __dmul_rn(c0, p.v[2][n]));
+    }
+    x0 = wrap01(x0);
+    x1 = wrap01(x1);
+    if (RANK == 3) x2 = wrap01(x2);
+    int i, ip, j, jp, k = 0, kp = 0;
+    double dx, dy, dz = 0.0;
+    cell_of32(x0, g.fN1, N1, i, ip, dx);
+    cell_of32(x1, g.fN2, N2, j, jp, dy);
+    if (RANK == 3) cell_of32(x2, g.fN3, N3, k, kp, dz);
+    int ri = i - ti0 + NNPM_TH, rj = j - tj0 + NNPM_TH, rk = 0;
+    ri = ri < 0 ? ri + N1 : (ri >= N1 ? ri - N1 : ri);
+    rj = rj < 0 ? rj + N2 : (rj >= N2 ? rj - N2 : rj);
+    bool fast = ri < fx && rj < fy;
+    if (RANK == 3) {
+      rk = k - k0g + NNPM_TH;
+      rk = rk < 0 ? rk + N3 : (rk >= N3 ? rk - N3 : rk);
+      fast = fast && rk < fz;
+    }
+    // weights in the reference's order  m*(1-dx)*(1-dy)*(1-dz) ...  (ParticleMesh.jl:376-379, 395-402)
+    const double wx0 = __dmul_rn(mm, __dsub_rn(1.0, dx)), wx1 = __dmul_rn(mm, dx);
+    const double ody = __dsub_rn(1.0, dy);
+    const double w00 = __dmul_rn(wx0, ody), w01 = __dmul_rn(wx0, dy), w10 = __dmul_rn(wx1, ody), w11 = __dmul_rn(wx1, dy);
+    if (fast) {
+      const int b = rk * DXY + rj * DX + ri;
+      if (RANK == 2) {
+        sadd(b, w00); sadd(b + DX, w01); sadd(b + 1, w10); sadd(b + DX + 1, w11);
+      } else {
+        const double odz = __dsub_rn(1.0, dz);
+        sadd(b, __dmul_rn(w00, odz)); sadd(b + DX, __dmul_rn(w01, odz));
+        sadd(b + 1, __dmul_rn(w10, odz)); sadd(b + DX + 1, __dmul_rn(w11, odz));
+        sadd(b + DXY, __dmul_rn(w00, dz)); sadd(b + DXY + DX, __dmul_rn(w01, dz));
+        sadd(b + DXY + 1, __dmul_rn(w10, dz)); sadd(b + DXY + DX + 1, __dmul_rn(w11, dz));
+      }
+    } else {  // strayed beyond the box since the sort: straight to the mesh
+      const unsigned r0 = (unsigned)((int)g.rowp * j), r1 = (unsigned)((int)g.rowp * jp);
+      if (RANK == 2) {
+        const i64 off = g.plane * g.glo;
+        gadd(off + (r0 + i), w00); gadd(off + (r1 + i), w01); gadd(off + (r0 + ip), w10); gadd(off + (r1 + ip), w11);
+      } else {
+        const int p0 = local_plane32(k, g), p1 = local_plane32(kp, g);
+        if ((p0 | p1) < 0) { atomicAdd(viol, 1ull); continue; }
+        const double odz = __dsub_rn(1.0, dz);
+        const i64 o0 = g.plane * (i64)p0, o1 = g.plane * (i64)p1;
+        gadd(o0 + (r0 + i), __dmul_rn(w00, odz)); gadd(o0 + (r1 + i), __dmul_rn(w01, odz));
+        gadd(o0 + (r0 + ip), __dmul_rn(w10, odz)); gadd(o0 + (r1 + ip), __dmul_rn(w11, odz));
+        gadd(o1 + (r0 + i), __dmul_rn(w00, dz)); gadd(o1 + (r1 + i), __dmul_rn(w01, dz));
+        gadd(o1 + (r0 + ip), __dmul_rn(w10, dz)); gadd(o1 + (r1 + ip), __dmul_rn(w11, dz));
+      }
+    }
+  }
+  __syncthreads();
+  // flush: box cell (bx,by,bz) -> mesh cell (ti0 - H + bx, tj0 - H + by, k0g - H + bz), periodic
+  const int ex = tg.tx + 2 * NNPM_TH + 1, ey = tg.ty + 2 * NNPM_TH + 1, ez = (RANK == 3) ? tg.tz + 2 * NNPM_TH + 1 : 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int row = warp; row < ey * ez; row += 8) {
+    const int by = row % ey, bz = row / ey;
+    const int gj = wrap_small(tj0 - NNPM_TH + by, N2);
+    int lp = g.glo;
+    if (RANK == 3) {
+      lp = local_plane32(wrap_small(k0g - NNPM_TH + bz, N3), g);
+      if (lp < 0) continue;  // nothing can have been deposited there without a violation being counted
+    }
+    double* dst = mesh + g.plane * (i64)lp + (unsigned)((int)g.rowp * gj);
+    const double* src = box + bz * DXY + by * DX;
+    for (int bx = lane; bx < ex; bx += 32) {
+      const double w = src[bx];
+      if (FIXED) {
+        const u64 q = ((const u64*)src)[bx];
+        if (q) atomicAdd((u64*)dst + wrap_small(ti0 - NNPM_TH + bx, N1), q);
+      } else if (w != 0.0) {
+        atomicAdd(dst + wrap_small(ti0 - NNPM_TH + bx, N1), w);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K0 counting sort by tile of NNPM_TX x NNPM_TY x NNPM_TZ cells (histogram -> scan -> scatter).
 // After the scan `hist` holds the tile offsets the tiled deposit / push kernels index by.
 // ------------------------------------------------------------------------------------------
 template <int RANK>
-__global__ void k_sort_count(PartPtrs p, i64 np, Geom g, TileGeom tg, uint32_t* __restrict__ hist,
-                             uint32_t* __restrict__ key, uint32_t* __restrict__ rnk) {
-  i64 n = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (n >= np) return;
-  int i, j, k, dummy;
-  double d;
-  cell_of32(wrap01(p.x[0][n]), g.fN1, (int)g.N1, i, dummy, d);
-  cell_of32(wrap01(p.x[1][n]), g.fN2, (int)g.N2, j, dummy, d);
-  int kl = 0;
-  if (RANK == 3) {
-    cell_of32(wrap01(p.x[2][n]), g.fN3, (int)g.N3, k, dummy, d);
-    kl = k - (int)g.kz0;
-    if (kl < 0) kl = 0;              // strays (not yet migrated) sort into the boundary tiles
-    if (kl >= (int)g.nzl) kl = (int)g.nzl - 1;
+__global__ void __launch_bounds__(256)
+k_sort_count(PartPtrs p, i64 np, Geom g, TileGeom tg, uint32_t* __restrict__ hist,
+             uint32_t* __restrict__ key, uint32_t* __restrict__ rnk) {
+  const i64 n = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  uint32_t t = 0xFFFFFFFFu;  // lanes past the end form their own group and do nothing
+  if (n < np) {
+    int i, j, k, dummy;
+    double d;
+    cell_of32(wrap01(p.x[0][n]), g.fN1, (int)g.N1, i, dummy, d);
+    cell_of32(wrap01(p.x[1][n]), g.fN2, (int)g.N2, j, dummy, d);
+    int kl = 0;
+    if (RANK == 3) {
+      cell_of32(wrap01(p.x[2][n]), g.fN3, (int)g.N3, k, dummy, d);
+      kl = k - (int)g.kz0;
+      if (kl < 0) kl = 0;              // strays (not yet migrated) sort into the boundary tiles
+      if (kl >= (int)g.nzl) kl = (int)g.nzl - 1;
+    }
+    t = (uint32_t)((i / tg.tx) + tg.ntx * ((j / tg.ty) + tg.nty * (kl / tg.tz)));
   }
-  uint32_t t = (uint32_t)((i / tg.tx) + tg.ntx * ((j / tg.ty) + tg.nty * (kl / tg.tz)));
-  key[n] = t;
-  rnk[n] = atomicAdd(&hist[t], 1u);
+  // warp-aggregated histogram: particles arrive nearly sorted (lattice ICs, previous sorts), so a
+  // warp usually holds one or two distinct tiles -- one atomic per distinct tile instead of 32
+  // same-address atomics.
+  const unsigned peers = __match_any_sync(0xffffffffu, t);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if (lane == leader && n < np) base = atomicAdd(&hist[t], (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  if (n < np) {
+    key[n] = t;
+    rnk[n] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+  }
 }
 
 // exclusive scan of uint32 in three launches (block sums -> scan of sums -> add back)
