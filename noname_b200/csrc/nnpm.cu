@@ -79,7 +79,7 @@ struct nnpm_ctx {
   // cuFFT
   cufftHandle plan2f, plan2b, planz, plan3f, plan3b;
   bool have2, havez, have3;
-  int opt_fft3d, opt_zfused, opt_tile_deposit, opt_tile_push, opt_push_minb;
+  int opt_fft3d, opt_zfused, opt_tile_deposit, opt_tile_push, opt_push_minb, opt_bulk_flush;
   void* fftwork;
   size_t fftwork_bytes;
 
@@ -337,7 +337,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->hist = c->bsum = c->bsum2 = c->skey = c->srnk = nullptr;
   c->have2 = c->havez = c->have3 = false;
   c->have_tmap = false;
-  c->opt_fft3d = 0; c->opt_zfused = 1; c->opt_tile_deposit = 1; c->opt_tile_push = 1; c->opt_push_minb = 2;
+  c->opt_fft3d = 0; c->opt_zfused = 1; c->opt_tile_deposit = 1; c->opt_tile_push = 1; c->opt_push_minb = 2; c->opt_bulk_flush = 1;
   c->fftwork = nullptr; c->fftwork_bytes = 0;
   c->step_count = 0; c->launches = 0;
   c->nccl = nullptr; c->comm = nullptr;
@@ -703,12 +703,17 @@ extern "C" int nnpm_kick_comoving(nnpm_ctx* ctx, double dt, double a, double dad
 
 template <int RANK, int INTERP, bool FIXED>
 static void launch_deposit(nnpm_ctx* ctx, bool pre, double c0, u64* viol, i64 base) {
-  const i64 cnt = ctx->np - base;
+  const i64 cnt = base < 0 ? 0 : ctx->np - base;
   const double fscale = ldexp(1.0, ctx->cfg.fixed_bits);
   PartPtrs q = ctx->pp;
-  for (int d = 0; d < ctx->R; d++) { q.x[d] += base; q.v[d] += base; }
-  if (pre) k_deposit<RANK, INTERP, FIXED, true><<<nblk(cnt, 256), 256, 0, ctx->st>>>(q, cnt, c0, ctx->g, ctx->mesh, ctx->m, fscale, viol);
-  else k_deposit<RANK, INTERP, FIXED, false><<<nblk(cnt, 256), 256, 0, ctx->st>>>(q, cnt, c0, ctx->g, ctx->mesh, ctx->m, fscale, viol);
+  for (int d = 0; d < ctx->R && base > 0; d++) { q.x[d] += base; q.v[d] += base; }
+  const bool stragglers = base < 0;  // the tiled kernel's device-side list instead of a range
+  const uint32_t* list = stragglers ? ctx->srnk : nullptr;
+  const u64* lcount = (const u64*)(ctx->d_red + 5);
+  const unsigned grid = stragglers ? 148 * 4 : nblk(cnt, 256);
+  if (stragglers) q = ctx->pp;
+  if (pre) k_deposit<RANK, INTERP, FIXED, true><<<grid, 256, 0, ctx->st>>>(q, cnt, list, lcount, c0, ctx->g, ctx->mesh, ctx->m, fscale, viol);
+  else k_deposit<RANK, INTERP, FIXED, false><<<grid, 256, 0, ctx->st>>>(q, cnt, list, lcount, c0, ctx->g, ctx->mesh, ctx->m, fscale, viol);
 }
 
 // zero + scatter + ghost fold (+ fixed -> f64).  pre: apply x + c0*v on the fly.
@@ -724,10 +729,16 @@ static int do_deposit(nnpm_ctx* ctx, bool pre, double c0) {
   i64 covered = 0;
   if (interp == NNPM_INTERP_CIC && ctx->opt_tile_deposit && ctx->sorted_np > 0 && ctx->np > 0) {
     covered = ctx->sorted_np < ctx->np ? ctx->sorted_np : ctx->np;
-#define DT(RK, FX, PR) k_deposit_tile<RK, FX, PR><<<(unsigned)ctx->ntiles, 256, 0, ctx->st>>>(ctx->pp, covered, c0, ctx->g, ctx->tg, ctx->hist, ctx->mesh, ctx->m, fscale, viol)
+    CK(cudaMemsetAsync(ctx->d_red + 5, 0, 8, ctx->st));
+    const int bulk = ctx->opt_bulk_flush && (g.N1 % 2 == 0) && g.N1 >= NNPM_DX && ctx->tg.tx == NNPM_TX;
+#define DT(RK, FX, PR) k_deposit_tile<RK, FX, PR><<<(unsigned)ctx->ntiles, 256, 0, ctx->st>>>(ctx->pp, covered, c0, ctx->g, ctx->tg, ctx->hist, ctx->mesh, ctx->m, fscale, ctx->srnk, (u64*)(ctx->d_red + 5), bulk)
     if (ctx->R == 3) { if (fixed) { if (pre) DT(3, true, true); else DT(3, true, false); } else { if (pre) DT(3, false, true); else DT(3, false, false); } }
     else { if (fixed) { if (pre) DT(2, true, true); else DT(2, true, false); } else { if (pre) DT(2, false, true); else DT(2, false, false); } }
 #undef DT
+    LAUNCHED(ctx);
+    // stragglers (device-side count) through the global-atomic kernel
+    if (ctx->R == 3) { if (fixed) launch_deposit<3, 1, true>(ctx, pre, c0, viol, -1); else launch_deposit<3, 1, false>(ctx, pre, c0, viol, -1); }
+    else { if (fixed) launch_deposit<2, 1, true>(ctx, pre, c0, viol, -1); else launch_deposit<2, 1, false>(ctx, pre, c0, viol, -1); }
     LAUNCHED(ctx);
     KCHECK();
   }
@@ -1103,6 +1114,7 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   else if (!strcmp(name, "tile_push")) ctx->opt_tile_push = v;
   else if (!strcmp(name, "push_minb")) ctx->opt_push_minb = v;
   else if (!strcmp(name, "zcols")) ctx->opt_zcols = v;
+  else if (!strcmp(name, "bulk_flush")) ctx->opt_bulk_flush = v;
   else return fail(ctx, NNPM_ERR_ARG, "unknown option '%s'", name);
   return NNPM_OK;
 }

@@ -68,6 +68,24 @@ __device__ __forceinline__ void cell_of32(double x, double fN, int N, int& i0, i
   i0 = z;
   ip = (z == N - 1) ? 0 : z + 1;
 }
+// Branch-free variants for the tiled hot loops.  wrap01_sel == wrap01 bit for bit except that -0.0
+// becomes +0.0; cell_fast returns floor(x*N) in [0, N] un-wrapped (index N, i.e. x == 1.0, is folded
+// by the caller's tile-relative wrap) and the reference's offset d = (x*N - ii) + 1, ii = floor+1.
+__device__ __forceinline__ double wrap01_sel(double x) {
+  x = __dadd_rn(x, __hiloint2double(x < 0. ? 0x3FF00000 : 0, 0));
+  return __dsub_rn(x, __hiloint2double(x > 1. ? 0x3FF00000 : 0, 0));
+}
+__device__ __forceinline__ void cell_fast(double x, double fN, int& i0, double& d) {
+  const double t = __dmul_rn(x, fN);
+  i0 = __double2int_rd(t);
+  d = __dadd_rn(__dsub_rn(t, (double)i0 + 1.0), 1.0);
+}
+__device__ __forceinline__ int tile_rel(int i, int org, int N) {  // i - org folded into [0, N)
+  int r = i - org;
+  r += (r < 0) ? N : 0;
+  r -= (r >= N) ? N : 0;
+  return r;
+}
 __device__ __forceinline__ int local_plane32(int k, const Geom& g) {
   int d = k - (int)g.kz0;
   if (g.glo) {
@@ -184,10 +202,13 @@ __global__ void k_kick_comoving(double* v, const double* pa, double dt, double a
 // ------------------------------------------------------------------------------------------
 template <int RANK, int INTERP, bool FIXED, bool PRE>
 __global__ void __launch_bounds__(256)
-k_deposit(PartPtrs p, i64 np, double c0, Geom g, double* __restrict__ mesh, double m, double fscale,
-          u64* __restrict__ viol) {
-  i64 n = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  if (n >= np) return;
+k_deposit(PartPtrs p, i64 np, const uint32_t* __restrict__ list, const u64* __restrict__ list_count, double c0, Geom g,
+          double* __restrict__ mesh, double m, double fscale, u64* __restrict__ viol) {
+  // work items: particles [0, np), or (list != nullptr) the indices list[0 .. *list_count) -- the
+  // tiled deposit's stragglers -- walked with a grid stride
+  const i64 total = list ? (i64)*list_count : np;
+  for (i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+  const i64 n = list ? (i64)list[t] : t;
   double x0 = p.x[0][n], x1 = p.x[1][n], x2 = (RANK == 3) ? p.x[2][n] : 0.0;
   if (PRE) {
     x0 = __dadd_rn(x0, __dmul_rn(c0, p.v[0][n]));
@@ -220,9 +241,9 @@ k_deposit(PartPtrs p, i64 np, double c0, Geom g, double* __restrict__ mesh, doub
     i = wrap_idx(i, g.N1);
     j = wrap_idx(j, g.N2);
     int pl = (RANK == 3) ? local_plane(k, g) : g.glo;
-    if (pl < 0) { atomicAdd(viol, 1ull); return; }
+    if (pl < 0) { atomicAdd(viol, 1ull); continue; }
     add(i + g.rowp * j + g.plane * pl, FIXED ? 1.0 : m);
-    return;
+    continue;
   }
 
   int i, ip, j, jp;
@@ -239,13 +260,13 @@ k_deposit(PartPtrs p, i64 np, double c0, Geom g, double* __restrict__ mesh, doub
     add(off + (r1 + i), __dmul_rn(wx0, dy));
     add(off + (r0 + ip), __dmul_rn(wx1, ody));
     add(off + (r1 + ip), __dmul_rn(wx1, dy));
-    return;
+    continue;
   }
   int k, kp;
   double dz;
   cell_of32(x2, g.fN3, (int)g.N3, k, kp, dz);
   const int p0 = local_plane32(k, g), p1 = local_plane32(kp, g);
-  if ((p0 | p1) < 0) { atomicAdd(viol, 1ull); return; }
+  if ((p0 | p1) < 0) { atomicAdd(viol, 1ull); continue; }
   const double odz = __dsub_rn(1.0, dz);
   const i64 o0 = g.plane * (i64)p0, o1 = g.plane * (i64)p1;
   // :395-402
@@ -257,6 +278,7 @@ k_deposit(PartPtrs p, i64 np, double c0, Geom g, double* __restrict__ mesh, doub
   add(o1 + (r1 + i), __dmul_rn(__dmul_rn(wx0, dy), dz));
   add(o1 + (r0 + ip), __dmul_rn(__dmul_rn(wx1, ody), dz));
   add(o1 + (r1 + ip), __dmul_rn(__dmul_rn(wx1, dy), dz));
+}
 }
 
 // int64 fixed-point accumulations -> f64 density, in place: rho = m * (Q * 2^-B)
@@ -629,6 +651,21 @@ struct TileGeom {
   int tx, ty, tz;      // tile extent in cells (clamped to the mesh)
 };
 
+// CTA rasterisation for the tiled kernels, 1-D grid of ntx*nty*ntz CTAs: tiles are walked x fastest, then y
+// within bands of NNPM_YB tile rows, then z, then the next band -- so that the halo planes a tile
+// shares with its z neighbour are touched again after NNPM_YB*ntx tiles (a few MB: still in L2)
+// instead of after a whole plane of tiles (~100 MB at 1024^2 cells per plane).
+#define NNPM_YB 8
+__device__ __forceinline__ void tile_of_block(const TileGeom& tg, int& ttx, int& tty, int& ttz) {
+  const int L = blockIdx.x / tg.ntx;
+  ttx = blockIdx.x - L * tg.ntx;
+  const int band = L / (NNPM_YB * tg.ntz);
+  const int rows = min(NNPM_YB, tg.nty - band * NNPM_YB);
+  const int r = L - band * NNPM_YB * tg.ntz;
+  ttz = r / rows;
+  tty = band * NNPM_YB + (r - ttz * rows);
+}
+
 // Fast-path gather: same operator as cic_grad_gather with the products re-associated so that the
 // FP64 pipe (16 lanes per SM sub-partition -- a co-limit of this kernel next to HBM) sees 72
 // instead of 141 operations: corner weights w = wx*wy*wz*(-N1/2) are formed once and shared by
@@ -769,20 +806,15 @@ k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g
   extern __shared__ __align__(128) double box[];  // [BZ][BY][BX]
   __shared__ __align__(8) unsigned long long mbar;
   constexpr int BX = NNPM_BX, BY = NNPM_BY, BZ = (RANK == 3) ? NNPM_BZ : 1, BXY = BX * BY;
-  const int t = blockIdx.x;
-  i64 n0 = tile_off[t], n1 = tile_off[t + 1];
+  int ttx, tty, ttz;
+  tile_of_block(tg, ttx, tty, ttz);
+  const int t = ttx + tg.ntx * (tty + tg.nty * ttz);
+  const i64 n0 = tile_off[t];
+  i64 n1 = tile_off[t + 1];
   if (n1 > np) n1 = np;
   if (n0 >= n1) return;  // uniform across the block
   const int N1 = (int)g.N1, N2 = (int)g.N2, N3 = (int)g.N3;
-  const int ttx = t % tg.ntx, tty = (t / tg.ntx) % tg.nty, ttz = t / (tg.ntx * tg.nty);
   const int ti0 = ttx * tg.tx, tj0 = tty * tg.ty, tk0 = ttz * tg.tz;  // tk0: plane within the slab
-  // first particle's loads go out before the box is staged
-  i64 n = n0 + threadIdx.x;
-  double cx[3], cv[3];
-  if (n < n1) {
-#pragma unroll
-    for (int d = 0; d < RANK; d++) { cx[d] = p.x[d][n]; cv[d] = p.v[d][n]; }
-  }
   // Stage the phi box.  Interior tiles (box inside the mesh, no periodic wrap): ONE TMA tensor copy
   // issued by one thread, completion on an mbarrier.  Tiles whose box wraps: cp.async row by row.
   const int bx0 = ti0 - NNPM_TH - 1, by0 = tj0 - NNPM_TH - 1;
@@ -790,13 +822,11 @@ k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g
   const bool interior = bx0 >= 0 && bx0 + BX - 1 <= N1 && by0 >= 0 && by0 + BY <= N2 &&
                         (RANK == 2 || g.glo != 0 || (bz0 >= 0 && bz0 + BZ <= N3));
   if (interior) {
-    if (threadIdx.x == 0) mbar_init(&mbar, 1);
-    __syncthreads();
     if (threadIdx.x == 0) {
+      mbar_init(&mbar, 1);
       mbar_expect_tx(&mbar, (unsigned)(BX * BY * BZ * sizeof(double)));
       tma_load_3d(box, &tmap, bx0, by0, bz0, &mbar);
     }
-    mbar_wait(&mbar, 0);
   } else {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int gi0 = wrap_small(bx0 + lane, N1);
@@ -822,51 +852,74 @@ k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g
       }
     }
     __pipeline_commit();
-    __pipeline_wait_prior(0);
   }
-  __syncthreads();
+  // the first particle's loads are in flight while the box arrives
+  const double* __restrict__ px0 = p.x[0] + n0;
+  const double* __restrict__ px1 = p.x[1] + n0;
+  const double* __restrict__ px2 = (RANK == 3) ? p.x[2] + n0 : nullptr;
+  const double* __restrict__ pv0 = p.v[0] + n0;
+  const double* __restrict__ pv1 = p.v[1] + n0;
+  const double* __restrict__ pv2 = (RANK == 3) ? p.v[2] + n0 : nullptr;
+  const int cnt = (int)(n1 - n0);
+  // two register sets (A, B) alternate: while one particle is processed the next one's loads are in
+  // flight, without register-to-register copies
+  auto fetch = [&](double* x, double* v, int q) {
+    if (q < cnt) {
+      x[0] = px0[q]; x[1] = px1[q]; v[0] = pv0[q]; v[1] = pv1[q];
+      if (RANK == 3) { x[2] = px2[q]; v[2] = pv2[q]; }
+    }
+  };
+  int q = threadIdx.x;
+  double xa[3] = {0.0, 0.0, 0.0}, va[3] = {0.0, 0.0, 0.0}, xb[3] = {0.0, 0.0, 0.0}, vb[3] = {0.0, 0.0, 0.0};
+  fetch(xa, va, q);
+  if (interior) {
+    __syncthreads();        // mbarrier initialised by thread 0 before anyone polls it
+    mbar_wait(&mbar, 0);
+  } else {
+    __pipeline_wait_prior(0);
+    __syncthreads();
+  }
   const double gfac = -0.5 * g.fN1;
   const double ra = 1.0 / pp.a;
-  const int k0g = (int)g.kz0 + tk0;  // global plane of the tile origin
-  const int fx = tg.tx + 2 * NNPM_TH, fy = tg.ty + 2 * NNPM_TH, fz = tg.tz + 2 * NNPM_TH;
+  const int oi = ti0 - NNPM_TH, oj = tj0 - NNPM_TH, ok = (int)g.kz0 + tk0 - NNPM_TH;  // mesh cell of halo cell 0
+  const unsigned fx = tg.tx + 2 * NNPM_TH, fy = tg.ty + 2 * NNPM_TH, fz = tg.tz + 2 * NNPM_TH;
   double mxa = -INFINITY, mxv = -INFINITY, mxp = -INFINITY;
-  while (n < n1) {
-    double x[3], v[3], pa[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-    for (int d = 0; d < RANK; d++) { x[d] = cx[d]; v[d] = cv[d]; }
-    const i64 nn = n + 256;
-    if (nn < n1) {  // prefetch the next particle of this thread
-#pragma unroll
-      for (int d = 0; d < RANK; d++) { cx[d] = p.x[d][nn]; cv[d] = p.v[d][nn]; }
-    }
+  auto process = [&](double* x, double* v, int q) {
+    double pa[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int d = 0; d < RANK; d++) {
       if (COMOVING) x[d] = __dadd_rn(x[d], __dmul_rn(pp.c0, v[d]));
-      x[d] = wrap01(x[d]);
+      x[d] = wrap01_sel(x[d]);
     }
-    int i, j, k = 0, dummy;
+    int i, j, k = 0;
     double dx, dy, dz = 0.0;
-    cell_of32(x[0], g.fN1, N1, i, dummy, dx);
-    cell_of32(x[1], g.fN2, N2, j, dummy, dy);
-    int ri = i - ti0 + NNPM_TH, rj = j - tj0 + NNPM_TH, rk = 0;
-    ri = ri < 0 ? ri + N1 : (ri >= N1 ? ri - N1 : ri);
-    rj = rj < 0 ? rj + N2 : (rj >= N2 ? rj - N2 : rj);
+    cell_fast(x[0], g.fN1, i, dx);
+    cell_fast(x[1], g.fN2, j, dy);
+    const unsigned ri = (unsigned)tile_rel(i, oi, N1), rj = (unsigned)tile_rel(j, oj, N2);
+    unsigned rk = 0;
     bool fast = ri < fx && rj < fy;
     if (RANK == 3) {
-      cell_of32(x[2], g.fN3, N3, k, dummy, dz);
-      rk = k - k0g + NNPM_TH;
-      rk = rk < 0 ? rk + N3 : (rk >= N3 ? rk - N3 : rk);
+      cell_fast(x[2], g.fN3, k, dz);
+      rk = (unsigned)tile_rel(k, ok, N3);
       fast = fast && rk < fz;
     }
     if (!fast) {
-      slow_list[atomicAdd(slow_count, 1ull)] = (uint32_t)n;
+      slow_list[atomicAdd(slow_count, 1ull)] = (uint32_t)(n0 + q);
     } else {
       const double* b0 = box + (rk * BXY + rj * BX + ri);
       if (RANK == 2) cic_grad_gather_fma<2>([&](int a, int b, int) { return b0[b * BX + a]; }, dx, dy, 0.0, gfac, pa);
       else cic_grad_gather_fma<3>([&](int a, int b, int c) { return b0[c * BXY + b * BX + a]; }, dx, dy, dz, gfac, pa);
-      push_finish_fast<RANK, COMOVING>(p, n, x, v, pa, pp, ra, mxa, mxv, mxp);
+      push_finish_fast<RANK, COMOVING>(p, n0 + q, x, v, pa, pp, ra, mxa, mxv, mxp);
     }
-    n = nn;
+  };
+  while (q < cnt) {
+    fetch(xb, vb, q + 256);
+    process(xa, va, q);
+    q += 256;
+    if (q >= cnt) break;
+    fetch(xa, va, q + 256);
+    process(xb, vb, q);
+    q += 256;
   }
   block_max3(mxa, mxv, mxp, red);
 }
@@ -877,120 +930,151 @@ k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g
 // into a shared-memory box covering cells [-H, T+H+1) around the tile (H = NNPM_TH cells a particle
 // may have strayed since the sort, +1 for the CIC upper neighbour); the box is then flushed to the
 // mesh with one global reduction per box cell -- (T+3)^3/T^3 ~ 2 global atomics per cell instead of
-// 8 per particle.  64-bit shared-memory atomics are compare-and-swap loops on sm_100 (ATOMS.CAST.SPIN
-// for f64 and u64 alike); the box is private to the CTA so contention is limited to particles of one
-// tile that share a cell.  FIXED accumulates llrint(w * 2^B) as integers (order-independent, hence
-// bit-exact run to run); particles outside the box take the global-atomic path directly.
+// 8 per particle.
+//   64-bit shared-memory atomics are compare-and-swap loops on sm_100 (ATOMS.CAST.SPIN, for f64 and
+// u64 alike; measured slower than the global REDG path), so the box accumulates unit-mass weights in
+// 64-bit fixed point (2^-B resolution, B = fixed_bits) built from NATIVE 32-bit shared atomics: add
+// the low word (ATOMS.ADD returning the old value), derive the carry, add high word + carry.  The
+// sum is exact integer arithmetic, hence independent of the order of the adds.
+//   FIXED : the flush adds the integers into the int64 mesh (bit-exact run to run, and identical to
+//           the global fixed-point path);  otherwise the flush converts to m * q * 2^-B and uses
+//           f64 global reductions.  Particles outside the box take the global-atomic path directly.
 // ------------------------------------------------------------------------------------------
-#define NNPM_DX (NNPM_TX + 2 * NNPM_TH + 1)
+#define NNPM_DX (NNPM_TX + 2 * NNPM_TH + 2)  // box x origin = tile origin - H - 1: even, so rows are 16-byte aligned
 #define NNPM_DY (NNPM_TY + 2 * NNPM_TH + 1)
 #define NNPM_DZ (NNPM_TZ + 2 * NNPM_TH + 1)
 
+// bulk asynchronous reduction shared -> global (TMA engine): dst[0..n) += src[0..n), n*8 bytes, both
+// 16-byte aligned.  PTX ISA 8.0+, sm_90+: cp.reduce.async.bulk ... .add.f64 / .add.u64
+template <bool FIXED>
+__device__ __forceinline__ void bulk_reduce_add(void* gdst, const void* ssrc, unsigned bytes) {
+  if (FIXED)
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+  else
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+
+// BULK: flush rows with cp.reduce.async.bulk (needs N1 even and >= NNPM_DX); otherwise per-cell atomics.
 template <int RANK, bool FIXED, bool PRE>
 __global__ void __launch_bounds__(256)
 k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, const uint32_t* __restrict__ tile_off,
-               double* __restrict__ mesh, double m, double fscale, u64* __restrict__ viol) {
+               double* __restrict__ mesh, double m, double fscale, uint32_t* __restrict__ slow_list,
+               u64* __restrict__ slow_count, int bulk) {
   constexpr int DX = NNPM_DX, DY = NNPM_DY, DZ = (RANK == 3) ? NNPM_DZ : 1, DXY = DX * DY, NBOX = DXY * DZ;
-  __shared__ __align__(16) double box[NBOX];
-  const int t = blockIdx.x;
-  i64 n0 = tile_off[t], n1 = tile_off[t + 1];
+  // accumulators: little-endian (lo, hi) uint32 pairs == one u64 per cell; converted in place to f64
+  __shared__ __align__(16) uint32_t acc[2 * NBOX];
+  int ttx, tty, ttz;
+  tile_of_block(tg, ttx, tty, ttz);
+  const int t = ttx + tg.ntx * (tty + tg.nty * ttz);
+  const i64 n0 = tile_off[t];
+  i64 n1 = tile_off[t + 1];
   if (n1 > np) n1 = np;
   if (n0 >= n1) return;  // uniform across the block
-  for (int c = threadIdx.x; c < NBOX; c += 256) box[c] = 0.0;
+  for (int c = threadIdx.x; c < NBOX / 2; c += 256) ((uint4*)acc)[c] = make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x == 0 && (NBOX & 1)) { acc[2 * NBOX - 2] = 0u; acc[2 * NBOX - 1] = 0u; }
   const int N1 = (int)g.N1, N2 = (int)g.N2, N3 = (int)g.N3;
-  const int ttx = t % tg.ntx, tty = (t / tg.ntx) % tg.nty, ttz = t / (tg.ntx * tg.nty);
-  const int ti0 = ttx * tg.tx, tj0 = tty * tg.ty, tk0 = ttz * tg.tz;
-  const int k0g = (int)g.kz0 + tk0;
-  const int fx = tg.tx + 2 * NNPM_TH, fy = tg.ty + 2 * NNPM_TH, fz = tg.tz + 2 * NNPM_TH;
-  const double mm = FIXED ? 1.0 : m;
+  const int bi0 = ttx * tg.tx - NNPM_TH - 1, bj0 = tty * tg.ty - NNPM_TH;  // mesh cell of box cell (0,0,0)
+  const int bk0 = (int)g.kz0 + ttz * tg.tz - NNPM_TH;                       // global plane
+  const unsigned fx = tg.tx + 2 * NNPM_TH, fy = tg.ty + 2 * NNPM_TH, fz = tg.tz + 2 * NNPM_TH;
+  const double* __restrict__ px0 = p.x[0] + n0;
+  const double* __restrict__ px1 = p.x[1] + n0;
+  const double* __restrict__ px2 = (RANK == 3) ? p.x[2] + n0 : nullptr;
+  const double* __restrict__ pv0 = p.v[0] + n0;
+  const double* __restrict__ pv1 = p.v[1] + n0;
+  const double* __restrict__ pv2 = (RANK == 3) ? p.v[2] + n0 : nullptr;
+  const int cnt = (int)(n1 - n0);
   __syncthreads();
+  // 64-bit fixed-point add from two native 32-bit shared atomics (the low word returns the old value)
   auto sadd = [&](int idx, double w) {
-    if (FIXED) atomicAdd((u64*)box + idx, (u64)__double2ll_rn(__dmul_rn(w, fscale)));
-    else atomicAdd(box + idx, w);
+    const u64 q = (u64)__double2ll_rn(w);
+    const uint32_t lo = (uint32_t)q;
+    const uint32_t old = atomicAdd(&acc[2 * idx], lo);
+    atomicAdd(&acc[2 * idx + 1], (uint32_t)(q >> 32) + (old > ~lo ? 1u : 0u));
   };
-  auto gadd = [&](i64 idx, double w) {
-    if (FIXED) atomicAdd((u64*)mesh + idx, (u64)__double2ll_rn(__dmul_rn(w, fscale)));
-    else atomicAdd(mesh + idx, w);
-  };
-  for (i64 n = n0 + threadIdx.x; n < n1; n += 256) {
-    double x0 = p.x[0][n], x1 = p.x[1][n], x2 = (RANK == 3) ? p.x[2][n] : 0.0;
+  for (int q = threadIdx.x; q < cnt; q += 256) {
+    double x0 = px0[q], x1 = px1[q], x2 = (RANK == 3) ? px2[q] : 0.0;
     if (PRE) {
-      x0 = __dadd_rn(x0, __dmul_rn(c0, p.v[0][n]));
-      x1 = __dadd_rn(x1, __dmul_rn(c0, p.v[1][n]));
-      if (RANK == 3) x2 = __dadd_rn(x2, __dmul_rn(c0, p.v[2][n]));
+      x0 = __dadd_rn(x0, __dmul_rn(c0, pv0[q]));
+      x1 = __dadd_rn(x1, __dmul_rn(c0, pv1[q]));
+      if (RANK == 3) x2 = __dadd_rn(x2, __dmul_rn(c0, pv2[q]));
     }
-    x0 = wrap01(x0);
-    x1 = wrap01(x1);
-    if (RANK == 3) x2 = wrap01(x2);
-    int i, ip, j, jp, k = 0, kp = 0;
+    int i, j, k = 0;
     double dx, dy, dz = 0.0;
-    cell_of32(x0, g.fN1, N1, i, ip, dx);
-    cell_of32(x1, g.fN2, N2, j, jp, dy);
-    if (RANK == 3) cell_of32(x2, g.fN3, N3, k, kp, dz);
-    int ri = i - ti0 + NNPM_TH, rj = j - tj0 + NNPM_TH, rk = 0;
-    ri = ri < 0 ? ri + N1 : (ri >= N1 ? ri - N1 : ri);
-    rj = rj < 0 ? rj + N2 : (rj >= N2 ? rj - N2 : rj);
-    bool fast = ri < fx && rj < fy;
+    cell_fast(wrap01_sel(x0), g.fN1, i, dx);
+    cell_fast(wrap01_sel(x1), g.fN2, j, dy);
+    const unsigned ri = (unsigned)tile_rel(i, bi0, N1), rj = (unsigned)tile_rel(j, bj0, N2);
+    unsigned rk = 0;
+    bool fast = (ri - 1u) < fx && rj < fy;   // box column 0 is alignment padding
     if (RANK == 3) {
-      rk = k - k0g + NNPM_TH;
-      rk = rk < 0 ? rk + N3 : (rk >= N3 ? rk - N3 : rk);
+      cell_fast(wrap01_sel(x2), g.fN3, k, dz);
+      rk = (unsigned)tile_rel(k, bk0, N3);
       fast = fast && rk < fz;
     }
-    // weights in the reference's order  m*(1-dx)*(1-dy)*(1-dz) ...  (ParticleMesh.jl:376-379, 395-402)
-    const double wx0 = __dmul_rn(mm, __dsub_rn(1.0, dx)), wx1 = __dmul_rn(mm, dx);
+    if (!fast) {  // strayed beyond the box since the sort: the global-atomic kernel takes it
+      slow_list[atomicAdd(slow_count, 1ull)] = (uint32_t)(n0 + q);
+      continue;
+    }
+    // unit-mass weights in the reference's order (1-dx)*(1-dy)*(1-dz) ... (ParticleMesh.jl:376-379,
+    // :395-402), pre-scaled by 2^B (exact: a power of two commutes with every rounding)
+    const double wx0 = __dmul_rn(__dsub_rn(1.0, dx), fscale), wx1 = __dmul_rn(dx, fscale);
     const double ody = __dsub_rn(1.0, dy);
     const double w00 = __dmul_rn(wx0, ody), w01 = __dmul_rn(wx0, dy), w10 = __dmul_rn(wx1, ody), w11 = __dmul_rn(wx1, dy);
-    if (fast) {
-      const int b = rk * DXY + rj * DX + ri;
-      if (RANK == 2) {
-        sadd(b, w00); sadd(b + DX, w01); sadd(b + 1, w10); sadd(b + DX + 1, w11);
-      } else {
-        const double odz = __dsub_rn(1.0, dz);
-        sadd(b, __dmul_rn(w00, odz)); sadd(b + DX, __dmul_rn(w01, odz));
-        sadd(b + 1, __dmul_rn(w10, odz)); sadd(b + DX + 1, __dmul_rn(w11, odz));
-        sadd(b + DXY, __dmul_rn(w00, dz)); sadd(b + DXY + DX, __dmul_rn(w01, dz));
-        sadd(b + DXY + 1, __dmul_rn(w10, dz)); sadd(b + DXY + DX + 1, __dmul_rn(w11, dz));
-      }
-    } else {  // strayed beyond the box since the sort: straight to the mesh
-      const unsigned r0 = (unsigned)((int)g.rowp * j), r1 = (unsigned)((int)g.rowp * jp);
-      if (RANK == 2) {
-        const i64 off = g.plane * g.glo;
-        gadd(off + (r0 + i), w00); gadd(off + (r1 + i), w01); gadd(off + (r0 + ip), w10); gadd(off + (r1 + ip), w11);
-      } else {
-        const int p0 = local_plane32(k, g), p1 = local_plane32(kp, g);
-        if ((p0 | p1) < 0) { atomicAdd(viol, 1ull); continue; }
-        const double odz = __dsub_rn(1.0, dz);
-        const i64 o0 = g.plane * (i64)p0, o1 = g.plane * (i64)p1;
-        gadd(o0 + (r0 + i), __dmul_rn(w00, odz)); gadd(o0 + (r1 + i), __dmul_rn(w01, odz));
-        gadd(o0 + (r0 + ip), __dmul_rn(w10, odz)); gadd(o0 + (r1 + ip), __dmul_rn(w11, odz));
-        gadd(o1 + (r0 + i), __dmul_rn(w00, dz)); gadd(o1 + (r1 + i), __dmul_rn(w01, dz));
-        gadd(o1 + (r0 + ip), __dmul_rn(w10, dz)); gadd(o1 + (r1 + ip), __dmul_rn(w11, dz));
-      }
+    const int b = (int)(rk * DXY + rj * DX + ri);
+    if (RANK == 2) {
+      sadd(b, w00); sadd(b + DX, w01); sadd(b + 1, w10); sadd(b + DX + 1, w11);
+    } else {
+      const double odz = __dsub_rn(1.0, dz);
+      sadd(b, __dmul_rn(w00, odz)); sadd(b + DX, __dmul_rn(w01, odz));
+      sadd(b + 1, __dmul_rn(w10, odz)); sadd(b + DX + 1, __dmul_rn(w11, odz));
+      sadd(b + DXY, __dmul_rn(w00, dz)); sadd(b + DXY + DX, __dmul_rn(w01, dz));
+      sadd(b + DXY + 1, __dmul_rn(w10, dz)); sadd(b + DXY + DX + 1, __dmul_rn(w11, dz));
     }
   }
   __syncthreads();
-  // flush: box cell (bx,by,bz) -> mesh cell (ti0 - H + bx, tj0 - H + by, k0g - H + bz), periodic
-  const int ex = tg.tx + 2 * NNPM_TH + 1, ey = tg.ty + 2 * NNPM_TH + 1, ez = (RANK == 3) ? tg.tz + 2 * NNPM_TH + 1 : 1;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int row = warp; row < ey * ez; row += 8) {
-    const int by = row % ey, bz = row / ey;
-    const int gj = wrap_small(tj0 - NNPM_TH + by, N2);
+  // flush: box cell (bx,by,bz) -> mesh cell (bi0 + bx, bj0 + by, bk0 + bz), periodic.  Box extents are
+  // <= N + 3, so one fold brings every coordinate into [0, N).
+  const int ey = tg.ty + 2 * NNPM_TH + 1, ez = (RANK == 3) ? tg.tz + 2 * NNPM_TH + 1 : 1;
+  const double inv_scale = 1.0 / fscale;  // exact: fscale = 2^B
+  u64* acc64 = (u64*)acc;
+  if (bulk) {
+    if (!FIXED) {  // integers -> m * q * 2^-B, in place
+      for (int c = threadIdx.x; c < NBOX; c += 256)
+        ((double*)acc)[c] = __dmul_rn(m, __dmul_rn((double)(i64)acc64[c], inv_scale));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async-proxy reads
+    __syncthreads();
+    const int row = threadIdx.x;  // one row (DX cells, 16-byte aligned) per thread: one or two bulk reductions
+    if (row < ey * ez) {
+      const int by = row % ey, bz = row / ey;
+      int lp = g.glo;
+      if (RANK == 3) lp = local_plane32(tile_rel(bk0 + bz, 0, N3), g);
+      if (lp >= 0) {
+        double* drow = mesh + g.plane * (i64)lp + (unsigned)((int)g.rowp * tile_rel(bj0 + by, 0, N2));
+        const double* srow = (const double*)acc + (bz * DXY + by * DX);
+        const int start = tile_rel(bi0, 0, N1);                 // even: bi0 and N1 are even
+        const int len1 = (N1 - start) < DX ? (N1 - start) : DX;  // cells before the periodic wrap
+        bulk_reduce_add<FIXED>(drow + start, srow, (unsigned)len1 * 8u);
+        if (len1 < DX) bulk_reduce_add<FIXED>(drow, srow + len1, (unsigned)(DX - len1) * 8u);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the reads
+    }
+    return;
+  }
+  const int ex = tg.tx + 2 * NNPM_TH + 2;
+  for (int c = threadIdx.x; c < NBOX; c += 256) {
+    const u64 q = acc64[c];
+    if (!q) continue;
+    const int bx = c % DX, by = (c / DX) % DY, bz = c / DXY;  // compile-time divisors
+    if (bx >= ex || by >= ey || bz >= ez) continue;
     int lp = g.glo;
     if (RANK == 3) {
-      lp = local_plane32(wrap_small(k0g - NNPM_TH + bz, N3), g);
-      if (lp < 0) continue;  // nothing can have been deposited there without a violation being counted
+      lp = local_plane32(tile_rel(bk0 + bz, 0, N3), g);
+      if (lp < 0) continue;  // cannot hold mass: such a particle went to the slow list
     }
-    double* dst = mesh + g.plane * (i64)lp + (unsigned)((int)g.rowp * gj);
-    const double* src = box + bz * DXY + by * DX;
-    for (int bx = lane; bx < ex; bx += 32) {
-      const double w = src[bx];
-      if (FIXED) {
-        const u64 q = ((const u64*)src)[bx];
-        if (q) atomicAdd((u64*)dst + wrap_small(ti0 - NNPM_TH + bx, N1), q);
-      } else if (w != 0.0) {
-        atomicAdd(dst + wrap_small(ti0 - NNPM_TH + bx, N1), w);
-      }
-    }
+    double* dst = mesh + g.plane * (i64)lp + (unsigned)((int)g.rowp * tile_rel(bj0 + by, 0, N2)) + tile_rel(bi0 + bx, 0, N1);
+    if (FIXED) atomicAdd((u64*)dst, q);
+    else atomicAdd(dst, __dmul_rn(m, __dmul_rn((double)(i64)q, inv_scale)));
   }
 }
 
