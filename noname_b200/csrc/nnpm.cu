@@ -105,6 +105,12 @@ struct nnpm_ctx {
   double* pk_buf;
   double2* ztw;  // z-FFT twiddles W_N3^m
   int opt_zcols;
+  // NVLink peer-memory transposes (nranks > 1): every rank's mesh / meshT mapped through CUDA IPC
+  double* peer_mesh[64];
+  double* peer_meshT[64];
+  bool peer_ok;
+  int opt_peer;
+  int* bar_buf;
 };
 
 static thread_local std::string g_create_err;
@@ -345,6 +351,8 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->last_migrated = 0;
   c->pk_buf = nullptr;
   c->ztw = nullptr; c->opt_zcols = 8;
+  for (int i = 0; i < 64; i++) { c->peer_mesh[i] = nullptr; c->peer_meshT[i] = nullptr; }
+  c->peer_ok = false; c->opt_peer = 1; c->bar_buf = nullptr;
   c->mig_lo = nullptr; c->ghost_rx = nullptr; c->red_buf = nullptr;
   c->np = 0; c->m = 0.0; c->ids_dirty = false; c->field_state = 0;
   c->own_stream = false;
@@ -1115,6 +1123,7 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   else if (!strcmp(name, "push_minb")) ctx->opt_push_minb = v;
   else if (!strcmp(name, "zcols")) ctx->opt_zcols = v;
   else if (!strcmp(name, "bulk_flush")) ctx->opt_bulk_flush = v;
+  else if (!strcmp(name, "peer_transpose")) ctx->opt_peer = v;
   else return fail(ctx, NNPM_ERR_ARG, "unknown option '%s'", name);
   return NNPM_OK;
 }

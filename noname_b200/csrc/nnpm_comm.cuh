@@ -88,6 +88,48 @@ extern "C" int nnpm_comm_unique_id(uint8_t id_out[128]) {
 
 static const int MIG_REC = 7;  // doubles per migrating particle record: x[3], v[3], id bits
 
+static int comm_allreduce(nnpm_ctx* ctx, double* host, int n, ncclRedOp_t op);
+
+// Map every rank's mesh and meshT into this process (CUDA IPC) so that the slab transposes can store
+// straight into the peers' buffers over NVLink.  All ranks agree (allreduce-min) on whether it worked;
+// if not, the grouped ncclSend/ncclRecv all-to-all is used.
+static int peer_setup(nnpm_ctx* ctx) {
+  const int P = ctx->P, r = ctx->r;
+  ctx->peer_ok = false;
+  if (getenv("NNPM_NO_PEER")) return NNPM_OK;
+  struct Rec { cudaIpcMemHandle_t mesh, meshT; };
+  static_assert(sizeof(Rec) == 128, "two 64-byte IPC handles");
+  Rec mine;
+  int ok = 1;
+  if (cudaIpcGetMemHandle(&mine.mesh, ctx->mesh) != cudaSuccess) ok = 0;
+  if (cudaIpcGetMemHandle(&mine.meshT, ctx->meshT) != cudaSuccess) ok = 0;
+  cudaGetLastError();
+  uint8_t* d_all = nullptr;
+  CKR(dalloc(ctx, &d_all, (size_t)128 * (P + 1)));
+  CK(cudaMemcpyAsync(d_all + 128 * P, &mine, 128, cudaMemcpyHostToDevice, ctx->st));
+  CKN(ctx->nccl->AllGather(d_all + 128 * P, d_all, 128, ncclUint8, COMM, ctx->st));
+  std::vector<Rec> all((size_t)P);
+  CK(cudaMemcpyAsync(all.data(), d_all, (size_t)128 * P, cudaMemcpyDeviceToHost, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  for (int d = 0; d < P && ok; d++) {
+    if (d == r) { ctx->peer_mesh[d] = ctx->mesh; ctx->peer_meshT[d] = ctx->meshT; continue; }
+    void *pm = nullptr, *pt = nullptr;
+    if (cudaIpcOpenMemHandle(&pm, all[d].mesh, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&pt, all[d].meshT, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      ok = 0;
+      cudaGetLastError();
+      break;
+    }
+    ctx->peer_mesh[d] = (double*)pm;
+    ctx->peer_meshT[d] = (double*)pt;
+  }
+  double flag = ok ? 1.0 : 0.0;
+  CKR(comm_allreduce(ctx, &flag, 1, ncclMin));
+  ctx->peer_ok = flag > 0.5;
+  if (getenv("NNPM_VERBOSE")) fprintf(stderr, "[nnpm] rank %d: NVLink peer-memory transposes %s\n", r, ctx->peer_ok ? "enabled" : "unavailable (NCCL send/recv)");
+  return NNPM_OK;
+}
+
 extern "C" int nnpm_comm_init(nnpm_ctx* ctx, const uint8_t id[128]) {
   if (!ctx || !id) return NNPM_ERR_ARG;
   if (ctx->P == 1) return NNPM_OK;
@@ -111,10 +153,19 @@ extern "C" int nnpm_comm_init(nnpm_ctx* ctx, const uint8_t id[128]) {
   CKR(dalloc(ctx, &ctx->mig_holes, (size_t)ctx->mig_cap));
   CKR(dalloc(ctx, &ctx->mig_lo, (size_t)ctx->mig_cap));
   CKR(dalloc(ctx, &ctx->mig_cnt, (size_t)(80 + 64)));  // [0..P) per-dest counts, [16] holes, [17] overflow, [18] nlo, [19] nfill, [24..) scratch, [80..) allgather
+  CKR(dalloc(ctx, &ctx->bar_buf, 4));
+  CK(cudaMemsetAsync(ctx->bar_buf, 0, 16, ctx->st));
+  CKR(peer_setup(ctx));
   return NNPM_OK;
 }
 
 static void comm_destroy(nnpm_ctx* ctx) {
+  for (int d = 0; d < ctx->P && d < 64; d++) {
+    if (d == ctx->r) continue;
+    if (ctx->peer_mesh[d]) cudaIpcCloseMemHandle(ctx->peer_mesh[d]);
+    if (ctx->peer_meshT[d]) cudaIpcCloseMemHandle(ctx->peer_meshT[d]);
+    ctx->peer_mesh[d] = ctx->peer_meshT[d] = nullptr;
+  }
   if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(COMM);
   ctx->comm = nullptr;
 }
@@ -191,9 +242,49 @@ static int comm_all_to_all(nnpm_ctx* ctx, const double* src, double* dst) {
   return NNPM_OK;
 }
 
+// ---- fused pack + all-to-all over NVLink peer memory -------------------------------------------
+// forward:  A[kl][j][ic] (this rank's planes, all j) is stored straight into the owner of row block
+//           d = j / njl:  T_d[kz0 + kl][jl][ic].   backward:  T[k][jl][ic] (all k, this rank's j block)
+//           goes to the owner of plane k:  A_d[kl][j0 + jl][ic].  One kernel reads local HBM once and
+//           writes the remote (or local) destination once -- no staging buffer, no pack/unpack pass.
+struct PeerPtrs { double2* p[64]; };
+__global__ void __launch_bounds__(128)
+k_transpose_fwd_peer(const double2* __restrict__ A, PeerPtrs T, int icn, int njl, int nzl, i64 aplane_c, int kz0) {
+  const int j = blockIdx.y, kl = blockIdx.z;
+  const int d = j / njl, jl = j - d * njl;
+  const double2* src = A + (i64)icn * j + aplane_c * kl;
+  double2* dst = T.p[d] + (i64)icn * (jl + (i64)njl * (kz0 + kl));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < icn; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void __launch_bounds__(128)
+k_transpose_bwd_peer(PeerPtrs A, const double2* __restrict__ T, int icn, int njl, int nzl, i64 aplane_c, int j0) {
+  const int jl = blockIdx.y, k = blockIdx.z;
+  const int d = k / nzl, kl = k - d * nzl;
+  const double2* src = T + (i64)icn * (jl + (i64)njl * k);
+  double2* dst = A.p[d] + (i64)icn * (j0 + jl) + aplane_c * kl;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < icn; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+// stream-ordered barrier over all ranks: remote stores of the kernels before it are complete (kernel
+// boundary) before any rank's later work starts
+static int comm_barrier(nnpm_ctx* ctx) {
+  CKN(ctx->nccl->AllReduce(ctx->bar_buf, ctx->bar_buf, 1, ncclInt32, ncclSum, COMM, ctx->st));
+  ctx->launches += 1;
+  return NNPM_OK;
+}
+
 static int comm_transpose_fwd(nnpm_ctx* ctx) {
   NEED_COMM();
   const Geom& g = ctx->g;
+  if (ctx->peer_ok && ctx->opt_peer) {
+    PeerPtrs T;
+    for (int d = 0; d < ctx->P; d++) T.p[d] = (double2*)ctx->peer_meshT[d];
+    dim3 grid(nblk(ctx->icn, 256), (unsigned)g.N2, (unsigned)g.nzl);
+    k_transpose_fwd_peer<<<grid, 128, 0, ctx->st>>>((const double2*)(ctx->mesh + g.plane * g.glo), T, (int)ctx->icn, (int)ctx->njl,
+                                                    (int)g.nzl, g.plane / 2, (int)g.kz0);
+    LAUNCHED(ctx);
+    KCHECK();
+    return comm_barrier(ctx);
+  }
   const double2* A = (const double2*)(ctx->mesh + g.plane * g.glo);
   dim3 grid(nblk(ctx->icn, 128), (unsigned)g.N2, (unsigned)g.nzl);
   k_pack_fwd<<<grid, 128, 0, ctx->st>>>(A, (double2*)ctx->meshS, ctx->icn, g.N2, ctx->njl, g.nzl, g.plane / 2);
@@ -205,6 +296,16 @@ static int comm_transpose_fwd(nnpm_ctx* ctx) {
 static int comm_transpose_bwd(nnpm_ctx* ctx) {
   NEED_COMM();
   const Geom& g = ctx->g;
+  if (ctx->peer_ok && ctx->opt_peer) {
+    PeerPtrs A;
+    for (int d = 0; d < ctx->P; d++) A.p[d] = (double2*)(ctx->peer_mesh[d] + g.plane * g.glo);
+    dim3 grid(nblk(ctx->icn, 256), (unsigned)ctx->njl, (unsigned)g.N3);
+    k_transpose_bwd_peer<<<grid, 128, 0, ctx->st>>>(A, (const double2*)ctx->meshT, (int)ctx->icn, (int)ctx->njl, (int)g.nzl,
+                                                    g.plane / 2, (int)(ctx->njl * ctx->r));
+    LAUNCHED(ctx);
+    KCHECK();
+    return comm_barrier(ctx);
+  }
   CKR(comm_all_to_all(ctx, ctx->meshT, ctx->meshS));
   double2* A = (double2*)(ctx->mesh + g.plane * g.glo);
   dim3 grid(nblk(ctx->icn, 128), (unsigned)g.N2, (unsigned)g.nzl);

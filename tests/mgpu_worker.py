@@ -37,8 +37,10 @@ def main():
         if not ok:
             errs.append(f"rank {rank}: {name} FAILED {detail}")
 
-    for mode in ("atomic", "fixedpoint"):
-        dev = DevicePM(dims, npart, rank=3, device=lr, nranks=P, rank_id=rank, deposit_mode=mode, timing=True)
+    # (deposit mode, sort cadence): sort_every > 0 runs the tiled shared-memory deposit / push on slabs
+    for mode, sort_every in (("atomic", 0), ("fixedpoint", 0), ("atomic", 1), ("fixedpoint", 2)):
+        dev = DevicePM(dims, npart, rank=3, device=lr, nranks=P, rank_id=rank, deposit_mode=mode, timing=True,
+                       sort_every=sort_every)
         uid = [DevicePM.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         dev.comm_init(uid[0])
@@ -97,7 +99,7 @@ def main():
         ok = np.isfinite(pr)
         check("P(k)", np.max(np.abs(pg[ok] / pr[ok] - 1)) < 1e-6)
         if rank == 0:
-            print(f"[mgpu P={P} {mode}] migrated(last step, all ranks)={int(cnt[1].item())} ms={st.as_dict()['ms']}")
+            print(f"[mgpu P={P} {mode} sort_every={sort_every}] untiled={st.n_untiled} migrated(last step, all ranks)={int(cnt[1].item())} ms={st.as_dict()['ms']}")
         dev.close()
 
     # device-generated ICs agree across decompositions
