@@ -109,8 +109,10 @@ struct nnpm_ctx {
   double* peer_mesh[64];
   double* peer_meshT[64];
   bool peer_ok;
-  int opt_peer;
+  int opt_peer;   // 0 = NCCL send/recv, 1 = copy-engine peer copies (default), 2 = remote-store kernels
   int* bar_buf;
+  cudaStream_t st2[4];    // side streams: the blocks of a transpose go out on several copy engines at once
+  cudaEvent_t ev_fork, ev_join[4];
 };
 
 static thread_local std::string g_create_err;
@@ -353,6 +355,8 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->ztw = nullptr; c->opt_zcols = 8;
   for (int i = 0; i < 64; i++) { c->peer_mesh[i] = nullptr; c->peer_meshT[i] = nullptr; }
   c->peer_ok = false; c->opt_peer = 1; c->bar_buf = nullptr;
+  c->ev_fork = nullptr;
+  for (int i = 0; i < 4; i++) { c->st2[i] = nullptr; c->ev_join[i] = nullptr; }
   c->mig_lo = nullptr; c->ghost_rx = nullptr; c->red_buf = nullptr;
   c->np = 0; c->m = 0.0; c->ids_dirty = false; c->field_state = 0;
   c->own_stream = false;

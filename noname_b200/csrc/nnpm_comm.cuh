@@ -152,10 +152,15 @@ extern "C" int nnpm_comm_init(nnpm_ctx* ctx, const uint8_t id[128]) {
   CKR(dalloc(ctx, &ctx->mig_recv, (size_t)ctx->mig_cap * MIG_REC));
   CKR(dalloc(ctx, &ctx->mig_holes, (size_t)ctx->mig_cap));
   CKR(dalloc(ctx, &ctx->mig_lo, (size_t)ctx->mig_cap));
-  CKR(dalloc(ctx, &ctx->mig_cnt, (size_t)(80 + 64)));  // [0..P) per-dest counts, [16] holes, [17] overflow, [18] nlo, [19] nfill, [24..) scratch, [80..) allgather
+  CKR(dalloc(ctx, &ctx->mig_cnt, (size_t)(80 + 24 * 64)));  // [0..P) per-dest counts, [16] holes, [17] overflow, [18] nlo, [19] nfill, [24..) scratch, [80..) allgather
   CKR(dalloc(ctx, &ctx->bar_buf, 4));
   CK(cudaMemsetAsync(ctx->bar_buf, 0, 16, ctx->st));
   CKR(peer_setup(ctx));
+  CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 4; i++) {
+    CK(cudaStreamCreateWithFlags(&ctx->st2[i], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+  }
   return NNPM_OK;
 }
 
@@ -166,6 +171,12 @@ static void comm_destroy(nnpm_ctx* ctx) {
     if (ctx->peer_meshT[d]) cudaIpcCloseMemHandle(ctx->peer_meshT[d]);
     ctx->peer_mesh[d] = ctx->peer_meshT[d] = nullptr;
   }
+  for (int i = 0; i < 4; i++) {
+    if (ctx->st2[i]) { cudaStreamSynchronize(ctx->st2[i]); cudaStreamDestroy(ctx->st2[i]); ctx->st2[i] = nullptr; }
+    if (ctx->ev_join[i]) { cudaEventDestroy(ctx->ev_join[i]); ctx->ev_join[i] = nullptr; }
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  ctx->ev_fork = nullptr;
   if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(COMM);
   ctx->comm = nullptr;
 }
@@ -272,9 +283,45 @@ static int comm_barrier(nnpm_ctx* ctx) {
   return NNPM_OK;
 }
 
+// Copy-engine form of the same transposes.  For a fixed destination rank d the block is one strided
+// 2-D copy: nzl chunks of njl*icn complex numbers, contiguous on both sides --
+//   forward   src A[kl][d*njl ..][:]  (chunk stride = padded plane)  ->  T_d[kz0+kl][:][:]  (contiguous)
+//   backward  src T[d*nzl+kl][:][:]   (contiguous)                   ->  A_d[kl][j0 ..][:]  (plane stride)
+// so the whole all-to-all is P-1 peer cudaMemcpy2DAsync calls on the NVLink copy engines (no SM
+// time), spread over up to four side streams so several copy engines run at once.
+static int comm_transpose_ce(nnpm_ctx* ctx, bool fwd) {
+  const Geom& g = ctx->g;
+  const size_t chunk = (size_t)ctx->njl * ctx->icn * 16;      // bytes of one (plane, j-block) chunk
+  const size_t plane_b = (size_t)g.plane * 8;
+  const size_t glo_b = (size_t)g.plane * g.glo * 8;
+  const int ns = ctx->P < 4 ? ctx->P : 4;
+  CK(cudaEventRecord(ctx->ev_fork, ctx->st));
+  for (int i = 0; i < ns; i++) CK(cudaStreamWaitEvent(ctx->st2[i], ctx->ev_fork, 0));
+  for (int o = 0; o < ctx->P; o++) {
+    const int d = (ctx->r + o) % ctx->P;
+    cudaStream_t s = ctx->st2[o % ns];
+    if (fwd) {
+      const char* src = (const char*)ctx->mesh + glo_b + chunk * d;
+      char* dst = (char*)ctx->peer_meshT[d] + chunk * (size_t)g.kz0;
+      CK(cudaMemcpy2DAsync(dst, chunk, src, plane_b, chunk, (size_t)g.nzl, cudaMemcpyDeviceToDevice, s));
+    } else {
+      const char* src = (const char*)ctx->meshT + chunk * (size_t)g.nzl * d;
+      char* dst = (char*)ctx->peer_mesh[d] + glo_b + chunk * ctx->r;
+      CK(cudaMemcpy2DAsync(dst, plane_b, src, chunk, chunk, (size_t)g.nzl, cudaMemcpyDeviceToDevice, s));
+    }
+    ctx->launches += 1;
+  }
+  for (int i = 0; i < ns; i++) {
+    CK(cudaEventRecord(ctx->ev_join[i], ctx->st2[i]));
+    CK(cudaStreamWaitEvent(ctx->st, ctx->ev_join[i], 0));
+  }
+  return comm_barrier(ctx);
+}
+
 static int comm_transpose_fwd(nnpm_ctx* ctx) {
   NEED_COMM();
   const Geom& g = ctx->g;
+  if (ctx->peer_ok && ctx->opt_peer == 1) return comm_transpose_ce(ctx, true);
   if (ctx->peer_ok && ctx->opt_peer) {
     PeerPtrs T;
     for (int d = 0; d < ctx->P; d++) T.p[d] = (double2*)ctx->peer_meshT[d];
@@ -296,6 +343,7 @@ static int comm_transpose_fwd(nnpm_ctx* ctx) {
 static int comm_transpose_bwd(nnpm_ctx* ctx) {
   NEED_COMM();
   const Geom& g = ctx->g;
+  if (ctx->peer_ok && ctx->opt_peer == 1) return comm_transpose_ce(ctx, false);
   if (ctx->peer_ok && ctx->opt_peer) {
     PeerPtrs A;
     for (int d = 0; d < ctx->P; d++) A.p[d] = (double2*)(ctx->peer_mesh[d] + g.plane * g.glo);
