@@ -111,6 +111,12 @@ struct nnpm_ctx {
   bool peer_ok;
   int opt_peer;   // 0 = NCCL send/recv, 1 = copy-engine peer copies (default), 2 = remote-store kernels
   int* bar_buf;
+  // TMA-staged column FFT engine (nnpm_colfft.cuh)
+  CUtensorMap tm_y, tm_z;
+  bool have_tm_y, have_tm_z, have1;
+  double2* ytw;
+  cufftHandle plan1f, plan1b;  // batched 1-D x transforms (r2c / c2r) over the owned rows
+  int opt_colfft, opt_colfft_z, opt_cfrun_y, opt_cfrun_z, nsm;
   cudaStream_t st2[4];    // side streams: the blocks of a transpose go out on several copy engines at once
   cudaEvent_t ev_fork, ev_join[4];
 };
@@ -165,6 +171,7 @@ static int dalloc(nnpm_ctx* ctx, T** p, size_t count) {
 
 #include "nnpm_comm.cuh"
 #include "nnpm_zfft.cuh"
+#include "nnpm_colfft.cuh"
 
 // ------------------------------------------------------------------------------------------
 // lifetime
@@ -188,9 +195,9 @@ static int grow_fftwork(nnpm_ctx* ctx, size_t need) {
   ctx->fftwork = q;
   ctx->fftwork_bytes = need;
   ctx->dev_bytes += need;
-  cufftHandle hs[5] = {ctx->plan2f, ctx->plan2b, ctx->planz, ctx->plan3f, ctx->plan3b};
-  bool on[5] = {ctx->have2, ctx->have2, ctx->havez, ctx->have3, ctx->have3};
-  for (int i = 0; i < 5; i++)
+  cufftHandle hs[7] = {ctx->plan2f, ctx->plan2b, ctx->planz, ctx->plan3f, ctx->plan3b, ctx->plan1f, ctx->plan1b};
+  bool on[7] = {ctx->have2, ctx->have2, ctx->havez, ctx->have3, ctx->have3, ctx->have1, ctx->have1};
+  for (int i = 0; i < 7; i++)
     if (on[i]) CKF(cufftSetWorkArea(hs[i], ctx->fftwork));
   return NNPM_OK;
 }
@@ -218,6 +225,15 @@ static int make_plans(nnpm_ctx* ctx) {
   CKR(new_plan(ctx, &ctx->plan2b, 2, n, onembed, 1, g.plane / 2, inembed, 1, g.plane, CUFFT_Z2D, g.nzl, &ws));
   wmax = ws > wmax ? ws : wmax;
   ctx->have2 = true;
+  {  // x-only transforms for the [cuFFT x pass + TMA column-FFT y pass] form of the 2-D transform
+    long long n1[1] = {g.N1};
+    long long e1[1] = {g.rowp}, e2[1] = {ctx->icn};
+    CKR(new_plan(ctx, &ctx->plan1f, 1, n1, e1, 1, g.rowp, e2, 1, ctx->icn, CUFFT_D2Z, g.N2 * g.nzl, &ws));
+    wmax = ws > wmax ? ws : wmax;
+    CKR(new_plan(ctx, &ctx->plan1b, 1, n1, e2, 1, ctx->icn, e1, 1, g.rowp, CUFFT_Z2D, g.N2 * g.nzl, &ws));
+    wmax = ws > wmax ? ws : wmax;
+    ctx->have1 = true;
+  }
   if (g.N3 > 1) {
     long long nz[1] = {g.N3};
     long long stride = ctx->njl * ctx->icn;  // [k][jl][ic]: k has stride njl*icn
@@ -357,6 +373,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->peer_ok = false; c->opt_peer = 1; c->bar_buf = nullptr;
   c->ev_fork = nullptr;
   for (int i = 0; i < 4; i++) { c->st2[i] = nullptr; c->ev_join[i] = nullptr; }
+  c->have_tm_y = c->have_tm_z = c->have1 = false; c->ytw = nullptr; c->opt_colfft = 1; c->opt_colfft_z = 0; c->opt_cfrun_y = 1; c->opt_cfrun_z = 1; c->nsm = 148;
   c->mig_lo = nullptr; c->ghost_rx = nullptr; c->red_buf = nullptr;
   c->np = 0; c->m = 0.0; c->ids_dirty = false; c->field_state = 0;
   c->own_stream = false;
@@ -371,6 +388,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
 #define CKB(call) do { int rc2_ = [&]() -> int { call; return NNPM_OK; }(); if (rc2_ != NNPM_OK) return bail(rc2_); } while (0)
 
   CKB(CK(cudaSetDevice(cfg->device)));
+  CKB(CK(cudaDeviceGetAttribute(&c->nsm, cudaDevAttrMultiProcessorCount, cfg->device)));
   if (cfg->stream) c->st = (cudaStream_t)cfg->stream;
   else { CKB(CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking))); c->own_stream = true; }
 
@@ -427,6 +445,7 @@ extern "C" int nnpm_destroy(nnpm_ctx* ctx) {
   if (ctx->st) cudaStreamSynchronize(ctx->st);
   comm_destroy(ctx);
   if (ctx->have2) { cufftDestroy(ctx->plan2f); cufftDestroy(ctx->plan2b); }
+  if (ctx->have1) { cufftDestroy(ctx->plan1f); cufftDestroy(ctx->plan1b); }
   if (ctx->havez) cufftDestroy(ctx->planz);
   if (ctx->have3) { cufftDestroy(ctx->plan3f); cufftDestroy(ctx->plan3b); }
   for (void* p : ctx->allocs) cudaFree(p);
@@ -797,8 +816,14 @@ static int fft_forward(nnpm_ctx* ctx, double2** Tout, bool z_too, cudaEvent_t* c
     *Tout = (double2*)own;
     return NNPM_OK;
   }
-  CKF(cufftExecD2Z(ctx->plan2f, own, (cufftDoubleComplex*)own));
-  LAUNCHED(ctx);
+  if (ctx->opt_colfft && colfft_supported_n(g.N2)) {
+    CKF(cufftExecD2Z(ctx->plan1f, own, (cufftDoubleComplex*)own));
+    LAUNCHED(ctx);
+    CKR(colfft_y(ctx, false));
+  } else {
+    CKF(cufftExecD2Z(ctx->plan2f, own, (cufftDoubleComplex*)own));
+    LAUNCHED(ctx);
+  }
   double2* T = (double2*)own;
   if (ctx->P > 1) {
     if (comm_t) CK(cudaEventRecord(comm_t[0], ctx->st));
@@ -826,8 +851,14 @@ static int fft_inverse(nnpm_ctx* ctx, bool z_too, cudaEvent_t* comm_t) {
     CKR(comm_transpose_bwd(ctx));
     if (comm_t) CK(cudaEventRecord(comm_t[3], ctx->st));
   }
-  CKF(cufftExecZ2D(ctx->plan2b, (cufftDoubleComplex*)own, own));
-  LAUNCHED(ctx);
+  if (ctx->opt_colfft && colfft_supported_n(g.N2)) {
+    CKR(colfft_y(ctx, true));
+    CKF(cufftExecZ2D(ctx->plan1b, (cufftDoubleComplex*)own, own));
+    LAUNCHED(ctx);
+  } else {
+    CKF(cufftExecZ2D(ctx->plan2b, (cufftDoubleComplex*)own, own));
+    LAUNCHED(ctx);
+  }
   return NNPM_OK;
 }
 
@@ -842,7 +873,10 @@ static int do_solve(nnpm_ctx* ctx, cudaEvent_t* ev) {
   CKR(fft_forward(ctx, &T, !fusedz, ev));
   if (ev) CK(cudaEventRecord(ev[4], ctx->st));
   if (fusedz) {
-    CKR(zfused_launch(ctx, T, scale));
+    // measured at 1024^3: the register-resident k_zfused (128-byte rows, exact DRAM traffic) 7.0 ms;
+    // the TMA-staged variant (64-byte rows, 4 warps per SM) 7.6 ms -> k_zfused is the default
+    if (ctx->opt_colfft_z) CKR(colfft_z_green(ctx, T, scale));
+    else CKR(zfused_launch(ctx, T, scale));
   } else {
     dim3 grid(nblk(ctx->icn, 128), (unsigned)ctx->njl, (unsigned)(g.N3 < 64 ? g.N3 : 64));
     k_green<<<grid, 128, 0, ctx->st>>>(T, ctx->icn, ctx->njl, ctx->njl * ctx->r, g.N3, ctx->s1, ctx->s2, ctx->s3, ctx->R == 3, scale);
@@ -1127,6 +1161,10 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   else if (!strcmp(name, "push_minb")) ctx->opt_push_minb = v;
   else if (!strcmp(name, "zcols")) ctx->opt_zcols = v;
   else if (!strcmp(name, "bulk_flush")) ctx->opt_bulk_flush = v;
+  else if (!strcmp(name, "colfft")) ctx->opt_colfft = v;
+  else if (!strcmp(name, "colfft_z")) ctx->opt_colfft_z = v;
+  else if (!strcmp(name, "cfrun_y")) ctx->opt_cfrun_y = v < 1 ? 1 : v;
+  else if (!strcmp(name, "cfrun_z")) ctx->opt_cfrun_z = v < 1 ? 1 : v;
   else if (!strcmp(name, "peer_transpose")) ctx->opt_peer = v;
   else return fail(ctx, NNPM_ERR_ARG, "unknown option '%s'", name);
   return NNPM_OK;

@@ -1,0 +1,283 @@
+// nnpm_colfft.cuh -- strided-column FFT engine with TMA staging (sm_100a), used for
+//   * the y pass of the 2-D transforms (forward after cuFFT's x r2c, inverse before its x c2r), and
+//   * the fused z pass [z-FFT -> Green's function multiply (ParticleMesh.jl:482-502) -> z-iFFT].
+//
+// Why: a column of the half spectrum is N elements 8 KB .. 8 MB apart.  Load/store instructions
+// issued from registers (k_zfused, cuFFT's regular_fft) keep too few bytes in flight per SM for that
+// access pattern (ncu: 25-31 % of DRAM peak, lg_throttle / long_scoreboard stalls).  Here the TMA
+// engine moves whole column groups: one persistent CTA per SM cycles two shared-memory buffers of
+// [N][4] double2 (a group of 4 adjacent columns = 64 B per row); while the CTA transforms group g in
+// registers + a padded exchange buffer, cp.async.bulk.tensor loads of group g+1 and the tensor store
+// of group g-1 are in flight.  The threads never touch global memory.
+//
+//   tensor map   3-D over doubles: (2*icn, n_mid, n_outer) = (ic pairs, j, k); box (8, 1|RB, RB|1)
+//   y pass       column = (plane, ic), rows = j:  coords (8*icg, row0, plane)
+//   z pass       column = (jl, ic),   rows = k:  coords (8*icg, jl, row0)
+//   columns past icn (513 = 128*4 + 1) are out of bounds: TMA zero-fills them on load and drops
+//   them on store.
+//
+// Arithmetic: N = R1*R2, two register-resident radix passes (ZDif/ZDit of nnpm_zfft.cuh).
+//   pass A  thread n' (< R2): rows n' + n1*R2 -> radix-R1 DIF -> y1[k1][n']  -> exchange E[k1*(R2+1) + n']
+//   pass B  thread k1 (< R1): E[k1*(R2+1) + n'] * W_N^(n' k1) -> radix-R2 DIF -> X[k1 + R1*k2]
+// E is padded by one element per k1 row so that both sides of the exchange are bank-conflict free
+// with 4 columns per row (quarter-warps touch two rows whose indices differ by an odd number).
+#pragma once
+
+enum { CF_FWD = 0, CF_INV = 1, CF_GREEN = 2 };
+
+struct ColFftArgs {
+  int ngroups;        // column groups = n_outer_cols * nicg
+  int nicg;           // groups per outer index = ceil(icn / 4)
+  int icn;
+  int run;            // adjacent groups a CTA processes back to back (1 or 2)
+  i64 j0;             // global j of local row-block start (Green's function, z pass)
+  const double* s1;   // sin^2 tables (z pass)
+  const double* s2;
+  const double* s3;
+  const double2* tw;  // W_N^m, m < N
+  double scale;
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+// YPASS: rows run along tensor dimension 1 (j), the outer column index along dimension 2 (plane);
+// otherwise rows along dimension 2 (k), outer index along dimension 1 (jl).
+template <int R1, int R2, int MODE, bool YPASS>
+__global__ void __launch_bounds__(4 * (R1 > R2 ? R1 : R2), 1)
+k_colfft(const __grid_constant__ CUtensorMap tmap, ColFftArgs a) {
+  constexpr int C = 4, N = R1 * R2, RM = R1 > R2 ? R1 : R2, B1 = zf_log2(R1), B2 = zf_log2(R2);
+  constexpr int RB = N < 256 ? N : 256, NOPS = N / RB;         // rows per TMA operation (box limit 256)
+  constexpr int EST = R2 + 1;                                   // padded exchange row
+  constexpr int SIGN = (MODE == CF_INV) ? +1 : -1;              // sign of the (first) transform
+  extern __shared__ __align__(128) unsigned char cf_smem[];
+  double2* buf0 = (double2*)cf_smem;                            // [2][N][C]
+  double2* E = buf0 + 2 * N * C;                                // [R1][EST][C]
+  double2* stw = E + R1 * EST * C;                              // [N]
+  double* ss3 = (double*)(stw + N);                             // [N] (CF_GREEN)
+  __shared__ __align__(8) unsigned long long full[2];
+  const int tid = threadIdx.x, c = tid % C, j = tid / C;
+  for (int t = tid; t < N; t += blockDim.x) {
+    stw[t] = __ldg(a.tw + t);
+    if (MODE == CF_GREEN) ss3[t] = __ldg(a.s3 + t);
+  }
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+  }
+  __syncthreads();
+  // Group schedule: CTA b works on runs of `a.run` adjacent groups, runs dealt round-robin to the CTAs:
+  //   g(b, it) = ((it / run) * gridDim + b) * run + it % run.
+  // At any time the CTAs together cover one contiguous stretch of every row (DRAM page locality);
+  // with run = 2 the two 64-byte halves of a 128-byte line are requested by the same CTA in
+  // consecutive iterations, so the half that L2 over-fetches is still resident when it is needed.
+  const int run = a.run;
+  auto group_of = [&](int it) { return ((it / run) * (int)gridDim.x + (int)blockIdx.x) * run + it % run; };
+  auto issue_load = [&](int g, int b) {  // thread 0 only
+    const int outer = g / a.nicg, icg = g - outer * a.nicg;
+    mbar_expect_tx(&full[b], (unsigned)(N * C * sizeof(double2)));
+#pragma unroll
+    for (int o = 0; o < NOPS; o++) {
+      if (YPASS) tma_load_3d(buf0 + (b * N + o * RB) * C, &tmap, icg * 8, o * RB, outer, &full[b]);
+      else tma_load_3d(buf0 + (b * N + o * RB) * C, &tmap, icg * 8, outer, o * RB, &full[b]);
+    }
+  };
+  int g = group_of(0);
+  if (tid == 0 && g < a.ngroups) issue_load(g, 0);
+  unsigned phase[2] = {0u, 0u};
+  double2 v[RM];
+  for (int it = 0; g < a.ngroups; it++) {
+    const int b = it & 1;
+    const int gnext = group_of(it + 1);
+    const int outer = g / a.nicg, icg = g - outer * a.nicg;
+    // prefetch the next group into the other buffer: its previous contents were stored one iteration
+    // ago; the store must have finished READING shared memory before the load overwrites it
+    if (tid == 0 && gnext < a.ngroups) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      issue_load(gnext, b ^ 1);
+    }
+    // Green's function column factors, requested before the wait so their latency hides behind it
+    double sxy = 1.0;
+    bool dc_col = false;
+    if (MODE == CF_GREEN) {
+      const int ic = icg * C + c;
+      if (ic < a.icn) sxy = __ldg(a.s1 + ic) + __ldg(a.s2 + a.j0 + outer);
+      dc_col = (ic == 0 && a.j0 + outer == 0);
+    }
+    double2* B = buf0 + b * N * C;
+    mbar_wait(&full[b], phase[b]);
+    phase[b] ^= 1u;
+    // ---- pass A: radix R1 over rows j + r*R2
+    if (j < R2) {
+#pragma unroll
+      for (int r = 0; r < R1; r++) v[r] = B[(j + r * R2) * C + c];
+      ZDif<R1, 0, SIGN>::run(v);
+#pragma unroll
+      for (int q = 0; q < R1; q++) E[(q * EST + j) * C + c] = v[zf_brev(q, B1)];
+    }
+    __syncthreads();
+    // ---- pass B: radix R2 over n' for k1 = j
+    if (j < R1) {
+#pragma unroll
+      for (int r = 0; r < R2; r++) v[r] = E[(j * EST + r) * C + c];
+#pragma unroll
+      for (int r = 1; r < R2; r++) {
+        const double2 w = stw[r * j];
+        v[r] = zmul(v[r], w.x, SIGN < 0 ? w.y : -w.y);
+      }
+      ZDif<R2, 0, SIGN>::run(v);  // v[brev(q)] = X[j + q*R1]
+      if (MODE != CF_GREEN) {
+#pragma unroll
+        for (int q = 0; q < R2; q++) B[(j + q * R1) * C + c] = v[zf_brev(q, B2)];
+      } else {
+        // Green's function on the bit-reversed registers: X[kz] *= scale / Ginv(i, j, kz)
+        //   Ginv = -4 (sin^2(kx/2) + sin^2(ky/2) + sin^2(kz/2)), rt[1,1,1] = 0   ParticleMesh.jl:494-501
+#pragma unroll
+        for (int q = 0; q < R2; q++) {
+          const int kz = j + q * R1;
+          const double ginv = -4.0 * (sxy + ss3[kz]);
+          double f = (ginv != 0.0) ? a.scale * zf_rcp(ginv) : a.scale;
+          if (dc_col && kz == 0) f = 0.0;
+          double2& e = v[zf_brev(q, B2)];
+          e.x *= f;
+          e.y *= f;
+        }
+        // ---- inverse pass A': radix R2 DIT (bit-reversed in, natural out) -> E in place
+        ZDit<R2, 0, +1>::run(v);
+#pragma unroll
+        for (int r = 0; r < R2; r++) E[(j * EST + r) * C + c] = v[r];
+      }
+    }
+    if (MODE == CF_GREEN) {
+      __syncthreads();
+      // ---- inverse pass B': radix R1 over k1 for n' = j -> rows j + q*R2
+      if (j < R2) {
+#pragma unroll
+        for (int r = 0; r < R1; r++) v[r] = E[(r * EST + j) * C + c];
+#pragma unroll
+        for (int r = 1; r < R1; r++) {
+          const double2 w = stw[r * j];
+          v[r] = zmul(v[r], w.x, -w.y);
+        }
+        ZDif<R1, 0, +1>::run(v);
+#pragma unroll
+        for (int q = 0; q < R1; q++) B[(j + q * R2) * C + c] = v[zf_brev(q, B1)];
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> TMA store reads
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int o = 0; o < NOPS; o++) {
+        if (YPASS) tma_store_3d(&tmap, B + o * RB * C, icg * 8, o * RB, outer);
+        else tma_store_3d(&tmap, B + o * RB * C, icg * 8, outer, o * RB);
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    g = gnext;
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
+}
+
+// ---- host side -------------------------------------------------------------------------------
+static int colfft_tensor_map(nnpm_ctx* ctx, CUtensorMap* tm, double* base, i64 n_mid, i64 n_outer, i64 mid_stride_b,
+                             i64 outer_stride_b, bool ypass, i64 N) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) return fail(ctx, NNPM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  const cuuint32_t rb = (cuuint32_t)(N < 256 ? N : 256);
+  cuuint64_t dims[3] = {(cuuint64_t)(2 * ctx->icn), (cuuint64_t)n_mid, (cuuint64_t)n_outer};
+  cuuint64_t strides[2] = {(cuuint64_t)mid_stride_b, (cuuint64_t)outer_stride_b};
+  cuuint32_t box[3] = {8, ypass ? rb : 1u, ypass ? 1u : rb};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = ((encode_fn)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, NNPM_ERR_CUDA, "cuTensorMapEncodeTiled (column FFT) failed (%d)", (int)r);
+  return NNPM_OK;
+}
+
+static int colfft_twiddles(nnpm_ctx* ctx, double2** tw, i64 N) {
+  if (*tw) return NNPM_OK;  // W_N^m = exp(-2 pi i m / N), m < N, in extended precision on the host
+  std::vector<double2> h((size_t)N);
+  for (i64 m = 0; m < N; m++) {
+    const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)N;
+    h[m] = make_double2((double)cosl(ang), (double)sinl(ang));
+  }
+  CKR(dalloc(ctx, tw, (size_t)N));
+  CK(cudaMemcpyAsync(*tw, h.data(), (size_t)N * sizeof(double2), cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return NNPM_OK;
+}
+
+template <int R1, int R2, int MODE, bool YPASS>
+static int colfft_go(nnpm_ctx* ctx, const CUtensorMap& tm, const ColFftArgs& a) {
+  constexpr int N = R1 * R2, RM = R1 > R2 ? R1 : R2;
+  const size_t smem = (size_t)2 * N * 4 * 16 + (size_t)R1 * (R2 + 1) * 4 * 16 + (size_t)N * 16 + (size_t)N * 8;
+  CK(cudaFuncSetAttribute(k_colfft<R1, R2, MODE, YPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = a.ngroups < ctx->nsm ? a.ngroups : ctx->nsm;
+  k_colfft<R1, R2, MODE, YPASS><<<grid, 4 * RM, smem, ctx->st>>>(tm, a);
+  LAUNCHED(ctx);
+  KCHECK();
+  return NNPM_OK;
+}
+
+template <int MODE, bool YPASS>
+static int colfft_dispatch(nnpm_ctx* ctx, i64 N, const CUtensorMap& tm, const ColFftArgs& a) {
+  switch (N) {
+    case 64: return colfft_go<8, 8, MODE, YPASS>(ctx, tm, a);
+    case 128: return colfft_go<16, 8, MODE, YPASS>(ctx, tm, a);
+    case 256: return colfft_go<16, 16, MODE, YPASS>(ctx, tm, a);
+    case 512: return colfft_go<32, 16, MODE, YPASS>(ctx, tm, a);
+    case 1024: return colfft_go<32, 32, MODE, YPASS>(ctx, tm, a);
+  }
+  return fail(ctx, NNPM_ERR_STATE, "column FFT does not support N = %lld", (long long)N);
+}
+
+static bool colfft_supported_n(i64 N) { int r1, r2; return zfused_factor(N, &r1, &r2); }
+
+// y pass over the owned planes, in place in the mesh (forward after the x r2c, inverse before the x c2r)
+static int colfft_y(nnpm_ctx* ctx, bool inverse) {
+  const Geom& g = ctx->g;
+  if (!ctx->have_tm_y) {
+    CKR(colfft_tensor_map(ctx, &ctx->tm_y, ctx->mesh + g.plane * g.glo, g.N2, g.nzl, ctx->icn * 16, g.plane * 8, true, g.N2));
+    ctx->have_tm_y = true;
+  }
+  CKR(colfft_twiddles(ctx, &ctx->ytw, g.N2));
+  ColFftArgs a;
+  memset(&a, 0, sizeof a);
+  a.nicg = (int)((ctx->icn + 3) / 4);
+  a.ngroups = (int)(g.nzl * a.nicg);
+  a.icn = (int)ctx->icn;
+  a.tw = ctx->ytw;
+  a.scale = 1.0;
+  a.run = ctx->opt_cfrun_y;
+  return inverse ? colfft_dispatch<CF_INV, true>(ctx, g.N2, ctx->tm_y, a) : colfft_dispatch<CF_FWD, true>(ctx, g.N2, ctx->tm_y, a);
+}
+
+// fused z pass on T[k][jl][ic] (the mesh itself when nranks == 1, meshT otherwise)
+static int colfft_z_green(nnpm_ctx* ctx, double2* T, double scale) {
+  const Geom& g = ctx->g;
+  if (!ctx->have_tm_z) {
+    CKR(colfft_tensor_map(ctx, &ctx->tm_z, (double*)T, ctx->njl, g.N3, ctx->icn * 16, ctx->njl * ctx->icn * 16, false, g.N3));
+    ctx->have_tm_z = true;
+  }
+  CKR(colfft_twiddles(ctx, &ctx->ztw, g.N3));
+  ColFftArgs a;
+  memset(&a, 0, sizeof a);
+  a.nicg = (int)((ctx->icn + 3) / 4);
+  a.ngroups = (int)(ctx->njl * a.nicg);
+  a.icn = (int)ctx->icn;
+  a.j0 = ctx->njl * ctx->r;
+  a.s1 = ctx->s1; a.s2 = ctx->s2; a.s3 = ctx->s3;
+  a.tw = ctx->ztw;
+  a.scale = scale;
+  a.run = ctx->opt_cfrun_z;
+  return colfft_dispatch<CF_GREEN, false>(ctx, g.N3, ctx->tm_z, a);
+}
