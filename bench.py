@@ -145,6 +145,8 @@ def main():
                     help="counting-sort cadence in steps; the default K = 16 timed steps contain exactly one sort")
     ap.add_argument("--deposit-mode", default="atomic")
     ap.add_argument("--opt", action="append", default=[], help="name=value passed to nnpm_set_option")
+    ap.add_argument("--ic", default="zeldovich", choices=["zeldovich", "clustered"],
+                    help="clustered = BASELINE config 4 stand-in: half the particles in 10^5 Gaussian blobs (sigma 1.5 cells)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -210,7 +212,11 @@ def main():
     a0 = cos.a_from_t_internal(scalars.cosmo, ts, ZINIT, zwherea1=ZINIT)
     ad0 = cos.dadt(scalars.cosmo, a0, zwherea1=ZINIT)
     m = (mesh ** 3) / float(n ** 3) * COSMO["OmegaM"]
-    dev.init_synthetic((n, n, n), seed=12345, nmodes=32, kmax=8, disp_rms=0.3 / mesh, vfac=ad0 / a0, m=m)
+    if args.ic == "clustered":
+        dev.init_synthetic((n, n, n), kind="clustered", seed=777, nmodes=100, kmax=1000, disp_rms=1.5 / mesh, vfac=2e-5, m=m)
+        config["workload"] = workload.replace("synthetic Zel'dovich ICs", "synthetic clustered late-time state (50% of the particles in 10^5 Gaussian blobs, sigma = 1.5 cells, b^-1/2 mass function)")
+    else:
+        dev.init_synthetic((n, n, n), seed=12345, nmodes=32, kmax=8, disp_rms=0.3 / mesh, vfac=ad0 / a0, m=m)
 
     state = {"t": ts, "dt": 1e-4}
 

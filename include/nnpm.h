@@ -52,7 +52,7 @@ enum { NNPM_DEPOSIT_ATOMIC = 0, NNPM_DEPOSIT_FIXED = 1 };
 /* fields for nnpm_get_field / nnpm_set_field */
 enum { NNPM_FIELD_RHO = 0, NNPM_FIELD_PHI = 1, NNPM_FIELD_ACC = 2, NNPM_FIELD_PA = 3 };
 /* synthetic initial conditions generated on the device (nnpm_init_synthetic) */
-enum { NNPM_IC_LATTICE = 0, NNPM_IC_ZELDOVICH_MODES = 1 };
+enum { NNPM_IC_LATTICE = 0, NNPM_IC_ZELDOVICH_MODES = 1, NNPM_IC_CLUSTERED = 2 };
 
 typedef struct {
   int32_t struct_size;      /* = sizeof(nnpm_config), for ABI checks */
@@ -133,7 +133,10 @@ int64_t nnpm_local_count(const nnpm_ctx *ctx);
 int nnpm_download_particles(nnpm_ctx *ctx, double *x_aos, double *v_aos, int64_t *ids_out);
 /* Device-side synthetic ICs (lattice of ParticleMesh.jl:257-287, optionally displaced by a
  * seeded plane-wave Zel'dovich field; oracle/pm_ref.py:synthetic_zeldovich is the checker).
- * pdims = ParticleDimensions; v = vfac * displacement. */
+ * pdims = ParticleDimensions; v = vfac * displacement.
+ * kind == NNPM_IC_CLUSTERED (BASELINE config 4 stand-in): half the particles stay on the lattice, half
+ * fall into nmodes*kmax Gaussian blobs of width disp_rms (box units) with a b^-1/2 mass function and
+ * velocity dispersion vfac; oracle/pm_ref.py:synthetic_clustered is the checker. */
 int nnpm_init_synthetic(nnpm_ctx *ctx, int kind, const int64_t pdims[3], uint64_t seed,
                         int32_t nmodes, int32_t kmax, double disp_rms, double vfac, double m);
 /* Counting sort of the local particles by cell (new; K0 of the design). */
@@ -178,7 +181,13 @@ int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, in
  *   "fft3d"        1 = single cuFFT 3-D plan instead of 2-D + fused z pass (nranks == 1 only)
  *   "zfused"       1 = hand-written fused z-FFT * Green * z-iFFT kernel (default), 0 = cuFFT z
  *   "tile_deposit" 1 = shared-memory tiled deposit on tile-sorted particles (default), 0 = global atomics
- *   "tile_push"    1 = push gathers phi from a shared-memory tile on sorted particles, 0 = L2 gather */
+ *   "tile_push"    1 = push gathers phi from a shared-memory tile on sorted particles, 0 = L2 gather
+ *   "bulk_flush"   1 = tiled deposit flushes its box with cp.reduce.async.bulk (default), 0 = per-cell atomics
+ *   "colfft"       1 = TMA-staged column FFT for the y passes (default), 0 = cuFFT 2-D plans
+ *   "colfft_z"     1 = TMA-staged fused z pass instead of the register-resident one
+ *   "peer_transpose" nranks > 1: 1 = copy-engine peer copies over NVLink (default), 2 = remote-store
+ *                  kernels, 0 = grouped ncclSend/ncclRecv
+ *   "push_minb", "zcols", "cfrun_y", "cfrun_z"  launch-shape experiments */
 int nnpm_set_option(nnpm_ctx *ctx, const char *name, double value);
 
 #ifdef __cplusplus

@@ -18,7 +18,7 @@ MS_NAMES = ("deposit", "solve", "push", "sort", "exchange", "comm", "fft_z", "ff
 INTERP = {"none": 0, "cic": 1}
 DEPOSIT_MODE = {"atomic": 0, "fixedpoint": 1, "fixed": 1}
 FIELD_RHO, FIELD_PHI, FIELD_ACC, FIELD_PA = 0, 1, 2, 3
-IC_LATTICE, IC_ZELDOVICH_MODES = 0, 1
+IC_LATTICE, IC_ZELDOVICH_MODES, IC_CLUSTERED = 0, 1, 2
 
 # every symbol include/nnpm.h declares (tests/test_abi.py checks the header against this list
 # and the built library against both)

@@ -64,6 +64,8 @@ struct nnpm_ctx {
 
   // sort scratch
   uint32_t *hist, *bsum, *bsum2, *skey, *srnk;
+  uint32_t *wcnt, *wtile, *wbeg;  // work list of the tiled kernels (k_work_count / k_work_fill)
+  i64 wcap;
   TileGeom tg;
   i64 ntiles;
   i64 sorted_np;     // particles [0, sorted_np) are covered by the tile offsets in `hist` (0 = not sorted)
@@ -359,6 +361,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->acc_valid = c->pa_valid = false;
   c->stage = nullptr; c->stage_elems = 0;
   c->hist = c->bsum = c->bsum2 = c->skey = c->srnk = nullptr;
+  c->wcnt = c->wtile = c->wbeg = nullptr; c->wcap = 0;
   c->have2 = c->havez = c->have3 = false;
   c->have_tmap = false;
   c->opt_fft3d = 0; c->opt_zfused = 1; c->opt_tile_deposit = 1; c->opt_tile_push = 1; c->opt_push_minb = 2; c->opt_bulk_flush = 1;
@@ -597,7 +600,7 @@ extern "C" int nnpm_init_synthetic(nnpm_ctx* ctx, int kind, const int64_t pdims[
   CK(cudaSetDevice(ctx->cfg.device));
   const i64 P1 = pdims[0], P2 = pdims[1], P3 = ctx->R == 3 ? pdims[2] : 1;
   if (P1 * P2 * P3 != ctx->cfg.npart_total) return fail(ctx, NNPM_ERR_ARG, "prod(pdims) != npart_total");
-  if (nmodes > 64 || nmodes < 0) return fail(ctx, NNPM_ERR_ARG, "nmodes must be in [0,64]");
+  if (kind != NNPM_IC_CLUSTERED && (nmodes > 64 || nmodes < 0)) return fail(ctx, NNPM_ERR_ARG, "nmodes must be in [0,64]");
   if (ctx->P > 1 && P3 % ctx->P) return fail(ctx, NNPM_ERR_ARG, "pdims[2] must be divisible by nranks");
   // this rank generates lattice planes [r*P3/P, (r+1)*P3/P)
   const i64 per = P3 / ctx->P * P1 * P2;
@@ -635,7 +638,16 @@ extern "C" int nnpm_init_synthetic(nnpm_ctx* ctx, int kind, const int64_t pdims[
     }
     M.amp = M.n ? disp_rms * sqrt((double)ctx->R) / sqrt(norm2) : 0.0;
   }
-  if (per) {
+  if (per && kind == NNPM_IC_CLUSTERED) {
+    // number of blobs = nmodes * kmax (two int32 factors so that 10^5 and more fit), disp_rms = blob
+    // sigma (box units), vfac = velocity dispersion
+    const i64 nblobs = kmax > 0 ? (i64)nmodes * (i64)kmax : (i64)nmodes;
+    if (nblobs < 1) return fail(ctx, NNPM_ERR_ARG, "clustered ICs need nmodes*kmax >= 1 blobs");
+    if (ctx->R == 3) k_init_clustered<3><<<nblk(per, 256), 256, 0, ctx->st>>>(ctx->pp, ctx->ids, per, first, P1, P2, P3, seed, nblobs, disp_rms, vfac);
+    else k_init_clustered<2><<<nblk(per, 256), 256, 0, ctx->st>>>(ctx->pp, ctx->ids, per, first, P1, P2, P3, seed, nblobs, disp_rms, vfac);
+    LAUNCHED(ctx);
+    KCHECK();
+  } else if (per) {
     if (ctx->R == 3) k_init_synth<3><<<nblk(per, 256), 256, 0, ctx->st>>>(ctx->pp, ctx->ids, per, first, P1, P2, P3, M, vfac);
     else k_init_synth<2><<<nblk(per, 256), 256, 0, ctx->st>>>(ctx->pp, ctx->ids, per, first, P1, P2, P3, M, vfac);
     LAUNCHED(ctx);
@@ -691,6 +703,19 @@ extern "C" int nnpm_sort(nnpm_ctx* ctx) {
   LAUNCHED(ctx);
   KCHECK();
   CKR(permute_all(ctx, ctx->skey));
+  // work list: chunks of <= NNPM_CHUNK particles per tile along the banded raster
+  if (!ctx->wcnt) {
+    ctx->wcap = ctx->ntiles + ctx->cap / NNPM_CHUNK + 2;
+    CKR(dalloc(ctx, &ctx->wcnt, (size_t)ctx->ntiles + 1));
+    CKR(dalloc(ctx, &ctx->wtile, (size_t)ctx->wcap));
+    CKR(dalloc(ctx, &ctx->wbeg, (size_t)ctx->wcap));
+  }
+  k_work_count<<<nblk(ctx->ntiles + 1, 256), 256, 0, ctx->st>>>(ctx->tg, ctx->ntiles, ctx->hist, ctx->wcnt);
+  LAUNCHED(ctx);
+  CKR(scan_u32(ctx, ctx->wcnt, ctx->ntiles + 1));
+  k_work_fill<<<nblk(ctx->ntiles, 256), 256, 0, ctx->st>>>(ctx->tg, ctx->ntiles, ctx->hist, ctx->wcnt, ctx->wtile, ctx->wbeg);
+  LAUNCHED(ctx);
+  KCHECK();
   ctx->ids_dirty = true;
   ctx->pa_valid = false;
   ctx->sorted_np = np;
@@ -762,7 +787,9 @@ static int do_deposit(nnpm_ctx* ctx, bool pre, double c0) {
     covered = ctx->sorted_np < ctx->np ? ctx->sorted_np : ctx->np;
     CK(cudaMemsetAsync(ctx->d_red + 5, 0, 8, ctx->st));
     const int bulk = ctx->opt_bulk_flush && (g.N1 % 2 == 0) && g.N1 >= NNPM_DX && ctx->tg.tx == NNPM_TX;
-#define DT(RK, FX, PR) k_deposit_tile<RK, FX, PR><<<(unsigned)ctx->ntiles, 256, 0, ctx->st>>>(ctx->pp, covered, c0, ctx->g, ctx->tg, ctx->hist, ctx->mesh, ctx->m, fscale, ctx->srnk, (u64*)(ctx->d_red + 5), bulk)
+    const WorkList wl = {ctx->wtile, ctx->wbeg, ctx->wcnt + ctx->ntiles};
+    const unsigned wgrid = (unsigned)(ctx->ntiles + ctx->sorted_np / NNPM_CHUNK + 1);  // >= number of chunks
+#define DT(RK, FX, PR) k_deposit_tile<RK, FX, PR><<<wgrid, 256, 0, ctx->st>>>(ctx->pp, covered, c0, ctx->g, ctx->tg, wl, ctx->hist, ctx->mesh, ctx->m, fscale, ctx->srnk, (u64*)(ctx->d_red + 5), bulk)
     if (ctx->R == 3) { if (fixed) { if (pre) DT(3, true, true); else DT(3, true, false); } else { if (pre) DT(3, false, true); else DT(3, false, false); } }
     else { if (fixed) { if (pre) DT(2, true, true); else DT(2, true, false); } else { if (pre) DT(2, false, true); else DT(2, false, false); } }
 #undef DT
@@ -1037,10 +1064,12 @@ static int launch_push(nnpm_ctx* ctx, bool comoving, const PushParams& pp) {
   }
   const size_t smem = (size_t)NNPM_BX * NNPM_BY * (RANK == 3 ? NNPM_BZ : 1) * sizeof(double);
   const i64 covered = ctx->sorted_np < np ? ctx->sorted_np : np;
+  const WorkList wl = {ctx->wtile, ctx->wbeg, ctx->wcnt + ctx->ntiles};
+  const unsigned wgrid = (unsigned)(ctx->ntiles + ctx->sorted_np / NNPM_CHUNK + 1);  // >= number of chunks
 #define LT(CM, MB)                                                                                                  \
   do {                                                                                                              \
     CK(cudaFuncSetAttribute(k_push_tile<RANK, CM, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    k_push_tile<RANK, CM, MB><<<(unsigned)ctx->ntiles, 256, smem, ctx->st>>>(ctx->tmap_phi, ctx->pp, covered, ctx->g, ctx->tg, ctx->hist, \
+    k_push_tile<RANK, CM, MB><<<wgrid, 256, smem, ctx->st>>>(ctx->tmap_phi, ctx->pp, covered, ctx->g, ctx->tg, wl, ctx->hist, \
                                                                              ctx->mesh, pp, ctx->d_red, ctx->srnk, slow_count); \
   } while (0)
   if (ctx->opt_push_minb >= 3) { if (comoving) LT(true, 3); else LT(false, 3); }

@@ -651,19 +651,47 @@ struct TileGeom {
   int tx, ty, tz;      // tile extent in cells (clamped to the mesh)
 };
 
-// CTA rasterisation for the tiled kernels, 1-D grid of ntx*nty*ntz CTAs: tiles are walked x fastest, then y
-// within bands of NNPM_YB tile rows, then z, then the next band -- so that the halo planes a tile
-// shares with its z neighbour are touched again after NNPM_YB*ntx tiles (a few MB: still in L2)
-// instead of after a whole plane of tiles (~100 MB at 1024^2 cells per plane).
+// Work list of the tiled kernels, rebuilt by every sort: one entry per chunk of at most NNPM_CHUNK
+// particles of one tile, so that a tile holding a collapsed halo (10^3..10^5 x the mean occupancy in
+// the clustered late-time state) is spread over many CTAs instead of serialising one, and empty tiles
+// cost nothing.  Entries are ordered along a banded raster: tiles x fastest, then y within bands of
+// NNPM_YB tile rows, then z, then the next band -- the halo planes a tile shares with its z neighbour
+// are touched again after NNPM_YB*ntx tiles (a few MB, still in L2) instead of after a whole plane
+// of tiles (~100 MB at 1024^2 cells per plane).
 #define NNPM_YB 8
-__device__ __forceinline__ void tile_of_block(const TileGeom& tg, int& ttx, int& tty, int& ttz) {
-  const int L = blockIdx.x / tg.ntx;
-  ttx = blockIdx.x - L * tg.ntx;
+#define NNPM_CHUNK 4096
+struct WorkList {
+  const uint32_t* tile;  // tile index of chunk w
+  const uint32_t* beg;   // first particle of chunk w
+  const uint32_t* count; // number of chunks (device scalar)
+};
+__device__ __forceinline__ int tile_of_raster(const TileGeom& tg, int rpos) {
+  const int L = rpos / tg.ntx;
+  const int ttx = rpos - L * tg.ntx;
   const int band = L / (NNPM_YB * tg.ntz);
   const int rows = min(NNPM_YB, tg.nty - band * NNPM_YB);
   const int r = L - band * NNPM_YB * tg.ntz;
-  ttz = r / rows;
-  tty = band * NNPM_YB + (r - ttz * rows);
+  const int ttz = r / rows;
+  const int tty = band * NNPM_YB + (r - ttz * rows);
+  return ttx + tg.ntx * (tty + tg.nty * ttz);
+}
+// chunks per raster position (exclusive-scanned afterwards); nw[ntiles] = 0 receives the total
+__global__ void k_work_count(TileGeom tg, i64 ntiles, const uint32_t* __restrict__ tile_off, uint32_t* __restrict__ nw) {
+  const i64 r = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (r > ntiles) return;
+  if (r == ntiles) { nw[r] = 0u; return; }
+  const int t = tile_of_raster(tg, (int)r);
+  const uint32_t cnt = tile_off[t + 1] - tile_off[t];
+  nw[r] = (cnt + NNPM_CHUNK - 1) / NNPM_CHUNK;
+}
+__global__ void k_work_fill(TileGeom tg, i64 ntiles, const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ woff,
+                            uint32_t* __restrict__ wtile, uint32_t* __restrict__ wbeg) {
+  const i64 r = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (r >= ntiles) return;
+  const int t = tile_of_raster(tg, (int)r);
+  const uint32_t n0 = tile_off[t], n1 = tile_off[t + 1];
+  uint32_t w = woff[r];
+  for (uint32_t b = n0; b < n1; b += NNPM_CHUNK, w++) { wtile[w] = (uint32_t)t; wbeg[w] = b; }
 }
 
 // Fast-path gather: same operator as cic_grad_gather with the products re-associated so that the
@@ -800,19 +828,20 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
 
 template <int RANK, bool COMOVING, int MINB>
 __global__ void __launch_bounds__(256, MINB)
-k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g, TileGeom tg,
+k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g, TileGeom tg, WorkList wl,
             const uint32_t* __restrict__ tile_off, const double* __restrict__ phi, PushParams pp, i64* __restrict__ red,
             uint32_t* __restrict__ slow_list, u64* __restrict__ slow_count) {
   extern __shared__ __align__(128) double box[];  // [BZ][BY][BX]
   __shared__ __align__(8) unsigned long long mbar;
   constexpr int BX = NNPM_BX, BY = NNPM_BY, BZ = (RANK == 3) ? NNPM_BZ : 1, BXY = BX * BY;
-  int ttx, tty, ttz;
-  tile_of_block(tg, ttx, tty, ttz);
-  const int t = ttx + tg.ntx * (tty + tg.nty * ttz);
-  const i64 n0 = tile_off[t];
-  i64 n1 = tile_off[t + 1];
+  if (blockIdx.x >= *wl.count) return;  // the grid is sized for the worst case
+  const int t = (int)wl.tile[blockIdx.x];
+  const i64 n0 = wl.beg[blockIdx.x];
+  i64 n1 = n0 + NNPM_CHUNK;
+  if (n1 > (i64)tile_off[t + 1]) n1 = tile_off[t + 1];
   if (n1 > np) n1 = np;
   if (n0 >= n1) return;  // uniform across the block
+  const int ttx = t % tg.ntx, tty = (t / tg.ntx) % tg.nty, ttz = t / (tg.ntx * tg.nty);
   const int N1 = (int)g.N1, N2 = (int)g.N2, N3 = (int)g.N3;
   const int ti0 = ttx * tg.tx, tj0 = tty * tg.ty, tk0 = ttz * tg.tz;  // tk0: plane within the slab
   // Stage the phi box.  Interior tiles (box inside the mesh, no periodic wrap): ONE TMA tensor copy
@@ -957,19 +986,20 @@ __device__ __forceinline__ void bulk_reduce_add(void* gdst, const void* ssrc, un
 // BULK: flush rows with cp.reduce.async.bulk (needs N1 even and >= NNPM_DX); otherwise per-cell atomics.
 template <int RANK, bool FIXED, bool PRE>
 __global__ void __launch_bounds__(256)
-k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, const uint32_t* __restrict__ tile_off,
+k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, WorkList wl, const uint32_t* __restrict__ tile_off,
                double* __restrict__ mesh, double m, double fscale, uint32_t* __restrict__ slow_list,
                u64* __restrict__ slow_count, int bulk) {
   constexpr int DX = NNPM_DX, DY = NNPM_DY, DZ = (RANK == 3) ? NNPM_DZ : 1, DXY = DX * DY, NBOX = DXY * DZ;
   // accumulators: little-endian (lo, hi) uint32 pairs == one u64 per cell; converted in place to f64
   __shared__ __align__(16) uint32_t acc[2 * NBOX];
-  int ttx, tty, ttz;
-  tile_of_block(tg, ttx, tty, ttz);
-  const int t = ttx + tg.ntx * (tty + tg.nty * ttz);
-  const i64 n0 = tile_off[t];
-  i64 n1 = tile_off[t + 1];
+  if (blockIdx.x >= *wl.count) return;  // the grid is sized for the worst case
+  const int t = (int)wl.tile[blockIdx.x];
+  const i64 n0 = wl.beg[blockIdx.x];
+  i64 n1 = n0 + NNPM_CHUNK;
+  if (n1 > (i64)tile_off[t + 1]) n1 = tile_off[t + 1];
   if (n1 > np) n1 = np;
   if (n0 >= n1) return;  // uniform across the block
+  const int ttx = t % tg.ntx, tty = (t / tg.ntx) % tg.nty, ttz = t / (tg.ntx * tg.nty);
   for (int c = threadIdx.x; c < NBOX / 2; c += 256) ((uint4*)acc)[c] = make_uint4(0u, 0u, 0u, 0u);
   if (threadIdx.x == 0 && (NBOX & 1)) { acc[2 * NBOX - 2] = 0u; acc[2 * NBOX - 1] = 0u; }
   const int N1 = (int)g.N1, N2 = (int)g.N2, N3 = (int)g.N3;
@@ -1182,6 +1212,55 @@ __global__ void k_init_synth(PartPtrs p, uint32_t* ids, i64 nloc, i64 first, i64
   for (int d = 0; d < RANK; d++) {
     p.x[d][t] = wrap01(q[d] + psi[d]);
     p.v[d][t] = vfac * psi[d];
+  }
+  ids[t] = (uint32_t)gidx;
+}
+
+// Clustered late-time stand-in (BASELINE config 4): even-hash particles stay on
+// the lattice, the others fall into `nblobs` Gaussian blobs of width sigma with a b^-1/2 mass function
+// (blob rank b in [1, nblobs]); centres, membership and offsets are pure functions of (seed, global
+// particle index), so any decomposition generates the same particles.  Mirrored by
+// oracle/pm_ref.py:synthetic_clustered.
+__device__ __forceinline__ u64 mix64(u64 z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ double u01(u64 h) { return ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+template <int RANK>
+__global__ void k_init_clustered(PartPtrs p, uint32_t* ids, i64 nloc, i64 first, i64 P1, i64 P2, i64 P3, u64 seed, i64 nblobs,
+                                 double sigma, double vdisp) {
+  i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t >= nloc) return;
+  const i64 gidx = first + t;
+  const i64 i = gidx % P1, j = (gidx / P1) % P2, k = gidx / (P1 * P2);
+  double x[3];
+  x[0] = __ddiv_rn(__dsub_rn((double)(i + 1), 0.5), (double)P1);
+  x[1] = __ddiv_rn(__dsub_rn((double)(j + 1), 0.5), (double)P2);
+  x[2] = (RANK == 3) ? __ddiv_rn(__dsub_rn((double)(k + 1), 0.5), (double)P3) : 0.0;
+  const u64 h0 = mix64(seed ^ mix64((u64)gidx));
+  double v[3] = {0.0, 0.0, 0.0};
+  if (h0 & 1ull) {
+    const double u = u01(mix64(h0 + 1));
+    const double sq = 1.0 + u * (sqrt((double)nblobs) - 1.0);
+    i64 b = (i64)(sq * sq);
+    if (b > nblobs) b = nblobs;
+    const u64 hb = mix64(seed * 0x100000001B3ull + (u64)b);
+#pragma unroll
+    for (int d = 0; d < RANK; d++) {
+      const double c = u01(mix64(hb + 11 * (d + 1)));
+      const double u1 = u01(mix64(h0 + 101 * (d + 1))), u2 = u01(mix64(h0 + 211 * (d + 1)));
+      const double r = sqrt(-2.0 * log(u1));
+      x[d] = c + sigma * r * cospi(2.0 * u2);
+      x[d] -= floor(x[d]);
+      v[d] = vdisp * r * sinpi(2.0 * u2);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < RANK; d++) {
+    p.x[d][t] = x[d];
+    p.v[d][t] = v[d];
   }
   ids[t] = (uint32_t)gidx;
 }

@@ -145,7 +145,7 @@ class DevicePM:
     def init_synthetic(self, pdims, kind="zeldovich", seed=12345, nmodes=32, kmax=8, disp_rms=0.0,
                        vfac=0.0, m=1.0):
         pd = (C.c_int64 * 3)(*[int(p) for p in pdims])
-        k = _lib.IC_ZELDOVICH_MODES if kind == "zeldovich" else _lib.IC_LATTICE
+        k = {"zeldovich": _lib.IC_ZELDOVICH_MODES, "lattice": _lib.IC_LATTICE, "clustered": _lib.IC_CLUSTERED}[kind]
         self.m = float(m)
         self._ck(self._L.nnpm_init_synthetic(self._h, k, pd, int(seed), int(nmodes), int(kmax),
                                              float(disp_rms), float(vfac), self.m))

@@ -441,6 +441,45 @@ def synthetic_zeldovich(pdims, rank, seed, nmodes, kmax, disp_rms, vfac):
     return x, v
 
 
+def _mix64(z):
+    z = np.asarray(z, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def _u01(h):
+    return ((h >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+
+
+def synthetic_clustered(pdims, rank, seed, nblobs, sigma, vdisp):
+    """Clustered stand-in for BASELINE config 4 (NOT in the reference): mirrors the device generator
+    k_init_clustered hash for hash.  Half the particles on the lattice, half in Gaussian blobs with a
+    b^-1/2 mass function."""
+    x = initialize_particles_uniform(pdims, rank)
+    v = np.zeros_like(x)
+    n = x.shape[0]
+    with np.errstate(over="ignore"):
+        h0 = _mix64(np.uint64(seed) ^ _mix64(np.arange(n, dtype=np.uint64)))
+        cl = (h0 & np.uint64(1)) == np.uint64(1)
+        u = _u01(_mix64(h0 + np.uint64(1)))
+        sq = 1.0 + u * (math.sqrt(float(nblobs)) - 1.0)
+        b = np.minimum((sq * sq).astype(np.int64), nblobs).astype(np.uint64)
+        hb = _mix64(np.uint64(seed) * np.uint64(0x100000001B3) + b)
+        for d in range(rank):
+            c = _u01(_mix64(hb + np.uint64(11 * (d + 1))))
+            u1 = _u01(_mix64(h0 + np.uint64(101 * (d + 1))))
+            u2 = _u01(_mix64(h0 + np.uint64(211 * (d + 1))))
+            r = np.sqrt(-2.0 * np.log(u1))
+            xd = c + sigma * r * np.cos(2.0 * math.pi * u2)
+            xd -= np.floor(xd)
+            x[cl, d] = xd[cl]
+            v[cl, d] = (vdisp * r * np.sin(2.0 * math.pi * u2))[cl]
+    return x, v
+
+
 # --------------------------------------------------------------------------------------
 # P(k)                                                            ParticleMesh.jl:65-100, 202-206
 # --------------------------------------------------------------------------------------

@@ -341,6 +341,38 @@ def test_synthetic_ics_match_oracle(lib_built, O):
         assert np.max(np.abs(vg - vr)) < 1e-13
 
 
+@pytest.mark.parametrize("mode", ["atomic", "fixedpoint"])
+def test_clustered_state_matches_oracle(lib_built, O, mode):
+    """BASELINE config 4 stand-in at test size: device-generated clustered particles equal the oracle's
+    generator; a tile then holds many chunks of the work list (collapsed blobs), and the tiled deposit /
+    push on that state equal the oracle."""
+    from noname_b200 import DevicePM
+    dims, n = (32, 32, 32), 48
+    xr, vr = O.synthetic_clustered((n, n, n), 3, 777, 3, 0.5 / 32, 0.002)
+    m = 32.0 ** 3 / n ** 3
+    with DevicePM(dims, n ** 3, rank=3, sort_every=1, deposit_mode=mode) as dev:
+        dev.init_synthetic((n, n, n), kind="clustered", seed=777, nmodes=3, kmax=1, disp_rms=0.5 / 32, vfac=0.002, m=m)
+        xg, vg = dev.download()
+        assert np.max(np.abs(xg - xr)) < 1e-13 and np.max(np.abs(vg - vr)) < 1e-15
+        dev.upload(xr, vr, m)                      # identical inputs from here on
+        f = O.Fields(dims, n ** 3, 3)
+        rho_ref = np.zeros((32, 32, 32))
+        O.deposit(rho_ref, xr.copy(), m, interpolation="cic")
+        assert rho_ref.max() > 1000 * rho_ref.mean()   # genuinely clustered: > 10^3 x the mean occupancy
+        for it in range(3):
+            sc = (1.0 + 0.01 * it, 1.02, 0.9, 1.03)
+            O.step_comoving(f, xr, vr, m, 0.01, *sc)
+            st = dev.step_comoving(0.01, *sc)
+            assert st.n_halo_violations == 0
+        assert nlinf(dev.get_field("phi"), f.phi) < 1e-11
+        xg, vg = dev.download()
+        assert np.max(np.abs(xg - xr)) < 1e-11 and nlinf(vg, vr) < 1e-10
+        dev.deposit()
+        ref = np.zeros((32, 32, 32))
+        O.deposit(ref, xr.copy(), m, interpolation="cic")
+        assert nlinf(dev.get_field("rho"), ref) < TOL
+
+
 def test_sort_keeps_particles_and_restores_order(lib_built):
     from noname_b200 import DevicePM
     x, v = make_particles(21, 10000, 3)
