@@ -1,7 +1,7 @@
 # quick perf probe (scratch; not part of the product)
 import sys, time
 import numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from noname_b200 import DevicePM
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 opts = dict(kv.split('=') for kv in sys.argv[2:])
