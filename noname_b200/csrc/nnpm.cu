@@ -118,7 +118,7 @@ struct nnpm_ctx {
   bool have_tm_y, have_tm_z, have1;
   double2* ytw;
   cufftHandle plan1f, plan1b;  // batched 1-D x transforms (r2c / c2r) over the owned rows
-  int opt_colfft, opt_colfft_z, opt_cfrun_y, opt_cfrun_z, nsm;
+  int opt_push_tma, opt_colfft, opt_colfft_z, opt_cfrun_y, opt_cfrun_z, nsm;
   cudaStream_t st2[4];    // side streams: the blocks of a transpose go out on several copy engines at once
   cudaEvent_t ev_fork, ev_join[4];
 };
@@ -376,7 +376,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->peer_ok = false; c->opt_peer = 1; c->bar_buf = nullptr;
   c->ev_fork = nullptr;
   for (int i = 0; i < 4; i++) { c->st2[i] = nullptr; c->ev_join[i] = nullptr; }
-  c->have_tm_y = c->have_tm_z = c->have1 = false; c->ytw = nullptr; c->opt_colfft = 1; c->opt_colfft_z = 0; c->opt_cfrun_y = 1; c->opt_cfrun_z = 1; c->nsm = 148;
+  c->have_tm_y = c->have_tm_z = c->have1 = false; c->ytw = nullptr; c->opt_push_tma = 0; c->opt_colfft = 1; c->opt_colfft_z = 0; c->opt_cfrun_y = 1; c->opt_cfrun_z = 1; c->nsm = 148;
   c->mig_lo = nullptr; c->ghost_rx = nullptr; c->red_buf = nullptr;
   c->np = 0; c->m = 0.0; c->ids_dirty = false; c->field_state = 0;
   c->own_stream = false;
@@ -404,8 +404,9 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   }
   for (int d = 0; d < 3; d++) { c->pp.x[d] = nullptr; c->pp.v[d] = nullptr; }
   for (int d = 0; d < c->R; d++) {
-    CKB(CKR(dalloc(c, &c->pp.x[d], (size_t)c->cap)));
-    CKB(CKR(dalloc(c, &c->pp.v[d], (size_t)c->cap)));
+    // +2: the bulk-copy push rounds its last 16-byte unit up and may read one element past np
+    CKB(CKR(dalloc(c, &c->pp.x[d], (size_t)c->cap + 2)));
+    CKB(CKR(dalloc(c, &c->pp.v[d], (size_t)c->cap + 2)));
   }
   CKB(CKR(dalloc(c, &c->ids, (size_t)c->cap)));
   CKB(CKR(dalloc(c, &c->d_red, 8)));
@@ -536,7 +537,7 @@ extern "C" int nnpm_upload_particles(nnpm_ctx* ctx, const double* x_aos, const d
 }
 
 static int ensure_spare(nnpm_ctx* ctx) {
-  if (!ctx->spare) CKR(dalloc(ctx, &ctx->spare, (size_t)ctx->cap));
+  if (!ctx->spare) CKR(dalloc(ctx, &ctx->spare, (size_t)ctx->cap + 2));
   if (!ctx->ids_spare) CKR(dalloc(ctx, &ctx->ids_spare, (size_t)ctx->cap));
   return NNPM_OK;
 }
@@ -1066,6 +1067,21 @@ static int launch_push(nnpm_ctx* ctx, bool comoving, const PushParams& pp) {
   const i64 covered = ctx->sorted_np < np ? ctx->sorted_np : np;
   const WorkList wl = {ctx->wtile, ctx->wbeg, ctx->wcnt + ctx->ntiles};
   const unsigned wgrid = (unsigned)(ctx->ntiles + ctx->sorted_np / NNPM_CHUNK + 1);  // >= number of chunks
+  // measured at 1024^3 (B200): register-load k_push_tile 25.3 ms; bulk-copy k_push_tma 26.8 ms -- the kernel
+  // is bound by instruction issue (FP64 + shared-memory gather), not by bytes in flight, so the
+  // DMA-warp variant stays an option ("push_tma") and the register-load kernel is the default
+  if (ctx->opt_push_tma) {
+    const size_t box_d = ((size_t)NNPM_BX * NNPM_BY * (RANK == 3 ? NNPM_BZ : 1) + 15) & ~(size_t)15;
+    const size_t smem2 = (box_d + (size_t)2 * 2 * RANK * NNPM_PS) * sizeof(double);
+#define LM(CM)                                                                                                      \
+  do {                                                                                                              \
+    CK(cudaFuncSetAttribute(k_push_tma<RANK, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));         \
+    k_push_tma<RANK, CM><<<wgrid, 288, smem2, ctx->st>>>(ctx->tmap_phi, ctx->pp, covered, ctx->g, ctx->tg, wl, ctx->hist, \
+                                                         ctx->mesh, pp, ctx->d_red, ctx->srnk, slow_count);          \
+  } while (0)
+    if (comoving) LM(true); else LM(false);
+#undef LM
+  } else {
 #define LT(CM, MB)                                                                                                  \
   do {                                                                                                              \
     CK(cudaFuncSetAttribute(k_push_tile<RANK, CM, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
@@ -1075,6 +1091,7 @@ static int launch_push(nnpm_ctx* ctx, bool comoving, const PushParams& pp) {
   if (ctx->opt_push_minb >= 3) { if (comoving) LT(true, 3); else LT(false, 3); }
   else { if (comoving) LT(true, 2); else LT(false, 2); }
 #undef LT
+  }
   LAUNCHED(ctx);
   global_push(0, 0, ctx->srnk, 148 * 4);                       // stragglers (device-side count)
   if (np > covered) global_push(covered, np - covered, nullptr, nblk(np - covered, 256));  // arrivals since the sort
@@ -1191,6 +1208,7 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   else if (!strcmp(name, "zcols")) ctx->opt_zcols = v;
   else if (!strcmp(name, "bulk_flush")) ctx->opt_bulk_flush = v;
   else if (!strcmp(name, "colfft")) ctx->opt_colfft = v;
+  else if (!strcmp(name, "push_tma")) ctx->opt_push_tma = v;
   else if (!strcmp(name, "colfft_z")) ctx->opt_colfft_z = v;
   else if (!strcmp(name, "cfrun_y")) ctx->opt_cfrun_y = v < 1 ? 1 : v;
   else if (!strcmp(name, "cfrun_z")) ctx->opt_cfrun_z = v < 1 ? 1 : v;

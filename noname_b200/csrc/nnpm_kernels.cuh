@@ -952,6 +952,223 @@ k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g
   }
   block_max3(mxa, mxv, mxp, red);
 }
+// ------------------------------------------------------------------------------------------
+// Tiled push with the particle streams on the TMA engine.  Same arithmetic as k_push_tile; what changes
+// is who talks to HBM: a dedicated DMA warp streams the work item's six arrays through two
+// shared-memory stages of NNPM_PS particles with cp.async.bulk (global -> shared, mbarrier
+// completion) and writes the updated x, v back with cp.async.bulk (shared -> global), while the eight
+// compute warps only ever touch shared memory.  Register loads keep too few bytes in flight per SM
+// for this kernel (ncu: 57 % of DRAM peak at 25 % occupancy, long_scoreboard stalls); the bulk
+// copies keep ~48 KB per CTA in flight regardless of occupancy.
+//   Bulk copies move 16-byte units: stages start at even particle indices; a work item whose first
+//   (last) particle has an odd (even) index shares a unit with the neighbouring item -- those single
+//   edge elements are excluded from the bulk store and written by ordinary stores.
+//   Particles that left the tile's box keep their original values in the stage (the bulk store writes
+//   them back unchanged) and go to the slow list, as in k_push_tile.
+// ------------------------------------------------------------------------------------------
+#define NNPM_PS 512  // particles per stage: 6 arrays x 4 KB
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int RANK, bool COMOVING>
+__global__ void __launch_bounds__(288, 2)
+k_push_tma(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g, TileGeom tg, WorkList wl,
+           const uint32_t* __restrict__ tile_off, const double* __restrict__ phi, PushParams pp, i64* __restrict__ red,
+           uint32_t* __restrict__ slow_list, u64* __restrict__ slow_count) {
+  extern __shared__ __align__(128) double sm_push[];  // box [BZ][BY][BX], then stages [2][2*RANK][NNPM_PS]
+  __shared__ __align__(8) unsigned long long mbar, full[2], done[2];
+  constexpr int BX = NNPM_BX, BY = NNPM_BY, BZ = (RANK == 3) ? NNPM_BZ : 1, BXY = BX * BY, NA = 2 * RANK, S = NNPM_PS;
+  double* box = sm_push;
+  double* stage = sm_push + ((BXY * BZ + 15) & ~15);
+  if (blockIdx.x >= *wl.count) return;  // the grid is sized for the worst case
+  const int t = (int)wl.tile[blockIdx.x];
+  const i64 n0 = wl.beg[blockIdx.x];
+  i64 n1 = n0 + NNPM_CHUNK;
+  if (n1 > (i64)tile_off[t + 1]) n1 = tile_off[t + 1];
+  if (n1 > np) n1 = np;
+  if (n0 >= n1) return;  // uniform across the block
+  const int ttx = t % tg.ntx, tty = (t / tg.ntx) % tg.nty, ttz = t / (tg.ntx * tg.nty);
+  const int N1 = (int)g.N1, N2 = (int)g.N2, N3 = (int)g.N3;
+  const int ti0 = ttx * tg.tx, tj0 = tty * tg.ty, tk0 = ttz * tg.tz;
+  const int bx0 = ti0 - NNPM_TH - 1, by0 = tj0 - NNPM_TH - 1;
+  const int bz0 = (RANK == 3) ? tk0 - NNPM_TH - 1 + g.glo : g.glo;
+  const bool interior = bx0 >= 0 && bx0 + BX - 1 <= N1 && by0 >= 0 && by0 + BY <= N2 &&
+                        (RANK == 2 || g.glo != 0 || (bz0 >= 0 && bz0 + BZ <= N3));
+  const i64 base = n0 & ~1ll;                       // even: 16-byte aligned in every array
+  const int span = (int)(n1 - base);                // particles from base to the end of the item
+  const int nst = (span + S - 1) / S;               // stages
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&mbar, 1);
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    mbar_init(&done[0], 256); mbar_init(&done[1], 256);
+  }
+  __syncthreads();
+  const double* gin[6] = {p.x[0], p.x[1], RANK == 3 ? p.x[2] : p.v[0], RANK == 3 ? p.v[0] : p.v[1], p.v[1], p.v[2]};
+  double* gout[6] = {p.x[0], p.x[1], RANK == 3 ? p.x[2] : p.v[0], RANK == 3 ? p.v[0] : p.v[1], p.v[1], p.v[2]};
+  // array a of the stage: a < RANK -> x[a], else v[a - RANK]
+  auto stage_len = [&](int s) { int l = span - s * S; l = l < S ? l : S; return (l + 1) & ~1; };  // even, may read 1 past n1
+  if (warp == 8) {
+    // ------------------------------------------------ DMA warp (lane 0 issues, the warp stays converged)
+    if (lane == 0) {
+      if (interior) {
+        mbar_expect_tx(&mbar, (unsigned)(BX * BY * BZ * sizeof(double)));
+        tma_load_3d(box, &tmap, bx0, by0, bz0, &mbar);
+      }
+      auto load_stage = [&](int s) {
+        const int b = s & 1, len = stage_len(s);
+        mbar_expect_tx(&full[b], (unsigned)(NA * len * 8));
+#pragma unroll
+        for (int a = 0; a < NA; a++) bulk_load(stage + (b * NA + a) * S, gin[a] + base + (i64)s * S, (unsigned)len * 8u, &full[b]);
+      };
+      load_stage(0);
+      if (nst > 1) load_stage(1);
+      unsigned dph[2] = {0u, 0u};
+      for (int s = 0; s < nst; s++) {
+        const int b = s & 1;
+        mbar_wait(&done[b], dph[b]);   // all 256 compute threads finished stage s (their writes fenced)
+        dph[b] ^= 1u;
+        // bulk-store the units fully inside [n0, n1)
+        i64 lo = base + (i64)s * S, hi = lo + S;
+        if (lo < n0) lo = n0 + 1;                       // n0 odd: unit (n0-1, n0) is shared with the previous item
+        if (hi > n1) hi = n1 & ~1ll;                    // n1 odd: unit (n1-1, n1) is shared with the next item
+        if (hi > lo) {
+          const int off = (int)(lo - (base + (i64)s * S));
+#pragma unroll
+          for (int a = 0; a < NA; a++) bulk_store(gout[a] + lo, stage + (b * NA + a) * S + off, (unsigned)(hi - lo) * 8u);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (s + 2 < nst) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage may be overwritten now
+          load_stage(s + 2);
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    return;
+  }
+  // ---------------------------------------------------- compute warps (256 threads)
+  if (!interior) {
+    int gi0 = wrap_small(bx0 + lane, N1);
+    int gi1 = wrap_small(bx0 + lane + 32, N1);
+    for (int row = warp; row < BY * BZ; row += 8) {
+      const int byi = row % BY, bzi = row / BY;  // compile-time divisors
+      const int gj = wrap_small(by0 + byi, N2);
+      int lp = g.glo;
+      bool valid = true;
+      if (RANK == 3) {
+        lp = bz0 + bzi;
+        if (g.glo) valid = lp >= 0 && lp < g.nplanes;
+        else lp = wrap_small(lp, N3);
+      }
+      const double* src = phi + g.plane * (i64)lp + (unsigned)((int)g.rowp * gj);
+      double* dst = box + row * BX;
+      if (valid) {
+        __pipeline_memcpy_async(dst + lane, src + gi0, 8);
+        if (lane + 32 < BX - 1) __pipeline_memcpy_async(dst + lane + 32, src + gi1, 8);
+      } else {
+        dst[lane] = 0.0;
+        if (lane + 32 < BX - 1) dst[lane + 32] = 0.0;
+      }
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // compute warps only (the DMA warp never joins)
+  } else {
+    mbar_wait(&mbar, 0);
+  }
+  const double gfac = -0.5 * g.fN1;
+  const double ra = 1.0 / pp.a;
+  const int oi = ti0 - NNPM_TH, oj = tj0 - NNPM_TH, ok = (int)g.kz0 + tk0 - NNPM_TH;
+  const unsigned fx = tg.tx + 2 * NNPM_TH, fy = tg.ty + 2 * NNPM_TH, fz = tg.tz + 2 * NNPM_TH;
+  double mxa = -INFINITY, mxv = -INFINITY, mxp = -INFINITY;
+  unsigned fph[2] = {0u, 0u};
+  for (int s = 0; s < nst; s++) {
+    const int b = s & 1;
+    double* sx = stage + b * NA * S;
+    mbar_wait(&full[b], fph[b]);
+    fph[b] ^= 1u;
+#pragma unroll
+    for (int h = 0; h < S / 256; h++) {
+      const int q = threadIdx.x + 256 * h;
+      const i64 n = base + (i64)s * S + q;
+      if (n < n0 || n >= n1) continue;
+      double x[3] = {0.0, 0.0, 0.0}, v[3] = {0.0, 0.0, 0.0}, pa[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int d = 0; d < RANK; d++) {
+        x[d] = sx[d * S + q];
+        v[d] = sx[(RANK + d) * S + q];
+        if (COMOVING) x[d] = __dadd_rn(x[d], __dmul_rn(pp.c0, v[d]));
+        x[d] = wrap01_sel(x[d]);
+      }
+      int i, j, k = 0;
+      double dx, dy, dz = 0.0;
+      cell_fast(x[0], g.fN1, i, dx);
+      cell_fast(x[1], g.fN2, j, dy);
+      const unsigned ri = (unsigned)tile_rel(i, oi, N1), rj = (unsigned)tile_rel(j, oj, N2);
+      unsigned rk = 0;
+      bool fast = ri < fx && rj < fy;
+      if (RANK == 3) {
+        cell_fast(x[2], g.fN3, k, dz);
+        rk = (unsigned)tile_rel(k, ok, N3);
+        fast = fast && rk < fz;
+      }
+      if (!fast) {
+        slow_list[atomicAdd(slow_count, 1ull)] = (uint32_t)n;
+        continue;
+      }
+      const double* b0 = box + (rk * BXY + rj * BX + ri);
+      if (RANK == 2) cic_grad_gather_fma<2>([&](int a, int bb, int) { return b0[bb * BX + a]; }, dx, dy, 0.0, gfac, pa);
+      else cic_grad_gather_fma<3>([&](int a, int bb, int c) { return b0[c * BXY + bb * BX + a]; }, dx, dy, dz, gfac, pa);
+      const bool edge = (n == n0 && (n0 & 1)) || (n == n1 - 1 && (n1 & 1));  // unit shared with a neighbouring item
+#pragma unroll
+      for (int d = 0; d < RANK; d++) {
+        double vn, xn;
+        if (COMOVING) {
+          const double vmid = __dadd_rn(v[d], __dmul_rn(__dmul_rn(pa[d], pp.dt), 0.5));
+          const double tt = __dadd_rn(__dmul_rn(-vmid, pp.hub), div_by_scalar(pa[d], pp.a, ra));
+          vn = __dadd_rn(v[d], __dmul_rn(tt, pp.dt));
+          xn = wrap01_sel(__dadd_rn(x[d], __dmul_rn(pp.c2, vn)));
+        } else {
+          const double x1 = __dadd_rn(x[d], __dmul_rn(pp.c1, v[d]));
+          vn = __dadd_rn(v[d], __dmul_rn(pp.dt, pa[d]));
+          xn = __dadd_rn(x1, __dmul_rn(pp.c1, vn));
+        }
+        sx[d * S + q] = xn;
+        sx[(RANK + d) * S + q] = vn;
+        if (edge) { p.x[d][n] = xn; p.v[d][n] = vn; }
+        mxa = fmax(mxa, fabs(vn));
+        mxv = fmax(mxv, vn);
+        mxp = fmax(mxp, pa[d]);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // stage writes -> bulk store reads
+    mbar_arrive(&done[b]);
+  }
+  // block_max3 uses __syncthreads: not available with the DMA warp gone -> named barrier version
+  {
+    __shared__ i64 smax[3];
+    if (threadIdx.x < 3) smax[threadIdx.x] = (i64)0x8000000000000000ull;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const i64 ka = warp_max_key(ord_encode(mxa)), kb = warp_max_key(ord_encode(mxv)), kc = warp_max_key(ord_encode(mxp));
+    if (lane == 0) {
+      atomicMax(&smax[0], ka);
+      atomicMax(&smax[1], kb);
+      atomicMax(&smax[2], kc);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (threadIdx.x < 3) atomicMax(&red[threadIdx.x], smax[threadIdx.x]);
+  }
+}
 #undef PHI
 
 // ------------------------------------------------------------------------------------------

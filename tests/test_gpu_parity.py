@@ -273,7 +273,8 @@ def test_fused_step_matches_oracle(lib_built, O, dims, rank, comoving, sort):
 
 @pytest.mark.parametrize("dims,rank", [((48, 20, 1), 2), ((64, 64, 1), 2), ((40, 24, 20), 3), ((64, 32, 32), 3)])
 @pytest.mark.parametrize("comoving", [False, True])
-def test_tiled_push_multi_step_matches_oracle(lib_built, O, dims, rank, comoving):
+@pytest.mark.parametrize("push_tma", [0, 1])
+def test_tiled_push_multi_step_matches_oracle(lib_built, O, dims, rank, comoving, push_tma):
     """Tile-sorted shared-memory path over several steps (particles stray from their tiles between
     sorts and take the global fallback): same trajectory as the oracle."""
     from noname_b200 import DevicePM
@@ -285,6 +286,7 @@ def test_tiled_push_multi_step_matches_oracle(lib_built, O, dims, rank, comoving
     xr, vr = x.copy(), v.copy()
     untiled = 0
     with DevicePM(dims, npart, rank=rank, sort_every=4) as dev:
+        dev.set_option("push_tma", push_tma)
         dev.upload(x, v, m)
         for it in range(6):
             dt = 0.02
