@@ -118,6 +118,10 @@ struct nnpm_ctx {
   bool have_tm_y, have_tm_z, have1;
   double2* ytw;
   cufftHandle plan1f, plan1b;  // batched 1-D x transforms (r2c / c2r) over the owned rows
+  cufftHandle plan1fc;         // the same over one chunk of planes (pipelined multi-GPU solve)
+  bool have1c;
+  int opt_pipeline;
+  cudaEvent_t ev_chunk[4];
   int opt_push_tma, opt_colfft, opt_colfft_z, opt_cfrun_y, opt_cfrun_z, nsm;
   cudaStream_t st2[4];    // side streams: the blocks of a transpose go out on several copy engines at once
   cudaEvent_t ev_fork, ev_join[4];
@@ -197,9 +201,9 @@ static int grow_fftwork(nnpm_ctx* ctx, size_t need) {
   ctx->fftwork = q;
   ctx->fftwork_bytes = need;
   ctx->dev_bytes += need;
-  cufftHandle hs[7] = {ctx->plan2f, ctx->plan2b, ctx->planz, ctx->plan3f, ctx->plan3b, ctx->plan1f, ctx->plan1b};
-  bool on[7] = {ctx->have2, ctx->have2, ctx->havez, ctx->have3, ctx->have3, ctx->have1, ctx->have1};
-  for (int i = 0; i < 7; i++)
+  cufftHandle hs[8] = {ctx->plan2f, ctx->plan2b, ctx->planz, ctx->plan3f, ctx->plan3b, ctx->plan1f, ctx->plan1b, ctx->plan1fc};
+  bool on[8] = {ctx->have2, ctx->have2, ctx->havez, ctx->have3, ctx->have3, ctx->have1, ctx->have1, ctx->have1c};
+  for (int i = 0; i < 8; i++)
     if (on[i]) CKF(cufftSetWorkArea(hs[i], ctx->fftwork));
   return NNPM_OK;
 }
@@ -376,6 +380,8 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->peer_ok = false; c->opt_peer = 1; c->bar_buf = nullptr;
   c->ev_fork = nullptr;
   for (int i = 0; i < 4; i++) { c->st2[i] = nullptr; c->ev_join[i] = nullptr; }
+  c->have1c = false; c->opt_pipeline = 1;
+  for (int i = 0; i < 4; i++) c->ev_chunk[i] = nullptr;
   c->have_tm_y = c->have_tm_z = c->have1 = false; c->ytw = nullptr; c->opt_push_tma = 0; c->opt_colfft = 1; c->opt_colfft_z = 0; c->opt_cfrun_y = 1; c->opt_cfrun_z = 1; c->nsm = 148;
   c->mig_lo = nullptr; c->ghost_rx = nullptr; c->red_buf = nullptr;
   c->np = 0; c->m = 0.0; c->ids_dirty = false; c->field_state = 0;
@@ -450,6 +456,8 @@ extern "C" int nnpm_destroy(nnpm_ctx* ctx) {
   comm_destroy(ctx);
   if (ctx->have2) { cufftDestroy(ctx->plan2f); cufftDestroy(ctx->plan2b); }
   if (ctx->have1) { cufftDestroy(ctx->plan1f); cufftDestroy(ctx->plan1b); }
+  if (ctx->have1c) cufftDestroy(ctx->plan1fc);
+  for (int i = 0; i < 4; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
   if (ctx->havez) cufftDestroy(ctx->planz);
   if (ctx->have3) { cufftDestroy(ctx->plan3f); cufftDestroy(ctx->plan3b); }
   for (void* p : ctx->allocs) cudaFree(p);
@@ -890,6 +898,52 @@ static int fft_inverse(nnpm_ctx* ctx, bool z_too, cudaEvent_t* comm_t) {
   return NNPM_OK;
 }
 
+// Multi-GPU solve with the NVLink transposes overlapped with the transforms: the owned planes are
+// transformed in NCH chunks, and as soon as a chunk's 2-D transform is done its block of the forward
+// transpose goes out on the copy engines (side streams) while the next chunk is computed; the fused
+// z pass is chunked over jl the same way for the backward transpose.  Only the last chunk's copies
+// (and the barrier) remain exposed.
+static int do_solve_pipelined(nnpm_ctx* ctx, cudaEvent_t* ev, double scale) {
+  const Geom& g = ctx->g;
+  const int NCH = 4;
+  double* own = ctx->mesh + g.plane * g.glo;
+  const i64 pc = g.nzl / NCH, jc = ctx->njl / NCH;
+  if (!ctx->have1c) {
+    size_t ws = 0;
+    long long n1[1] = {g.N1};
+    long long e1[1] = {g.rowp}, e2[1] = {ctx->icn};
+    CKR(new_plan(ctx, &ctx->plan1fc, 1, n1, e1, 1, g.rowp, e2, 1, ctx->icn, CUFFT_D2Z, g.N2 * pc, &ws));
+    ctx->have1c = true;
+    if (ws > ctx->fftwork_bytes) CKR(grow_fftwork(ctx, ws));
+    CKF(cufftSetWorkArea(ctx->plan1fc, ctx->fftwork));
+    for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
+  }
+  for (int c = 0; c < NCH; c++) {
+    double* pl = own + g.plane * pc * c;
+    CKF(cufftExecD2Z(ctx->plan1fc, pl, (cufftDoubleComplex*)pl));
+    LAUNCHED(ctx);
+    CKR(colfft_y(ctx, false, pc * c, pc));
+    CK(cudaEventRecord(ctx->ev_chunk[c], ctx->st));
+    CKR(comm_chunk_ce(ctx, true, c, NCH, ctx->ev_chunk[c]));
+  }
+  if (ev) CK(cudaEventRecord(ev[0], ctx->st));
+  CKR(comm_join_barrier(ctx));
+  if (ev) { CK(cudaEventRecord(ev[1], ctx->st)); CK(cudaEventRecord(ev[4], ctx->st)); }
+  const i64 cols = jc * ctx->icn;
+  for (int c = 0; c < NCH; c++) {
+    CKR(zfused_launch(ctx, (double2*)ctx->meshT, scale, cols * c, cols * (c + 1)));
+    CK(cudaEventRecord(ctx->ev_chunk[c], ctx->st));
+    CKR(comm_chunk_ce(ctx, false, c, NCH, ctx->ev_chunk[c]));
+  }
+  if (ev) { CK(cudaEventRecord(ev[5], ctx->st)); CK(cudaEventRecord(ev[2], ctx->st)); }
+  CKR(comm_join_barrier(ctx));
+  if (ev) CK(cudaEventRecord(ev[3], ctx->st));
+  CKR(colfft_y(ctx, true));
+  CKF(cufftExecZ2D(ctx->plan1b, (cufftDoubleComplex*)own, own));
+  LAUNCHED(ctx);
+  return NNPM_OK;
+}
+
 // compute_potential, ParticleMesh.jl:417-505: rho (in the mesh) -> phi (in the mesh).
 // ev (optional, 8 events): [0..3] around the transposes, [4],[5] around the z pass.
 static int do_solve(nnpm_ctx* ctx, cudaEvent_t* ev) {
@@ -897,6 +951,15 @@ static int do_solve(nnpm_ctx* ctx, cudaEvent_t* ev) {
   const double scale = 1.0 / ((double)g.N1 * (double)g.N2 * (double)g.N3) * 1 / ((double)g.N1 * (double)g.N1);
   const bool fft3d = ctx->opt_fft3d && ctx->P == 1 && g.N3 > 1;
   const bool fusedz = !fft3d && ctx->opt_zfused && g.N3 > 1 && zfused_supported(ctx);
+  if (ctx->P > 1 && ctx->opt_pipeline && ctx->peer_ok && ctx->opt_peer == 1 && fusedz && !ctx->opt_colfft_z && ctx->opt_colfft &&
+      colfft_supported_n(g.N2) && g.nzl % 4 == 0 && ctx->njl % 4 == 0) {
+    NEED_COMM();
+    CKR(do_solve_pipelined(ctx, ev, scale));
+    CKR(comm_fill_phi_ghosts(ctx));
+    ctx->field_state = 2;
+    ctx->acc_valid = false;
+    return NNPM_OK;
+  }
   double2* T = nullptr;
   CKR(fft_forward(ctx, &T, !fusedz, ev));
   if (ev) CK(cudaEventRecord(ev[4], ctx->st));
@@ -1208,6 +1271,7 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   else if (!strcmp(name, "zcols")) ctx->opt_zcols = v;
   else if (!strcmp(name, "bulk_flush")) ctx->opt_bulk_flush = v;
   else if (!strcmp(name, "colfft")) ctx->opt_colfft = v;
+  else if (!strcmp(name, "pipeline")) ctx->opt_pipeline = v;
   else if (!strcmp(name, "push_tma")) ctx->opt_push_tma = v;
   else if (!strcmp(name, "colfft_z")) ctx->opt_colfft_z = v;
   else if (!strcmp(name, "cfrun_y")) ctx->opt_cfrun_y = v < 1 ? 1 : v;

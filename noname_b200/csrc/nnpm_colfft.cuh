@@ -30,6 +30,7 @@ struct ColFftArgs {
   int nicg;           // groups per outer index = ceil(icn / 4)
   int icn;
   int run;            // adjacent groups a CTA processes back to back (1 or 2)
+  int outer0;         // first outer index (plane) of this launch: the y pass can run on a sub-range of planes
   i64 j0;             // global j of local row-block start (Green's function, z pass)
   const double* s1;   // sin^2 tables (z pass)
   const double* s2;
@@ -77,7 +78,7 @@ k_colfft(const __grid_constant__ CUtensorMap tmap, ColFftArgs a) {
   const int run = a.run;
   auto group_of = [&](int it) { return ((it / run) * (int)gridDim.x + (int)blockIdx.x) * run + it % run; };
   auto issue_load = [&](int g, int b) {  // thread 0 only
-    const int outer = g / a.nicg, icg = g - outer * a.nicg;
+    const int og = g / a.nicg, icg = g - og * a.nicg, outer = og + a.outer0;
     mbar_expect_tx(&full[b], (unsigned)(N * C * sizeof(double2)));
 #pragma unroll
     for (int o = 0; o < NOPS; o++) {
@@ -92,7 +93,7 @@ k_colfft(const __grid_constant__ CUtensorMap tmap, ColFftArgs a) {
   for (int it = 0; g < a.ngroups; it++) {
     const int b = it & 1;
     const int gnext = group_of(it + 1);
-    const int outer = g / a.nicg, icg = g - outer * a.nicg;
+    const int og_ = g / a.nicg, icg = g - og_ * a.nicg, outer = og_ + a.outer0;
     // prefetch the next group into the other buffer: its previous contents were stored one iteration
     // ago; the store must have finished READING shared memory before the load overwrites it
     if (tid == 0 && gnext < a.ngroups) {
@@ -243,7 +244,7 @@ static int colfft_dispatch(nnpm_ctx* ctx, i64 N, const CUtensorMap& tm, const Co
 static bool colfft_supported_n(i64 N) { int r1, r2; return zfused_factor(N, &r1, &r2); }
 
 // y pass over the owned planes, in place in the mesh (forward after the x r2c, inverse before the x c2r)
-static int colfft_y(nnpm_ctx* ctx, bool inverse) {
+static int colfft_y(nnpm_ctx* ctx, bool inverse, i64 plane0 = 0, i64 nplanes = -1) {
   const Geom& g = ctx->g;
   if (!ctx->have_tm_y) {
     CKR(colfft_tensor_map(ctx, &ctx->tm_y, ctx->mesh + g.plane * g.glo, g.N2, g.nzl, ctx->icn * 16, g.plane * 8, true, g.N2));
@@ -252,8 +253,10 @@ static int colfft_y(nnpm_ctx* ctx, bool inverse) {
   CKR(colfft_twiddles(ctx, &ctx->ytw, g.N2));
   ColFftArgs a;
   memset(&a, 0, sizeof a);
+  if (nplanes < 0) nplanes = g.nzl;
   a.nicg = (int)((ctx->icn + 3) / 4);
-  a.ngroups = (int)(g.nzl * a.nicg);
+  a.ngroups = (int)(nplanes * a.nicg);
+  a.outer0 = (int)plane0;
   a.icn = (int)ctx->icn;
   a.tw = ctx->ytw;
   a.scale = 1.0;

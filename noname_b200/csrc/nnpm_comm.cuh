@@ -318,6 +318,44 @@ static int comm_transpose_ce(nnpm_ctx* ctx, bool fwd) {
   return comm_barrier(ctx);
 }
 
+// Pipelined form: chunk c of nch.  forward: the planes [c*nzl/nch, (c+1)*nzl/nch) of this rank (all j);
+// backward: the rows jl in [c*njl/nch, (c+1)*njl/nch) of T (all k).  The copies are enqueued on the side
+// streams behind `after` (recorded by the caller on the compute stream when the chunk's data is ready),
+// so they run on the copy engines while the next chunk is being transformed.
+static int comm_chunk_ce(nnpm_ctx* ctx, bool fwd, int c, int nch, cudaEvent_t after) {
+  const Geom& g = ctx->g;
+  const size_t chunk = (size_t)ctx->njl * ctx->icn * 16;
+  const size_t plane_b = (size_t)g.plane * 8;
+  const size_t glo_b = (size_t)g.plane * g.glo * 8;
+  const int ns = ctx->P < 4 ? ctx->P : 4;
+  for (int i = 0; i < ns; i++) CK(cudaStreamWaitEvent(ctx->st2[i], after, 0));
+  for (int o = 0; o < ctx->P; o++) {
+    const int d = (ctx->r + o) % ctx->P;
+    cudaStream_t s = ctx->st2[o % ns];
+    if (fwd) {
+      const size_t pc = (size_t)g.nzl / nch;  // planes per chunk
+      const char* src = (const char*)ctx->mesh + glo_b + plane_b * pc * c + chunk * d;
+      char* dst = (char*)ctx->peer_meshT[d] + chunk * ((size_t)g.kz0 + pc * c);
+      CK(cudaMemcpy2DAsync(dst, chunk, src, plane_b, chunk, pc, cudaMemcpyDeviceToDevice, s));
+    } else {
+      const size_t wc = chunk / nch;          // bytes of the jl sub-block of one k row
+      const char* src = (const char*)ctx->meshT + chunk * (size_t)g.nzl * d + wc * c;
+      char* dst = (char*)ctx->peer_mesh[d] + glo_b + chunk * ctx->r + wc * c;
+      CK(cudaMemcpy2DAsync(dst, plane_b, src, chunk, wc, (size_t)g.nzl, cudaMemcpyDeviceToDevice, s));
+    }
+    ctx->launches += 1;
+  }
+  return NNPM_OK;
+}
+static int comm_join_barrier(nnpm_ctx* ctx) {
+  const int ns = ctx->P < 4 ? ctx->P : 4;
+  for (int i = 0; i < ns; i++) {
+    CK(cudaEventRecord(ctx->ev_join[i], ctx->st2[i]));
+    CK(cudaStreamWaitEvent(ctx->st, ctx->ev_join[i], 0));
+  }
+  return comm_barrier(ctx);
+}
+
 static int comm_transpose_fwd(nnpm_ctx* ctx) {
   NEED_COMM();
   const Geom& g = ctx->g;

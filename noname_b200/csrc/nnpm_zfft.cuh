@@ -104,7 +104,7 @@ __device__ __forceinline__ double zf_rcp(double x) {
 
 template <int R1, int R2, int C>
 __global__ void __launch_bounds__(C*(R1 > R2 ? R1 : R2), 1)
-k_zfused(double2* __restrict__ T, i64 ncol, i64 icn, i64 j0, const double* __restrict__ s1, const double* __restrict__ s2,
+k_zfused(double2* __restrict__ T, i64 ncol, i64 colbeg, i64 colend, i64 icn, i64 j0, const double* __restrict__ s1, const double* __restrict__ s2,
          const double* __restrict__ s3, const double2* __restrict__ tw, int rank3, double scale) {
   constexpr int RM = R1 > R2 ? R1 : R2, B1 = zf_log2(R1), B2 = zf_log2(R2);
   extern __shared__ double2 zsm[];  // [N][C] exchange buffer, then tw[N] (double2), then s3[N] (double)
@@ -116,8 +116,10 @@ k_zfused(double2* __restrict__ T, i64 ncol, i64 icn, i64 j0, const double* __res
     ss3[t] = __ldg(s3 + t);
   }
   const int c = threadIdx.x % C, j = threadIdx.x / C;
-  const i64 col = blockIdx.x * (i64)C + c;
-  const bool colok = col < ncol;
+  // columns [colbeg, colend) of the ncol-wide matrix (a sub-range when the solve is pipelined with the
+  // NVLink transposes)
+  const i64 col = colbeg + blockIdx.x * (i64)C + c;
+  const bool colok = col < colend;
   double2* Tc = T + col;
   double2 v[RM];
 
@@ -201,19 +203,20 @@ static bool zfused_supported(nnpm_ctx* ctx) {
 }
 
 template <int R1, int R2, int C>
-static int zfused_go(nnpm_ctx* ctx, double2* T, double scale) {
+static int zfused_go(nnpm_ctx* ctx, double2* T, double scale, i64 colbeg, i64 colend) {
   const i64 ncol = ctx->njl * ctx->icn;
+  if (colend < 0) { colbeg = 0; colend = ncol; }
   const size_t smem = (size_t)R1 * R2 * (C * sizeof(double2) + sizeof(double2) + sizeof(double));
   CK(cudaFuncSetAttribute(k_zfused<R1, R2, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const unsigned grid = (unsigned)((ncol + C - 1) / C);
-  k_zfused<R1, R2, C><<<grid, C*(R1 > R2 ? R1 : R2), smem, ctx->st>>>(T, ncol, ctx->icn, ctx->njl * ctx->r, ctx->s1, ctx->s2,
+  const unsigned grid = (unsigned)((colend - colbeg + C - 1) / C);
+  k_zfused<R1, R2, C><<<grid, C*(R1 > R2 ? R1 : R2), smem, ctx->st>>>(T, ncol, colbeg, colend, ctx->icn, ctx->njl * ctx->r, ctx->s1, ctx->s2,
                                                                       ctx->s3, ctx->ztw, 1, scale);
   LAUNCHED(ctx);
   KCHECK();
   return NNPM_OK;
 }
 
-static int zfused_launch(nnpm_ctx* ctx, double2* T, double scale) {
+static int zfused_launch(nnpm_ctx* ctx, double2* T, double scale, i64 colbeg = 0, i64 colend = -1) {
   const i64 N = ctx->g.N3;
   if (!ctx->ztw) {  // W_N^m = exp(-2 pi i m / N), m < N, in extended precision on the host
     std::vector<double2> h((size_t)N);
@@ -227,11 +230,11 @@ static int zfused_launch(nnpm_ctx* ctx, double2* T, double scale) {
   }
   const bool c4 = ctx->opt_zcols == 4;
   switch (N) {
-    case 64: return zfused_go<8, 8, 8>(ctx, T, scale);
-    case 128: return zfused_go<16, 8, 8>(ctx, T, scale);
-    case 256: return zfused_go<16, 16, 8>(ctx, T, scale);
-    case 512: return c4 ? zfused_go<32, 16, 4>(ctx, T, scale) : zfused_go<32, 16, 8>(ctx, T, scale);
-    case 1024: return c4 ? zfused_go<32, 32, 4>(ctx, T, scale) : zfused_go<32, 32, 8>(ctx, T, scale);
+    case 64: return zfused_go<8, 8, 8>(ctx, T, scale, colbeg, colend);
+    case 128: return zfused_go<16, 8, 8>(ctx, T, scale, colbeg, colend);
+    case 256: return zfused_go<16, 16, 8>(ctx, T, scale, colbeg, colend);
+    case 512: return c4 ? zfused_go<32, 16, 4>(ctx, T, scale, colbeg, colend) : zfused_go<32, 16, 8>(ctx, T, scale, colbeg, colend);
+    case 1024: return c4 ? zfused_go<32, 32, 4>(ctx, T, scale, colbeg, colend) : zfused_go<32, 32, 8>(ctx, T, scale, colbeg, colend);
   }
   return fail(ctx, NNPM_ERR_STATE, "fused z pass does not support N3 = %lld", (long long)N);
 }
