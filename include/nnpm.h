@@ -184,6 +184,8 @@ int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, in
  *   "tile_push"    1 = push gathers phi from a shared-memory tile on sorted particles, 0 = L2 gather
  *   "bulk_flush"   1 = tiled deposit flushes its box with cp.reduce.async.bulk (default), 0 = per-cell atomics
  *   "colfft"       1 = TMA-staged column FFT for the y passes (default), 0 = cuFFT 2-D plans
+ *   "pipeline"     nranks > 1: 1 = overlap the transposes with chunked transforms when the chunks are
+ *                  large enough (default), 2 = always, 0 = never
  *   "push_tma"     1 = tiled push streams x, v through shared memory with cp.async.bulk (DMA warp)
  *   "colfft_z"     1 = TMA-staged fused z pass instead of the register-resident one
  *   "peer_transpose" nranks > 1: 1 = copy-engine peer copies over NVLink (default), 2 = remote-store

@@ -951,7 +951,11 @@ static int do_solve(nnpm_ctx* ctx, cudaEvent_t* ev) {
   const double scale = 1.0 / ((double)g.N1 * (double)g.N2 * (double)g.N3) * 1 / ((double)g.N1 * (double)g.N1);
   const bool fft3d = ctx->opt_fft3d && ctx->P == 1 && g.N3 > 1;
   const bool fusedz = !fft3d && ctx->opt_zfused && g.N3 > 1 && zfused_supported(ctx);
-  if (ctx->P > 1 && ctx->opt_pipeline && ctx->peer_ok && ctx->opt_peer == 1 && fusedz && !ctx->opt_colfft_z && ctx->opt_colfft &&
+  // chunking pays only while a chunk's copy to one peer stays large (measured at 1024^3: P = 2, 537 MB
+  // per copy: solve 17.5 -> 15.5 ms; P = 8, 34 MB per copy: 6.3 -> 7.0 ms); "pipeline" = 2 forces it
+  const double chunk_copy_mb = (double)g.nzl * ctx->njl * ctx->icn * 16.0 / 4.0 / 1048576.0;
+  const bool pipe = ctx->opt_pipeline == 2 || (ctx->opt_pipeline == 1 && chunk_copy_mb >= 256.0);
+  if (ctx->P > 1 && pipe && ctx->peer_ok && ctx->opt_peer == 1 && fusedz && !ctx->opt_colfft_z && ctx->opt_colfft &&
       colfft_supported_n(g.N2) && g.nzl % 4 == 0 && ctx->njl % 4 == 0) {
     NEED_COMM();
     CKR(do_solve_pipelined(ctx, ev, scale));

@@ -111,7 +111,7 @@ def main():
     O.compute_potential(ref, rho - rho.mean(), np.zeros((N2, N2, N2 // 2 + 1), dtype=np.complex128))
     nz2 = N2 // P
     got = {}
-    for name, opts in (("pipelined", {}), ("unpipelined", {"pipeline": 0}), ("kernel", {"peer_transpose": 2}), ("nccl", {"peer_transpose": 0})):
+    for name, opts in (("pipelined", {"pipeline": 2}), ("unpipelined", {"pipeline": 0}), ("kernel", {"peer_transpose": 2}), ("nccl", {"peer_transpose": 0})):
         dev = DevicePM((N2, N2, N2), 8, rank=3, device=lr, nranks=P, rank_id=rank)
         uid = [DevicePM.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
