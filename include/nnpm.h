@@ -187,7 +187,8 @@ int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, in
  *   "pipeline"     nranks > 1: 1 = overlap the transposes with chunked transforms when the chunks are
  *                  large enough (default), 2 = always, 0 = never
  *   "push_tma"     1 = tiled push streams x, v through shared memory with cp.async.bulk (DMA warp)
- *   "colfft_z"     1 = TMA-staged fused z pass instead of the register-resident one
+ *   "colfft_z"     1 = TMA-staged fused z pass instead of the register-resident one, 2 = the same at two
+ *                  CTAs per SM (both measured slower than the default at 1024^3)
  *   "peer_transpose" nranks > 1: 1 = copy-engine peer copies over NVLink (default), 2 = remote-store
  *                  kernels, 0 = grouped ncclSend/ncclRecv
  *   "push_minb", "zcols", "cfrun_y", "cfrun_z"  launch-shape experiments */

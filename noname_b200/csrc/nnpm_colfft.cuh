@@ -183,6 +183,105 @@ k_colfft(const __grid_constant__ CUtensorMap tmap, ColFftArgs a) {
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
 }
 
+// Fused z pass, two CTAs per SM: ONE shared-memory buffer per CTA holds the column group in natural
+// order (TMA load / store side) and, aliased onto it, the padded exchange layout; the memory phases
+// of one CTA (store drain, next load) are covered by the compute phases of its sibling on the same SM.
+template <int R1, int R2>
+__global__ void __launch_bounds__(4 * (R1 > R2 ? R1 : R2), 2)
+k_colfft_z2(const __grid_constant__ CUtensorMap tmap, ColFftArgs a) {
+  constexpr int C = 4, N = R1 * R2, RM = R1 > R2 ? R1 : R2, B1 = zf_log2(R1), B2 = zf_log2(R2);
+  constexpr int RB = N < 256 ? N : 256, NOPS = N / RB;
+  constexpr int EST = R2 + 1;
+  extern __shared__ __align__(128) unsigned char cf_smem[];
+  double2* B = (double2*)cf_smem;        // natural [N][C]   /   exchange [R1][EST][C]  (aliased)
+  double2* E = B;
+  double2* stw = B + R1 * EST * C;
+  double* ss3 = (double*)(stw + N);
+  __shared__ __align__(8) unsigned long long full;
+  const int tid = threadIdx.x, c = tid % C, j = tid / C;
+  for (int t = tid; t < N; t += blockDim.x) {
+    stw[t] = __ldg(a.tw + t);
+    ss3[t] = __ldg(a.s3 + t);
+  }
+  if (tid == 0) mbar_init(&full, 1);
+  __syncthreads();
+  unsigned phase = 0u;
+  double2 v[RM];
+  for (int g = blockIdx.x; g < a.ngroups; g += gridDim.x) {
+    const int outer = g / a.nicg, icg = g - outer * a.nicg;
+    if (tid == 0) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous store has read the buffer
+      mbar_expect_tx(&full, (unsigned)(N * C * sizeof(double2)));
+#pragma unroll
+      for (int o = 0; o < NOPS; o++) tma_load_3d(B + o * RB * C, &tmap, icg * 8, outer, o * RB, &full);
+    }
+    const int ic = icg * C + c;
+    double sxy = 1.0;
+    if (ic < a.icn) sxy = __ldg(a.s1 + ic) + __ldg(a.s2 + a.j0 + outer);
+    const bool dc_col = (ic == 0 && a.j0 + outer == 0);
+    mbar_wait(&full, phase);
+    phase ^= 1u;
+    if (j < R2) {
+#pragma unroll
+      for (int r = 0; r < R1; r++) v[r] = B[(j + r * R2) * C + c];
+      ZDif<R1, 0, -1>::run(v);
+    }
+    __syncthreads();  // every thread has its rows in registers: the buffer may take the exchange layout
+    if (j < R2) {
+#pragma unroll
+      for (int q = 0; q < R1; q++) E[(q * EST + j) * C + c] = v[zf_brev(q, B1)];
+    }
+    __syncthreads();
+    if (j < R1) {
+#pragma unroll
+      for (int r = 0; r < R2; r++) v[r] = E[(j * EST + r) * C + c];
+#pragma unroll
+      for (int r = 1; r < R2; r++) {
+        const double2 w = stw[r * j];
+        v[r] = zmul(v[r], w.x, w.y);
+      }
+      ZDif<R2, 0, -1>::run(v);
+#pragma unroll
+      for (int q = 0; q < R2; q++) {
+        const int kz = j + q * R1;
+        const double ginv = -4.0 * (sxy + ss3[kz]);
+        double f = (ginv != 0.0) ? a.scale * zf_rcp(ginv) : a.scale;
+        if (dc_col && kz == 0) f = 0.0;
+        double2& e = v[zf_brev(q, B2)];
+        e.x *= f;
+        e.y *= f;
+      }
+      ZDit<R2, 0, +1>::run(v);
+#pragma unroll
+      for (int r = 0; r < R2; r++) E[(j * EST + r) * C + c] = v[r];
+    }
+    __syncthreads();
+    if (j < R2) {
+#pragma unroll
+      for (int r = 0; r < R1; r++) v[r] = E[(r * EST + j) * C + c];
+#pragma unroll
+      for (int r = 1; r < R1; r++) {
+        const double2 w = stw[r * j];
+        v[r] = zmul(v[r], w.x, -w.y);
+      }
+      ZDif<R1, 0, +1>::run(v);
+    }
+    __syncthreads();  // exchange layout fully consumed: back to natural order
+    if (j < R2) {
+#pragma unroll
+      for (int q = 0; q < R1; q++) B[(j + q * R2) * C + c] = v[zf_brev(q, B1)];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int o = 0; o < NOPS; o++) tma_store_3d(&tmap, B + o * RB * C, icg * 8, outer, o * RB);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ---- host side -------------------------------------------------------------------------------
 static int colfft_tensor_map(nnpm_ctx* ctx, CUtensorMap* tm, double* base, i64 n_mid, i64 n_outer, i64 mid_stride_b,
                              i64 outer_stride_b, bool ypass, i64 N) {
@@ -282,5 +381,25 @@ static int colfft_z_green(nnpm_ctx* ctx, double2* T, double scale) {
   a.tw = ctx->ztw;
   a.scale = scale;
   a.run = ctx->opt_cfrun_z;
+  if (ctx->opt_colfft_z == 2) {  // two CTAs per SM, single aliased buffer
+#define Z2(R1_, R2_)                                                                                                   \
+  do {                                                                                                                 \
+    const size_t smem = (size_t)R1_ * (R2_ + 1) * 4 * 16 + (size_t)R1_ * R2_ * 24;                                        \
+    CK(cudaFuncSetAttribute(k_colfft_z2<R1_, R2_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    const int grid = a.ngroups < 2 * ctx->nsm ? a.ngroups : 2 * ctx->nsm;                                               \
+    k_colfft_z2<R1_, R2_><<<grid, 4 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(ctx->tm_z, a);                            \
+    LAUNCHED(ctx);                                                                                                     \
+    KCHECK();                                                                                                          \
+    return NNPM_OK;                                                                                                    \
+  } while (0)
+    switch (g.N3) {
+      case 64: Z2(8, 8);
+      case 128: Z2(16, 8);
+      case 256: Z2(16, 16);
+      case 512: Z2(32, 16);
+      case 1024: Z2(32, 32);
+    }
+#undef Z2
+  }
   return colfft_dispatch<CF_GREEN, false>(ctx, g.N3, ctx->tm_z, a);
 }

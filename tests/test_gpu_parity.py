@@ -148,16 +148,17 @@ def test_potential_tma_column_fft(lib_built, O, dims):
     ref = np.empty(shape)
     O.compute_potential(ref, rho - rho.mean(), np.zeros((shape[0], shape[1], shape[2] // 2 + 1), dtype=np.complex128))
     out = {}
-    for cf in (1, 0):
+    for key, (cf, cz) in {1: (1, 1), 2: (1, 2), 0: (0, 0)}.items():   # cz: 1 = double-buffered, 2 = two CTAs per SM
         with DevicePM(dims, 1, rank=3 if dims[2] > 1 else 2) as dev:
             dev.set_option("colfft", cf)
-            dev.set_option("colfft_z", cf)
+            dev.set_option("colfft_z", cz)
             dev.set_field("rho", rho)
             dev.solve()
-            out[cf] = dev.get_field("phi")
+            out[key] = dev.get_field("phi")
             dev.set_field("rho", rho)          # a second solve through the same context (buffer ring reuse)
             dev.solve()
-            assert np.array_equal(out[cf], dev.get_field("phi"))
+            assert np.array_equal(out[key], dev.get_field("phi"))
+    assert nlinf(out[2], ref) < TOL
     assert nlinf(out[1], ref) < TOL
     assert nlinf(out[0], ref) < TOL
 
