@@ -179,7 +179,8 @@ int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, in
 
 /* Runtime tuning knobs (new; no reference counterpart).  Unknown names -> NNPM_ERR_ARG.
  *   "fft3d"        1 = single cuFFT 3-D plan instead of 2-D + fused z pass (nranks == 1 only)
- *   "zfused"       1 = hand-written fused z-FFT * Green * z-iFFT kernel (default), 0 = cuFFT z
+ *   "zfused"       2 = fused z-FFT * Green * z-iFFT kernel, persistent with TMA prefetch (default),
+ *                  1 = the same with one CTA per column group and register loads, 0 = cuFFT z + Green kernel
  *   "tile_deposit" 1 = shared-memory tiled deposit on tile-sorted particles (default), 0 = global atomics
  *   "tile_push"    1 = push gathers phi from a shared-memory tile on sorted particles, 0 = L2 gather
  *   "bulk_flush"   1 = tiled deposit flushes its box with cp.reduce.async.bulk (default), 0 = per-cell atomics

@@ -114,8 +114,8 @@ struct nnpm_ctx {
   int opt_peer;   // 0 = NCCL send/recv, 1 = copy-engine peer copies (default), 2 = remote-store kernels
   int* bar_buf;
   // TMA-staged column FFT engine (nnpm_colfft.cuh)
-  CUtensorMap tm_y, tm_z;
-  bool have_tm_y, have_tm_z, have1;
+  CUtensorMap tm_y, tm_z, tm_z8;
+  bool have_tm_y, have_tm_z, have_tm_z8, have1;
   double2* ytw;
   cufftHandle plan1f, plan1b;  // batched 1-D x transforms (r2c / c2r) over the owned rows
   cufftHandle plan1fc;         // the same over one chunk of planes (pipelined multi-GPU solve)
@@ -368,7 +368,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->wcnt = c->wtile = c->wbeg = nullptr; c->wcap = 0;
   c->have2 = c->havez = c->have3 = false;
   c->have_tmap = false;
-  c->opt_fft3d = 0; c->opt_zfused = 1; c->opt_tile_deposit = 1; c->opt_tile_push = 1; c->opt_push_minb = 2; c->opt_bulk_flush = 1;
+  c->opt_fft3d = 0; c->opt_zfused = 2; c->opt_tile_deposit = 1; c->opt_tile_push = 1; c->opt_push_minb = 2; c->opt_bulk_flush = 1;
   c->fftwork = nullptr; c->fftwork_bytes = 0;
   c->step_count = 0; c->launches = 0;
   c->nccl = nullptr; c->comm = nullptr;
@@ -382,7 +382,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   for (int i = 0; i < 4; i++) { c->st2[i] = nullptr; c->ev_join[i] = nullptr; }
   c->have1c = false; c->opt_pipeline = 1;
   for (int i = 0; i < 4; i++) c->ev_chunk[i] = nullptr;
-  c->have_tm_y = c->have_tm_z = c->have1 = false; c->ytw = nullptr; c->opt_push_tma = 0; c->opt_colfft = 1; c->opt_colfft_z = 0; c->opt_cfrun_y = 1; c->opt_cfrun_z = 1; c->nsm = 148;
+  c->have_tm_y = c->have_tm_z = c->have_tm_z8 = c->have1 = false; c->ytw = nullptr; c->opt_push_tma = 0; c->opt_colfft = 1; c->opt_colfft_z = 0; c->opt_cfrun_y = 1; c->opt_cfrun_z = 1; c->nsm = 148;
   c->mig_lo = nullptr; c->ghost_rx = nullptr; c->red_buf = nullptr;
   c->np = 0; c->m = 0.0; c->ids_dirty = false; c->field_state = 0;
   c->own_stream = false;
@@ -931,7 +931,8 @@ static int do_solve_pipelined(nnpm_ctx* ctx, cudaEvent_t* ev, double scale) {
   if (ev) { CK(cudaEventRecord(ev[1], ctx->st)); CK(cudaEventRecord(ev[4], ctx->st)); }
   const i64 cols = jc * ctx->icn;
   for (int c = 0; c < NCH; c++) {
-    CKR(zfused_launch(ctx, (double2*)ctx->meshT, scale, cols * c, cols * (c + 1)));
+    if (ctx->opt_zfused == 2) CKR(zfused_p_launch(ctx, (double2*)ctx->meshT, scale, jc * c, jc * (c + 1)));
+    else CKR(zfused_launch(ctx, (double2*)ctx->meshT, scale, cols * c, cols * (c + 1)));
     CK(cudaEventRecord(ctx->ev_chunk[c], ctx->st));
     CKR(comm_chunk_ce(ctx, false, c, NCH, ctx->ev_chunk[c]));
   }
@@ -971,6 +972,7 @@ static int do_solve(nnpm_ctx* ctx, cudaEvent_t* ev) {
     // measured at 1024^3: the register-resident k_zfused (128-byte rows, exact DRAM traffic) 7.0 ms;
     // the TMA-staged variant (64-byte rows, 4 warps per SM) 7.6 ms -> k_zfused is the default
     if (ctx->opt_colfft_z) CKR(colfft_z_green(ctx, T, scale));
+    else if (ctx->opt_zfused == 2) CKR(zfused_p_launch(ctx, T, scale, 0, ctx->njl));
     else CKR(zfused_launch(ctx, T, scale));
   } else {
     dim3 grid(nblk(ctx->icn, 128), (unsigned)ctx->njl, (unsigned)(g.N3 < 64 ? g.N3 : 64));

@@ -282,9 +282,114 @@ k_colfft_z2(const __grid_constant__ CUtensorMap tmap, ColFftArgs a) {
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// Persistent form of k_zfused (nnpm_zfft.cuh) with the NEXT column group prefetched by TMA: 8 adjacent
+// columns per group (128-byte rows: exact DRAM traffic), 8 warps, the [N][8] shared-memory buffer is
+// both the landing zone of the tensor load and the exchange buffer of the two radix passes.  As soon
+// as the last exchange read of group g is done (start of the final inverse pass), one thread issues the
+// tensor load of group g + gridDim.x, so the load latency and transfer run under the final pass'
+// arithmetic and its stores instead of in front of the next group's first pass.
+template <int R1, int R2>
+__global__ void __launch_bounds__(8 * (R1 > R2 ? R1 : R2), 1)
+k_zfused_p(const __grid_constant__ CUtensorMap tmap, double2* __restrict__ T, i64 ncol, ColFftArgs a) {
+  constexpr int C = 8, N = R1 * R2, RM = R1 > R2 ? R1 : R2, B1 = zf_log2(R1), B2 = zf_log2(R2);
+  constexpr int RB = N < 256 ? N : 256, NOPS = N / RB;
+  extern __shared__ __align__(128) unsigned char cf_smem[];
+  double2* zsm = (double2*)cf_smem;  // [N][C]
+  double2* stw = zsm + N * C;
+  double* ss3 = (double*)(stw + N);
+  __shared__ __align__(8) unsigned long long full;
+  const int tid = threadIdx.x, c = tid % C, j = tid / C;
+  for (int t = tid; t < N; t += blockDim.x) {
+    stw[t] = __ldg(a.tw + t);
+    ss3[t] = __ldg(a.s3 + t);
+  }
+  if (tid == 0) mbar_init(&full, 1);
+  __syncthreads();
+  auto issue_load = [&](int g) {  // thread 0 only
+    const int og = g / a.nicg, icg = g - og * a.nicg;
+    mbar_expect_tx(&full, (unsigned)(N * C * sizeof(double2)));
+#pragma unroll
+    for (int o = 0; o < NOPS; o++) tma_load_3d(zsm + o * RB * C, &tmap, icg * 16, og + a.outer0, o * RB, &full);
+  };
+  int g = blockIdx.x;
+  if (tid == 0 && g < a.ngroups) issue_load(g);
+  unsigned phase = 0u;
+  double2 v[RM];
+  for (; g < a.ngroups; g += gridDim.x) {
+    const int og = g / a.nicg, icg = g - og * a.nicg, jl = og + a.outer0;
+    const int ic = icg * C + c;
+    const bool colok = ic < a.icn;
+    double sxy = 1.0;
+    if (colok) sxy = __ldg(a.s1 + ic) + __ldg(a.s2 + a.j0 + jl);
+    const bool dc_col = (ic == 0 && a.j0 + jl == 0);
+    mbar_wait(&full, phase);
+    phase ^= 1u;
+    // ---- forward pass A: radix R1 over rows j + r*R2 (from the landing zone)
+    if (j < R2) {
+#pragma unroll
+      for (int r = 0; r < R1; r++) v[r] = zsm[(j + r * R2) * C + c];
+      ZDif<R1, 0, -1>::run(v);
+    }
+    __syncthreads();  // inputs are in registers: the buffer becomes the exchange
+    if (j < R2) {
+#pragma unroll
+      for (int q = 0; q < R1; q++) zsm[(j * R1 + q) * C + c] = v[zf_brev(q, B1)];
+    }
+    __syncthreads();
+    // ---- forward pass B, Green's function, inverse pass A'
+    if (j < R1) {
+#pragma unroll
+      for (int r = 0; r < R2; r++) v[r] = zsm[(j + r * R1) * C + c];
+    }
+    __syncthreads();
+    if (j < R1) {
+#pragma unroll
+      for (int r = 1; r < R2; r++) {
+        const double2 w = stw[r * j];
+        v[r] = zmul(v[r], w.x, w.y);
+      }
+      ZDif<R2, 0, -1>::run(v);
+#pragma unroll
+      for (int q = 0; q < R2; q++) {  // X[kz] *= scale / Ginv, kz = j + q*R1   (ParticleMesh.jl:494-501)
+        const int kz = j + q * R1;
+        const double ginv = -4.0 * (sxy + ss3[kz]);
+        double f = (ginv != 0.0) ? a.scale * zf_rcp(ginv) : a.scale;
+        if (dc_col && kz == 0) f = 0.0;
+        double2& e = v[zf_brev(q, B2)];
+        e.x *= f;
+        e.y *= f;
+      }
+      ZDit<R2, 0, +1>::run(v);
+#pragma unroll
+      for (int r = 0; r < R2; r++) zsm[(j * R2 + r) * C + c] = v[r];
+    }
+    __syncthreads();
+    // ---- inverse pass B': radix R1 -> rows j + q*R2, stored straight from registers
+    if (j < R2) {
+#pragma unroll
+      for (int r = 0; r < R1; r++) v[r] = zsm[(j + r * R2) * C + c];
+    }
+    __syncthreads();  // the exchange is consumed: the buffer is free for the next group's tensor load
+    if (tid == 0 && g + (int)gridDim.x < a.ngroups) issue_load(g + gridDim.x);
+    if (j < R2) {
+#pragma unroll
+      for (int r = 1; r < R1; r++) {
+        const double2 w = stw[r * j];
+        v[r] = zmul(v[r], w.x, -w.y);
+      }
+      ZDif<R1, 0, +1>::run(v);
+      if (colok) {
+        double2* Tc = T + (i64)jl * a.icn + ic;
+#pragma unroll
+        for (int q = 0; q < R1; q++) Tc[(i64)(j + q * R2) * ncol] = v[zf_brev(q, B1)];
+      }
+    }
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------
 static int colfft_tensor_map(nnpm_ctx* ctx, CUtensorMap* tm, double* base, i64 n_mid, i64 n_outer, i64 mid_stride_b,
-                             i64 outer_stride_b, bool ypass, i64 N) {
+                             i64 outer_stride_b, bool ypass, i64 N, int inner = 8) {
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -295,7 +400,7 @@ static int colfft_tensor_map(nnpm_ctx* ctx, CUtensorMap* tm, double* base, i64 n
   const cuuint32_t rb = (cuuint32_t)(N < 256 ? N : 256);
   cuuint64_t dims[3] = {(cuuint64_t)(2 * ctx->icn), (cuuint64_t)n_mid, (cuuint64_t)n_outer};
   cuuint64_t strides[2] = {(cuuint64_t)mid_stride_b, (cuuint64_t)outer_stride_b};
-  cuuint32_t box[3] = {8, ypass ? rb : 1u, ypass ? 1u : rb};
+  cuuint32_t box[3] = {(cuuint32_t)inner, ypass ? rb : 1u, ypass ? 1u : rb};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = ((encode_fn)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -402,4 +507,44 @@ static int colfft_z_green(nnpm_ctx* ctx, double2* T, double scale) {
 #undef Z2
   }
   return colfft_dispatch<CF_GREEN, false>(ctx, g.N3, ctx->tm_z, a);
+}
+
+// persistent k_zfused with TMA prefetch over the local rows jl in [jlbeg, jlend)
+static int zfused_p_launch(nnpm_ctx* ctx, double2* T, double scale, i64 jlbeg, i64 jlend) {
+  const Geom& g = ctx->g;
+  if (!ctx->have_tm_z8) {
+    CKR(colfft_tensor_map(ctx, &ctx->tm_z8, (double*)T, ctx->njl, g.N3, ctx->icn * 16, ctx->njl * ctx->icn * 16, false, g.N3, 16));
+    ctx->have_tm_z8 = true;
+  }
+  CKR(colfft_twiddles(ctx, &ctx->ztw, g.N3));
+  ColFftArgs a;
+  memset(&a, 0, sizeof a);
+  a.nicg = (int)((ctx->icn + 7) / 8);
+  a.ngroups = (int)((jlend - jlbeg) * a.nicg);
+  a.outer0 = (int)jlbeg;
+  a.icn = (int)ctx->icn;
+  a.j0 = ctx->njl * ctx->r;
+  a.s1 = ctx->s1; a.s2 = ctx->s2; a.s3 = ctx->s3;
+  a.tw = ctx->ztw;
+  a.scale = scale;
+  const i64 ncol = ctx->njl * ctx->icn;
+#define ZP(R1_, R2_)                                                                                                   \
+  do {                                                                                                                 \
+    const size_t smem = (size_t)R1_ * R2_ * (8 * 16 + 16 + 8);                                                           \
+    CK(cudaFuncSetAttribute(k_zfused_p<R1_, R2_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    const int grid = a.ngroups < ctx->nsm ? a.ngroups : ctx->nsm;                                                       \
+    k_zfused_p<R1_, R2_><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(ctx->tm_z8, T, ncol, a);                   \
+    LAUNCHED(ctx);                                                                                                     \
+    KCHECK();                                                                                                          \
+    return NNPM_OK;                                                                                                    \
+  } while (0)
+  switch (g.N3) {
+    case 64: ZP(8, 8);
+    case 128: ZP(16, 8);
+    case 256: ZP(16, 16);
+    case 512: ZP(32, 16);
+    case 1024: ZP(32, 32);
+  }
+#undef ZP
+  return fail(ctx, NNPM_ERR_STATE, "persistent fused z pass does not support N3 = %lld", (long long)g.N3);
 }

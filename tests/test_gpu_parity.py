@@ -76,7 +76,7 @@ def test_potential(PM, O, dims, rank):
     assert nlinf(got, ref) < TOL
 
 
-@pytest.mark.parametrize("dims", [(16, 8, 64), (12, 10, 128), (32, 16, 256), (8, 8, 512), (8, 4, 1024)])
+@pytest.mark.parametrize("dims", [(16, 8, 64), (12, 10, 128), (32, 16, 256), (8, 8, 512), (8, 4, 1024), (66, 40, 256), (128, 128, 128)])
 def test_potential_fused_z_pass(lib_built, O, dims):
     """the hand-written fused z-FFT * Green * z-iFFT kernel (N3 = 64 .. 1024) against the oracle and
     against the cuFFT-composed z path."""
@@ -87,15 +87,17 @@ def test_potential_fused_z_pass(lib_built, O, dims):
     ref = np.empty(shape)
     O.compute_potential(ref, rho - rho.mean(), np.zeros((shape[0], shape[1], shape[2] // 2 + 1), dtype=np.complex128))
     out = {}
-    for zf in (1, 0):
+    for zf in (2, 1, 0):          # 2 = persistent + TMA prefetch, 1 = one CTA per column group, 0 = cuFFT z + Green kernel
         with DevicePM(dims, 1, rank=3) as dev:
             dev.set_option("zfused", zf)
-            dev.set_field("rho", rho)
-            dev.solve()
-            out[zf] = dev.get_field("phi")
+            for rep in range(2):
+                dev.set_field("rho", rho)
+                dev.solve()
+                out[zf] = dev.get_field("phi")
+    assert nlinf(out[2], ref) < TOL
     assert nlinf(out[1], ref) < TOL
     assert nlinf(out[0], ref) < TOL
-    assert nlinf(out[1], out[0]) < TOL
+    assert nlinf(out[2], out[1]) < 1e-14    # same algorithm, different data movement (FMA contraction may differ)
 
 
 @pytest.mark.parametrize("dims,rank", [((48, 20, 1), 2), ((64, 64, 1), 2), ((40, 24, 20), 3), ((64, 32, 32), 3), ((16, 16, 16), 3)])
