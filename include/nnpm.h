@@ -192,6 +192,11 @@ int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, in
  *                  CTAs per SM (both measured slower than the default at 1024^3)
  *   "peer_transpose" nranks > 1: 1 = copy-engine peer copies over NVLink (default), 2 = remote-store
  *                  kernels, 0 = grouped ncclSend/ncclRecv
+ *   "push_persist" 1 = persistent tiled push: 2 resident CTAs per SM walk the work list with double-buffered
+ *                  phi boxes (next box staged by TMA while the current one is gathered from), 2 / 3 = the same
+ *                  with 320 / 384 threads per CTA (96 / 80 registers); 0 = one CTA per work item
+ *   "push_grid"    CTAs of the persistent push (0 = 2 * SMs - 1); small values make every CTA walk many items
+ *   "deposit_unroll" 2 = the tiled deposit issues the loads of two particles before scattering either
  *   "push_minb", "zcols", "cfrun_y", "cfrun_z"  launch-shape experiments */
 int nnpm_set_option(nnpm_ctx *ctx, const char *name, double value);
 

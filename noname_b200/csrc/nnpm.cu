@@ -122,7 +122,7 @@ struct nnpm_ctx {
   bool have1c;
   int opt_pipeline;
   cudaEvent_t ev_chunk[4];
-  int opt_push_tma, opt_colfft, opt_colfft_z, opt_cfrun_y, opt_cfrun_z, nsm;
+  int opt_push_tma, opt_push_persist, opt_push_grid, opt_deposit_unroll, opt_colfft, opt_colfft_z, opt_cfrun_y, opt_cfrun_z, nsm;
   cudaStream_t st2[4];    // side streams: the blocks of a transpose go out on several copy engines at once
   cudaEvent_t ev_fork, ev_join[4];
 };
@@ -382,7 +382,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   for (int i = 0; i < 4; i++) { c->st2[i] = nullptr; c->ev_join[i] = nullptr; }
   c->have1c = false; c->opt_pipeline = 1;
   for (int i = 0; i < 4; i++) c->ev_chunk[i] = nullptr;
-  c->have_tm_y = c->have_tm_z = c->have_tm_z8 = c->have1 = false; c->ytw = nullptr; c->opt_push_tma = 0; c->opt_colfft = 1; c->opt_colfft_z = 0; c->opt_cfrun_y = 1; c->opt_cfrun_z = 1; c->nsm = 148;
+  c->have_tm_y = c->have_tm_z = c->have_tm_z8 = c->have1 = false; c->ytw = nullptr; c->opt_push_tma = 0; c->opt_push_persist = 0; c->opt_push_grid = 0; c->opt_deposit_unroll = 1; c->opt_colfft = 1; c->opt_colfft_z = 0; c->opt_cfrun_y = 1; c->opt_cfrun_z = 1; c->nsm = 148;
   c->mig_lo = nullptr; c->ghost_rx = nullptr; c->red_buf = nullptr;
   c->np = 0; c->m = 0.0; c->ids_dirty = false; c->field_state = 0;
   c->own_stream = false;
@@ -798,7 +798,13 @@ static int do_deposit(nnpm_ctx* ctx, bool pre, double c0) {
     const int bulk = ctx->opt_bulk_flush && (g.N1 % 2 == 0) && g.N1 >= NNPM_DX && ctx->tg.tx == NNPM_TX;
     const WorkList wl = {ctx->wtile, ctx->wbeg, ctx->wcnt + ctx->ntiles};
     const unsigned wgrid = (unsigned)(ctx->ntiles + ctx->sorted_np / NNPM_CHUNK + 1);  // >= number of chunks
-#define DT(RK, FX, PR) k_deposit_tile<RK, FX, PR><<<wgrid, 256, 0, ctx->st>>>(ctx->pp, covered, c0, ctx->g, ctx->tg, wl, ctx->hist, ctx->mesh, ctx->m, fscale, ctx->srnk, (u64*)(ctx->d_red + 5), bulk)
+#define DT(RK, FX, PR)                                                                                                   \
+  do {                                                                                                                   \
+    if (ctx->opt_deposit_unroll == 2)                                                                                    \
+      k_deposit_tile<RK, FX, PR, 2><<<wgrid, 256, 0, ctx->st>>>(ctx->pp, covered, c0, ctx->g, ctx->tg, wl, ctx->hist, ctx->mesh, ctx->m, fscale, ctx->srnk, (u64*)(ctx->d_red + 5), bulk); \
+    else                                                                                                                 \
+      k_deposit_tile<RK, FX, PR, 1><<<wgrid, 256, 0, ctx->st>>>(ctx->pp, covered, c0, ctx->g, ctx->tg, wl, ctx->hist, ctx->mesh, ctx->m, fscale, ctx->srnk, (u64*)(ctx->d_red + 5), bulk); \
+  } while (0)
     if (ctx->R == 3) { if (fixed) { if (pre) DT(3, true, true); else DT(3, true, false); } else { if (pre) DT(3, false, true); else DT(3, false, false); } }
     else { if (fixed) { if (pre) DT(2, true, true); else DT(2, true, false); } else { if (pre) DT(2, false, true); else DT(2, false, false); } }
 #undef DT
@@ -1150,6 +1156,22 @@ static int launch_push(nnpm_ctx* ctx, bool comoving, const PushParams& pp) {
   } while (0)
     if (comoving) LM(true); else LM(false);
 #undef LM
+  } else if (ctx->opt_push_persist) {
+    // persistent variant: 2 CTAs per SM walk the work list with double-buffered boxes (k_push_tile_p)
+    const size_t smem2 = (size_t)2 * NNPM_BOXD(RANK) * sizeof(double);
+    // odd grid: the round-robin walk then visits every tile column equally often (tiles per row are a power of
+    // two on the usual meshes; an even stride would pin the costlier wrapping edge tiles on a few CTAs)
+    const unsigned pgrid = ctx->opt_push_grid > 0 ? (unsigned)ctx->opt_push_grid : (unsigned)(2 * ctx->nsm - 1);
+#define LQ(CM, NT)                                                                                                  \
+  do {                                                                                                              \
+    CK(cudaFuncSetAttribute(k_push_tile_p<RANK, CM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));  \
+    k_push_tile_p<RANK, CM, NT><<<pgrid, NT, smem2, ctx->st>>>(ctx->tmap_phi, ctx->pp, covered, ctx->g, ctx->tg, wl, ctx->hist, \
+                                                               ctx->mesh, pp, ctx->d_red, ctx->srnk, slow_count);    \
+  } while (0)
+    if (ctx->opt_push_persist == 3) { if (comoving) LQ(true, 384); else LQ(false, 384); }
+    else if (ctx->opt_push_persist == 2) { if (comoving) LQ(true, 320); else LQ(false, 320); }
+    else { if (comoving) LQ(true, 256); else LQ(false, 256); }
+#undef LQ
   } else {
 #define LT(CM, MB)                                                                                                  \
   do {                                                                                                              \
@@ -1279,6 +1301,9 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   else if (!strcmp(name, "colfft")) ctx->opt_colfft = v;
   else if (!strcmp(name, "pipeline")) ctx->opt_pipeline = v;
   else if (!strcmp(name, "push_tma")) ctx->opt_push_tma = v;
+  else if (!strcmp(name, "push_persist")) ctx->opt_push_persist = v;
+  else if (!strcmp(name, "deposit_unroll")) ctx->opt_deposit_unroll = v;
+  else if (!strcmp(name, "push_grid")) ctx->opt_push_grid = v;
   else if (!strcmp(name, "colfft_z")) ctx->opt_colfft_z = v;
   else if (!strcmp(name, "cfrun_y")) ctx->opt_cfrun_y = v < 1 ? 1 : v;
   else if (!strcmp(name, "cfrun_z")) ctx->opt_cfrun_z = v < 1 ? 1 : v;

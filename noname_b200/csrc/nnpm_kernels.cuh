@@ -952,6 +952,194 @@ k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g
   }
   block_max3(mxa, mxv, mxp, red);
 }
+
+// ------------------------------------------------------------------------------------------
+// Persistent tiled push.  Per-particle arithmetic is k_push_tile's, statement for statement; what
+// changes is the schedule.  k_push_tile starts one CTA per work item: every item pays the phi box
+// load (51 KB, ~2 us), the first particle's load latency, a block reduction and three global
+// atomics, with only one other CTA on the SM to cover it (ncu: 25 % occupancy, long_scoreboard and
+// barrier stalls).  Here 2 CTAs per SM stay resident and walk the work list round-robin (item
+// w = blockIdx.x + i * gridDim.x, which keeps the banded raster order between concurrent CTAs):
+//   * two box buffers: the box of item i+1 is staged (one TMA tensor copy for interior tiles, cp.async
+//     rows for tiles whose box wraps) while item i is processed;
+//   * the first 256 particles of item i+1 are prefetched into L2 at the start of item i and loaded into
+//     registers before the end-of-item barrier, so the loop of item i+1 starts on resident data;
+//   * work-list entries are read two items ahead, so no descriptor load is ever waited on;
+//   * one block reduction per CTA instead of one per item.
+// ------------------------------------------------------------------------------------------
+#define NNPM_BOXD(RK) ((NNPM_BX * NNPM_BY * ((RK) == 3 ? NNPM_BZ : 1) + 15) & ~15)  // doubles per box buffer (128 B multiple)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int RANK, bool COMOVING, int NT>
+__global__ void __launch_bounds__(NT, 2)
+k_push_tile_p(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g, TileGeom tg, WorkList wl,
+              const uint32_t* __restrict__ tile_off, const double* __restrict__ phi, PushParams pp, i64* __restrict__ red,
+              uint32_t* __restrict__ slow_list, u64* __restrict__ slow_count) {
+  extern __shared__ __align__(128) double box[];  // 2 x [BZ][BY][BX], NNPM_BOXD doubles apart
+  __shared__ __align__(8) unsigned long long mbar[2];
+  constexpr int BX = NNPM_BX, BY = NNPM_BY, BZ = (RANK == 3) ? NNPM_BZ : 1, BXY = BX * BY, BOXD = NNPM_BOXD(RANK);
+  const unsigned nwork = *wl.count;
+  const unsigned G = gridDim.x;
+  const int tid = threadIdx.x;
+  const int N1 = (int)g.N1, N2 = (int)g.N2, N3 = (int)g.N3;
+  // work item: tile t (< 0: none), particles [n0, n0 + cnt)
+  auto load_item = [&](unsigned w, int& t, i64& n0, int& cnt) {
+    t = -1; n0 = 0; cnt = 0;
+    if (w < nwork) {
+      t = (int)wl.tile[w];
+      n0 = wl.beg[w];
+      i64 n1 = n0 + NNPM_CHUNK;
+      const i64 te = tile_off[t + 1];
+      if (n1 > te) n1 = te;
+      if (n1 > np) n1 = np;
+      cnt = n1 > n0 ? (int)(n1 - n0) : 0;
+    }
+  };
+  // stage the phi box of tile t into buffer b; returns whether it went through the TMA engine
+  // (completion on mbar[b]) or through this thread's cp.async group (always committed, maybe empty)
+  auto stage = [&](int t, int b) -> bool {
+    const int ttx = t % tg.ntx, tty = (t / tg.ntx) % tg.nty, ttz = t / (tg.ntx * tg.nty);
+    const int bx0 = ttx * tg.tx - NNPM_TH - 1, by0 = tty * tg.ty - NNPM_TH - 1;
+    const int bz0 = (RANK == 3) ? ttz * tg.tz - NNPM_TH - 1 + g.glo : g.glo;  // local plane of the box origin
+    const bool interior = bx0 >= 0 && bx0 + BX - 1 <= N1 && by0 >= 0 && by0 + BY <= N2 &&
+                          (RANK == 2 || g.glo != 0 || (bz0 >= 0 && bz0 + BZ <= N3));
+    double* dstb = box + b * BOXD;
+    if (interior) {
+      if (tid == 0) {
+        fence_proxy_async_smem();  // the buffer was last touched through the generic proxy
+        mbar_expect_tx(&mbar[b], (unsigned)(BX * BY * BZ * sizeof(double)));
+        tma_load_3d(dstb, &tmap, bx0, by0, bz0, &mbar[b]);
+      }
+    } else {
+      const int lane = tid & 31, warp = tid >> 5;
+      const int gi0 = wrap_small(bx0 + lane, N1);
+      const int gi1 = wrap_small(bx0 + lane + 32, N1);
+      for (int row = warp; row < BY * BZ; row += NT / 32) {
+        const int byi = row % BY, bzi = row / BY;  // compile-time divisors
+        const int gj = wrap_small(by0 + byi, N2);
+        int lp = g.glo;
+        bool valid = true;
+        if (RANK == 3) {
+          lp = bz0 + bzi;
+          if (g.glo) valid = lp >= 0 && lp < g.nplanes;
+          else lp = wrap_small(lp, N3);
+        }
+        const double* src = phi + g.plane * (i64)lp + (unsigned)((int)g.rowp * gj);
+        double* dst = dstb + row * BX;
+        if (valid) {
+          __pipeline_memcpy_async(dst + lane, src + gi0, 8);
+          if (lane + 32 < BX - 1) __pipeline_memcpy_async(dst + lane + 32, src + gi1, 8);
+        } else {
+          dst[lane] = 0.0;
+          if (lane + 32 < BX - 1) dst[lane + 32] = 0.0;
+        }
+      }
+    }
+    __pipeline_commit();
+    return interior;
+  };
+
+  unsigned w = blockIdx.x;
+  int ct, ccnt, nt, ncnt, ft, fcnt;  // current, next and next-but-one item
+  i64 cn0, nn0, fn0;
+  load_item(w, ct, cn0, ccnt);
+  if (ct < 0) return;  // uniform: fewer items than CTAs
+  load_item(w + G, nt, nn0, ncnt);
+  if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
+  __syncthreads();
+  unsigned phase = 0;  // bit b: parity the next wait on mbar[b] expects
+  int b = 0;
+  bool cur_tma = stage(ct, 0);
+
+  const double gfac = -0.5 * g.fN1;
+  const double ra = 1.0 / pp.a;
+  const unsigned fx = tg.tx + 2 * NNPM_TH, fy = tg.ty + 2 * NNPM_TH, fz = tg.tz + 2 * NNPM_TH;
+  double mxa = -INFINITY, mxv = -INFINITY, mxp = -INFINITY;
+  double xa[3] = {0.0, 0.0, 0.0}, va[3] = {0.0, 0.0, 0.0}, xb[3] = {0.0, 0.0, 0.0}, vb[3] = {0.0, 0.0, 0.0};
+  auto load6 = [&](double* x, double* v, i64 idx) {
+    x[0] = p.x[0][idx]; x[1] = p.x[1][idx]; v[0] = p.v[0][idx]; v[1] = p.v[1][idx];
+    if (RANK == 3) { x[2] = p.x[2][idx]; v[2] = p.v[2][idx]; }
+  };
+  if (tid < ccnt) load6(xa, va, cn0 + tid);
+
+  for (;;) {
+    load_item(w + 2 * G, ft, fn0, fcnt);  // consumed at the top of the next iteration
+    bool nxt_tma = false;
+    if (nt >= 0) nxt_tma = stage(nt, b ^ 1);
+    else __pipeline_commit();
+    // pull the next item's first 256 particles into L2: one 128-byte line per thread and array
+    if (nt >= 0 && tid < 2 * RANK * 16) {  // 16 lines of 16 doubles cover 256 particles; NT > 256 leaves the rest to the loads
+      const int a = tid >> 4, l = tid & 15;
+      const double* base = p.x[0];  // select chain: a dynamic index would put PartPtrs on the stack
+#pragma unroll
+      for (int d = 1; d < RANK; d++) base = (a == d) ? p.x[d] : base;
+#pragma unroll
+      for (int d = 0; d < RANK; d++) base = (a == RANK + d) ? p.v[d] : base;
+      if (l * 16 < ncnt) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + nn0 + l * 16));
+    }
+    // box of the current item: its cp.async group is the last but one of this thread
+    __pipeline_wait_prior(1);
+    if (cur_tma) {
+      mbar_wait(&mbar[b], (phase >> b) & 1u);
+      phase ^= 1u << b;
+    } else {
+      __syncthreads();
+    }
+    const double* __restrict__ cbox = box + b * BOXD;
+    const int ttx = ct % tg.ntx, tty = (ct / tg.ntx) % tg.nty, ttz = ct / (tg.ntx * tg.nty);
+    const int oi = ttx * tg.tx - NNPM_TH, oj = tty * tg.ty - NNPM_TH, ok = (int)g.kz0 + ttz * tg.tz - NNPM_TH;  // mesh cell of halo cell 0
+    auto fetch = [&](double* x, double* v, int qn) {
+      if (qn < ccnt) load6(x, v, cn0 + qn);
+    };
+    auto process = [&](double* x, double* v, int q) {
+      double pa[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int d = 0; d < RANK; d++) {
+        if (COMOVING) x[d] = __dadd_rn(x[d], __dmul_rn(pp.c0, v[d]));
+        x[d] = wrap01_sel(x[d]);
+      }
+      int i, j, k = 0;
+      double dx, dy, dz = 0.0;
+      cell_fast(x[0], g.fN1, i, dx);
+      cell_fast(x[1], g.fN2, j, dy);
+      const unsigned ri = (unsigned)tile_rel(i, oi, N1), rj = (unsigned)tile_rel(j, oj, N2);
+      unsigned rk = 0;
+      bool fast = ri < fx && rj < fy;
+      if (RANK == 3) {
+        cell_fast(x[2], g.fN3, k, dz);
+        rk = (unsigned)tile_rel(k, ok, N3);
+        fast = fast && rk < fz;
+      }
+      if (!fast) {
+        slow_list[atomicAdd(slow_count, 1ull)] = (uint32_t)(cn0 + q);
+      } else {
+        const double* b0 = cbox + (rk * BXY + rj * BX + ri);
+        if (RANK == 2) cic_grad_gather_fma<2>([&](int a, int bb, int) { return b0[bb * BX + a]; }, dx, dy, 0.0, gfac, pa);
+        else cic_grad_gather_fma<3>([&](int a, int bb, int c) { return b0[c * BXY + bb * BX + a]; }, dx, dy, dz, gfac, pa);
+        push_finish_fast<RANK, COMOVING>(p, cn0 + q, x, v, pa, pp, ra, mxa, mxv, mxp);
+      }
+    };
+    int q = tid;
+    while (q < ccnt) {
+      fetch(xb, vb, q + NT);
+      process(xa, va, q);
+      q += NT;
+      if (q >= ccnt) break;
+      fetch(xa, va, q + NT);
+      process(xb, vb, q);
+      q += NT;
+    }
+    if (nt < 0) break;
+    if (tid < ncnt) load6(xa, va, nn0 + tid);  // L2 hits (prefetched above), in flight across the barrier and the staging
+    __syncthreads();  // every thread is done with buffer b before the next iteration's staging overwrites it
+    ct = nt; cn0 = nn0; ccnt = ncnt;
+    nt = ft; nn0 = fn0; ncnt = fcnt;
+    cur_tma = nxt_tma;
+    b ^= 1;
+    w += G;
+  }
+  block_max3(mxa, mxv, mxp, red);
+}
 // ------------------------------------------------------------------------------------------
 // Tiled push with the particle streams on the TMA engine.  Same arithmetic as k_push_tile; what changes
 // is who talks to HBM: a dedicated DMA warp streams the work item's six arrays through two
@@ -1201,7 +1389,9 @@ __device__ __forceinline__ void bulk_reduce_add(void* gdst, const void* ssrc, un
 }
 
 // BULK: flush rows with cp.reduce.async.bulk (needs N1 even and >= NNPM_DX); otherwise per-cell atomics.
-template <int RANK, bool FIXED, bool PRE>
+// UNR: particles whose loads are issued together before any of them is scattered (1 or 2): the loop has no
+// software prefetch, so UNR = 2 doubles the bytes each thread keeps in flight (at ~12 more registers).
+template <int RANK, bool FIXED, bool PRE, int UNR>
 __global__ void __launch_bounds__(256)
 k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, WorkList wl, const uint32_t* __restrict__ tile_off,
                double* __restrict__ mesh, double m, double fscale, uint32_t* __restrict__ slow_list,
@@ -1238,13 +1428,7 @@ k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, WorkList wl, 
     const uint32_t old = atomicAdd(&acc[2 * idx], lo);
     atomicAdd(&acc[2 * idx + 1], (uint32_t)(q >> 32) + (old > ~lo ? 1u : 0u));
   };
-  for (int q = threadIdx.x; q < cnt; q += 256) {
-    double x0 = px0[q], x1 = px1[q], x2 = (RANK == 3) ? px2[q] : 0.0;
-    if (PRE) {
-      x0 = __dadd_rn(x0, __dmul_rn(c0, pv0[q]));
-      x1 = __dadd_rn(x1, __dmul_rn(c0, pv1[q]));
-      if (RANK == 3) x2 = __dadd_rn(x2, __dmul_rn(c0, pv2[q]));
-    }
+  auto scatter = [&](int q, double x0, double x1, double x2) {
     int i, j, k = 0;
     double dx, dy, dz = 0.0;
     cell_fast(wrap01_sel(x0), g.fN1, i, dx);
@@ -1259,7 +1443,7 @@ k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, WorkList wl, 
     }
     if (!fast) {  // strayed beyond the box since the sort: the global-atomic kernel takes it
       slow_list[atomicAdd(slow_count, 1ull)] = (uint32_t)(n0 + q);
-      continue;
+      return;
     }
     // unit-mass weights in the reference's order (1-dx)*(1-dy)*(1-dz) ... (ParticleMesh.jl:376-379,
     // :395-402), pre-scaled by 2^B (exact: a power of two commutes with every rounding)
@@ -1275,6 +1459,33 @@ k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, WorkList wl, 
       sadd(b + 1, __dmul_rn(w10, odz)); sadd(b + DX + 1, __dmul_rn(w11, odz));
       sadd(b + DXY, __dmul_rn(w00, dz)); sadd(b + DXY + DX, __dmul_rn(w01, dz));
       sadd(b + DXY + 1, __dmul_rn(w10, dz)); sadd(b + DXY + DX + 1, __dmul_rn(w11, dz));
+    }
+  };
+  for (int q = threadIdx.x; q < cnt; q += 256 * UNR) {
+    double x0[UNR], x1[UNR], x2[UNR], v0[UNR], v1[UNR], v2[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      const int qu = q + 256 * u;
+      x0[u] = x1[u] = x2[u] = v0[u] = v1[u] = v2[u] = 0.0;
+      if (u == 0 || qu < cnt) {
+        x0[u] = px0[qu]; x1[u] = px1[qu];
+        if (RANK == 3) x2[u] = px2[qu];
+        if (PRE) {
+          v0[u] = pv0[qu]; v1[u] = pv1[qu];
+          if (RANK == 3) v2[u] = pv2[qu];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      const int qu = q + 256 * u;
+      if (u > 0 && qu >= cnt) break;
+      if (PRE) {
+        x0[u] = __dadd_rn(x0[u], __dmul_rn(c0, v0[u]));
+        x1[u] = __dadd_rn(x1[u], __dmul_rn(c0, v1[u]));
+        if (RANK == 3) x2[u] = __dadd_rn(x2[u], __dmul_rn(c0, v2[u]));
+      }
+      scatter(qu, x0[u], x1[u], x2[u]);
     }
   }
   __syncthreads();

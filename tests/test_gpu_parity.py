@@ -102,7 +102,8 @@ def test_potential_fused_z_pass(lib_built, O, dims):
 
 @pytest.mark.parametrize("dims,rank", [((48, 20, 1), 2), ((64, 64, 1), 2), ((40, 24, 20), 3), ((64, 32, 32), 3), ((16, 16, 16), 3)])
 @pytest.mark.parametrize("mode", ["atomic", "fixedpoint"])
-def test_tiled_deposit_matches_oracle_and_global_path(lib_built, O, dims, rank, mode):
+@pytest.mark.parametrize("unroll", [1, 2])
+def test_tiled_deposit_matches_oracle_and_global_path(lib_built, O, dims, rank, mode, unroll):
     """shared-memory tiled scatter on tile-sorted particles == oracle == global-atomic path, also after
     the particles strayed from their tiles (no re-sort); fixed-point sums are bit-identical."""
     from noname_b200 import DevicePM
@@ -111,6 +112,7 @@ def test_tiled_deposit_matches_oracle_and_global_path(lib_built, O, dims, rank, 
     m = 0.41
     shape = (dims[2], dims[1], dims[0])
     with DevicePM(dims, npart, rank=rank, deposit_mode=mode) as dev:
+        dev.set_option("deposit_unroll", unroll)
         dev.upload(x, v, m)
         dev.sort()
         for stray_dt in (0.0, 0.4, 3.0):           # 0.05-sigma velocities: up to ~cells of straying
@@ -274,10 +276,20 @@ def test_fused_step_matches_oracle(lib_built, O, dims, rank, comoving, sort):
     assert st.kernel_launches > 0 and st.n_halo_violations == 0
 
 
-@pytest.mark.parametrize("dims,rank", [((48, 20, 1), 2), ((64, 64, 1), 2), ((40, 24, 20), 3), ((64, 32, 32), 3)])
+# kernel variants of the tiled push: one CTA per work item (register loads / DMA warp), and the persistent
+# kernel at 256 / 320 / 384 threads, also on a 3-CTA grid so that every CTA walks many work items through
+# both box buffers (the default grid of 2 * SMs - 1 gives each CTA at most one item at test sizes)
+PUSH_VARIANTS = [{}, {"push_tma": 1}, {"push_persist": 1}, {"push_persist": 1, "push_grid": 3},
+                 {"push_persist": 2, "push_grid": 2}, {"push_persist": 3, "push_grid": 5}]
+
+
+# (128, 32, 32) and (128, 64, 1) have tiles whose phi box lies inside the mesh (staged by one TMA tensor
+# copy); on the smaller meshes every box wraps periodically (cp.async rows)
+@pytest.mark.parametrize("dims,rank", [((48, 20, 1), 2), ((64, 64, 1), 2), ((128, 64, 1), 2), ((40, 24, 20), 3),
+                                       ((64, 32, 32), 3), ((128, 32, 32), 3)])
 @pytest.mark.parametrize("comoving", [False, True])
-@pytest.mark.parametrize("push_tma", [0, 1])
-def test_tiled_push_multi_step_matches_oracle(lib_built, O, dims, rank, comoving, push_tma):
+@pytest.mark.parametrize("variant", PUSH_VARIANTS, ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "default")
+def test_tiled_push_multi_step_matches_oracle(lib_built, O, dims, rank, comoving, variant):
     """Tile-sorted shared-memory path over several steps (particles stray from their tiles between
     sorts and take the global fallback): same trajectory as the oracle."""
     from noname_b200 import DevicePM
@@ -289,7 +301,8 @@ def test_tiled_push_multi_step_matches_oracle(lib_built, O, dims, rank, comoving
     xr, vr = x.copy(), v.copy()
     untiled = 0
     with DevicePM(dims, npart, rank=rank, sort_every=4) as dev:
-        dev.set_option("push_tma", push_tma)
+        for k, val in variant.items():
+            dev.set_option(k, val)
         dev.upload(x, v, m)
         for it in range(6):
             dt = 0.02
@@ -347,7 +360,8 @@ def test_synthetic_ics_match_oracle(lib_built, O):
 
 
 @pytest.mark.parametrize("mode", ["atomic", "fixedpoint"])
-def test_clustered_state_matches_oracle(lib_built, O, mode):
+@pytest.mark.parametrize("variant", [{}, {"push_persist": 1, "push_grid": 7, "deposit_unroll": 2}], ids=["default", "persist"])
+def test_clustered_state_matches_oracle(lib_built, O, mode, variant):
     """BASELINE config 4 stand-in at test size: device-generated clustered particles equal the oracle's
     generator; a tile then holds many chunks of the work list (collapsed blobs), and the tiled deposit /
     push on that state equal the oracle."""
@@ -356,6 +370,8 @@ def test_clustered_state_matches_oracle(lib_built, O, mode):
     xr, vr = O.synthetic_clustered((n, n, n), 3, 777, 3, 0.5 / 32, 0.002)
     m = 32.0 ** 3 / n ** 3
     with DevicePM(dims, n ** 3, rank=3, sort_every=1, deposit_mode=mode) as dev:
+        for k, val in variant.items():
+            dev.set_option(k, val)
         dev.init_synthetic((n, n, n), kind="clustered", seed=777, nmodes=3, kmax=1, disp_rms=0.5 / 32, vfac=0.002, m=m)
         xg, vg = dev.download()
         assert np.max(np.abs(xg - xr)) < 1e-13 and np.max(np.abs(vg - vr)) < 1e-15
