@@ -192,11 +192,21 @@ int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, in
  *                  CTAs per SM (both measured slower than the default at 1024^3)
  *   "peer_transpose" nranks > 1: 1 = copy-engine peer copies over NVLink (default), 2 = remote-store
  *                  kernels, 0 = grouped ncclSend/ncclRecv
+ *   "l2pf_push"    1 = each CTA of the tiled push pulls its work item's x, v runs into L2 with one
+ *                  cp.async.bulk.prefetch.L2 per array before it stages its phi box (default); n > 1 = the item n
+ *                  CTAs ahead instead (measured slower); 0 = off
+ *   "l2pf_deposit" 1 = the same in the tiled deposit (default), 0 = off
+ *   "deposit_unroll" 2 = the tiled deposit issues the loads of two particles before scattering either (default), 1 = one
+ *   "push_depth"   2 = the tiled push keeps two particles' loads in flight ahead of the one processed (three register
+ *                  sets; measured equal to the default depth 1)
  *   "push_persist" 1 = persistent tiled push: 2 resident CTAs per SM walk the work list with double-buffered
  *                  phi boxes (next box staged by TMA while the current one is gathered from), 2 / 3 = the same
- *                  with 320 / 384 threads per CTA (96 / 80 registers); 0 = one CTA per work item
+ *                  with 320 / 384 threads per CTA (96 / 80 registers); 0 = one CTA per work item (default:
+ *                  measured equal at best)
+ *   "push_flags"   persistent push only, bit mask: 4 = dynamic schedule (work indices from a global counter),
+ *                  8 = bulk L2 prefetch of the whole next item, 1 = skip the proxy fence before a TMA re-fill of a
+ *                  box buffer (experiment), 2 = no per-line L2 prefetch; default 12
  *   "push_grid"    CTAs of the persistent push (0 = 2 * SMs - 1); small values make every CTA walk many items
- *   "deposit_unroll" 2 = the tiled deposit issues the loads of two particles before scattering either
  *   "push_minb", "zcols", "cfrun_y", "cfrun_z"  launch-shape experiments */
 int nnpm_set_option(nnpm_ctx *ctx, const char *name, double value);
 

@@ -65,6 +65,7 @@ struct nnpm_ctx {
   // sort scratch
   uint32_t *hist, *bsum, *bsum2, *skey, *srnk;
   uint32_t *wcnt, *wtile, *wbeg;  // work list of the tiled kernels (k_work_count / k_work_fill)
+  unsigned* wctr;                 // work counter of the persistent push's dynamic schedule
   i64 wcap;
   TileGeom tg;
   i64 ntiles;
@@ -122,7 +123,7 @@ struct nnpm_ctx {
   bool have1c;
   int opt_pipeline;
   cudaEvent_t ev_chunk[4];
-  int opt_push_tma, opt_push_persist, opt_push_grid, opt_deposit_unroll, opt_colfft, opt_colfft_z, opt_cfrun_y, opt_cfrun_z, nsm;
+  int opt_l2pf_push, opt_l2pf_deposit, opt_push_depth, opt_push_tma, opt_push_persist, opt_push_grid, opt_push_flags, opt_deposit_unroll, opt_colfft, opt_colfft_z, opt_cfrun_y, opt_cfrun_z, nsm;
   cudaStream_t st2[4];    // side streams: the blocks of a transpose go out on several copy engines at once
   cudaEvent_t ev_fork, ev_join[4];
 };
@@ -365,7 +366,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->acc_valid = c->pa_valid = false;
   c->stage = nullptr; c->stage_elems = 0;
   c->hist = c->bsum = c->bsum2 = c->skey = c->srnk = nullptr;
-  c->wcnt = c->wtile = c->wbeg = nullptr; c->wcap = 0;
+  c->wcnt = c->wtile = c->wbeg = nullptr; c->wcap = 0; c->wctr = nullptr;
   c->have2 = c->havez = c->have3 = false;
   c->have_tmap = false;
   c->opt_fft3d = 0; c->opt_zfused = 2; c->opt_tile_deposit = 1; c->opt_tile_push = 1; c->opt_push_minb = 2; c->opt_bulk_flush = 1;
@@ -382,7 +383,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   for (int i = 0; i < 4; i++) { c->st2[i] = nullptr; c->ev_join[i] = nullptr; }
   c->have1c = false; c->opt_pipeline = 1;
   for (int i = 0; i < 4; i++) c->ev_chunk[i] = nullptr;
-  c->have_tm_y = c->have_tm_z = c->have_tm_z8 = c->have1 = false; c->ytw = nullptr; c->opt_push_tma = 0; c->opt_push_persist = 0; c->opt_push_grid = 0; c->opt_deposit_unroll = 1; c->opt_colfft = 1; c->opt_colfft_z = 0; c->opt_cfrun_y = 1; c->opt_cfrun_z = 1; c->nsm = 148;
+  c->have_tm_y = c->have_tm_z = c->have_tm_z8 = c->have1 = false; c->ytw = nullptr; c->opt_push_tma = 0; c->opt_push_persist = 0; c->opt_push_grid = 0; c->opt_push_flags = 12; c->opt_push_depth = 1; c->opt_l2pf_push = 1; c->opt_l2pf_deposit = 1; c->opt_deposit_unroll = 2; c->opt_colfft = 1; c->opt_colfft_z = 0; c->opt_cfrun_y = 1; c->opt_cfrun_z = 1; c->nsm = 148;
   c->mig_lo = nullptr; c->ghost_rx = nullptr; c->red_buf = nullptr;
   c->np = 0; c->m = 0.0; c->ids_dirty = false; c->field_state = 0;
   c->own_stream = false;
@@ -801,9 +802,9 @@ static int do_deposit(nnpm_ctx* ctx, bool pre, double c0) {
 #define DT(RK, FX, PR)                                                                                                   \
   do {                                                                                                                   \
     if (ctx->opt_deposit_unroll == 2)                                                                                    \
-      k_deposit_tile<RK, FX, PR, 2><<<wgrid, 256, 0, ctx->st>>>(ctx->pp, covered, c0, ctx->g, ctx->tg, wl, ctx->hist, ctx->mesh, ctx->m, fscale, ctx->srnk, (u64*)(ctx->d_red + 5), bulk); \
+      k_deposit_tile<RK, FX, PR, 2><<<wgrid, 256, 0, ctx->st>>>(ctx->pp, covered, c0, ctx->g, ctx->tg, wl, ctx->hist, ctx->mesh, ctx->m, fscale, ctx->srnk, (u64*)(ctx->d_red + 5), bulk, ctx->opt_l2pf_deposit); \
     else                                                                                                                 \
-      k_deposit_tile<RK, FX, PR, 1><<<wgrid, 256, 0, ctx->st>>>(ctx->pp, covered, c0, ctx->g, ctx->tg, wl, ctx->hist, ctx->mesh, ctx->m, fscale, ctx->srnk, (u64*)(ctx->d_red + 5), bulk); \
+      k_deposit_tile<RK, FX, PR, 1><<<wgrid, 256, 0, ctx->st>>>(ctx->pp, covered, c0, ctx->g, ctx->tg, wl, ctx->hist, ctx->mesh, ctx->m, fscale, ctx->srnk, (u64*)(ctx->d_red + 5), bulk, ctx->opt_l2pf_deposit); \
   } while (0)
     if (ctx->R == 3) { if (fixed) { if (pre) DT(3, true, true); else DT(3, true, false); } else { if (pre) DT(3, false, true); else DT(3, false, false); } }
     else { if (fixed) { if (pre) DT(2, true, true); else DT(2, true, false); } else { if (pre) DT(2, false, true); else DT(2, false, false); } }
@@ -1161,26 +1162,29 @@ static int launch_push(nnpm_ctx* ctx, bool comoving, const PushParams& pp) {
     const size_t smem2 = (size_t)2 * NNPM_BOXD(RANK) * sizeof(double);
     // odd grid: the round-robin walk then visits every tile column equally often (tiles per row are a power of
     // two on the usual meshes; an even stride would pin the costlier wrapping edge tiles on a few CTAs)
+    if (!ctx->wctr) CKR(dalloc(ctx, &ctx->wctr, 1));
+    CK(cudaMemsetAsync(ctx->wctr, 0, sizeof(unsigned), ctx->st));
     const unsigned pgrid = ctx->opt_push_grid > 0 ? (unsigned)ctx->opt_push_grid : (unsigned)(2 * ctx->nsm - 1);
 #define LQ(CM, NT)                                                                                                  \
   do {                                                                                                              \
     CK(cudaFuncSetAttribute(k_push_tile_p<RANK, CM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));  \
     k_push_tile_p<RANK, CM, NT><<<pgrid, NT, smem2, ctx->st>>>(ctx->tmap_phi, ctx->pp, covered, ctx->g, ctx->tg, wl, ctx->hist, \
-                                                               ctx->mesh, pp, ctx->d_red, ctx->srnk, slow_count);    \
+                                                               ctx->mesh, pp, ctx->d_red, ctx->srnk, slow_count, ctx->opt_push_flags, ctx->wctr); \
   } while (0)
     if (ctx->opt_push_persist == 3) { if (comoving) LQ(true, 384); else LQ(false, 384); }
     else if (ctx->opt_push_persist == 2) { if (comoving) LQ(true, 320); else LQ(false, 320); }
     else { if (comoving) LQ(true, 256); else LQ(false, 256); }
 #undef LQ
   } else {
-#define LT(CM, MB)                                                                                                  \
+#define LT(CM, MB, PD)                                                                                              \
   do {                                                                                                              \
-    CK(cudaFuncSetAttribute(k_push_tile<RANK, CM, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    k_push_tile<RANK, CM, MB><<<wgrid, 256, smem, ctx->st>>>(ctx->tmap_phi, ctx->pp, covered, ctx->g, ctx->tg, wl, ctx->hist, \
-                                                                             ctx->mesh, pp, ctx->d_red, ctx->srnk, slow_count); \
+    CK(cudaFuncSetAttribute(k_push_tile<RANK, CM, MB, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_push_tile<RANK, CM, MB, PD><<<wgrid, 256, smem, ctx->st>>>(ctx->tmap_phi, ctx->pp, covered, ctx->g, ctx->tg, wl, ctx->hist, \
+                                                                 ctx->mesh, pp, ctx->d_red, ctx->srnk, slow_count, ctx->opt_l2pf_push); \
   } while (0)
-  if (ctx->opt_push_minb >= 3) { if (comoving) LT(true, 3); else LT(false, 3); }
-  else { if (comoving) LT(true, 2); else LT(false, 2); }
+  if (ctx->opt_push_minb >= 3) { if (comoving) LT(true, 3, 1); else LT(false, 3, 1); }
+  else if (ctx->opt_push_depth == 2) { if (comoving) LT(true, 2, 2); else LT(false, 2, 2); }
+  else { if (comoving) LT(true, 2, 1); else LT(false, 2, 1); }
 #undef LT
   }
   LAUNCHED(ctx);
@@ -1304,6 +1308,10 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   else if (!strcmp(name, "push_persist")) ctx->opt_push_persist = v;
   else if (!strcmp(name, "deposit_unroll")) ctx->opt_deposit_unroll = v;
   else if (!strcmp(name, "push_grid")) ctx->opt_push_grid = v;
+  else if (!strcmp(name, "push_flags")) ctx->opt_push_flags = v;
+  else if (!strcmp(name, "push_depth")) ctx->opt_push_depth = v;
+  else if (!strcmp(name, "l2pf_push")) ctx->opt_l2pf_push = v;
+  else if (!strcmp(name, "l2pf_deposit")) ctx->opt_l2pf_deposit = v;
   else if (!strcmp(name, "colfft_z")) ctx->opt_colfft_z = v;
   else if (!strcmp(name, "cfrun_y")) ctx->opt_cfrun_y = v < 1 ? 1 : v;
   else if (!strcmp(name, "cfrun_z")) ctx->opt_cfrun_z = v < 1 ? 1 : v;

@@ -826,11 +826,33 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
       : "memory");
 }
 
-template <int RANK, bool COMOVING, int MINB>
+
+// Pull [n0, n1) of every particle array the kernel reads into L2 with one bulk prefetch per array
+// (cp.async.bulk.prefetch.L2: the copy engine fetches the whole 16-32 KB run as one sequential DRAM burst,
+// no registers, no LSU traffic); the kernel's own 8-byte loads then hit L2.  Issued by threads 0..NARR-1.
+template <int RANK, bool WITH_V>
+__device__ __forceinline__ void l2_prefetch_particles(const PartPtrs& p, i64 n0, i64 n1) {
+  constexpr int NARR = WITH_V ? 2 * RANK : RANK;
+  const int a = threadIdx.x;
+  if (a >= NARR || n1 <= n0) return;
+  const double* base = p.x[0];  // select chain: a dynamic index would put PartPtrs on the stack
+#pragma unroll
+  for (int d = 1; d < RANK; d++) base = (a == d) ? p.x[d] : base;
+  if (WITH_V) {
+#pragma unroll
+    for (int d = 0; d < RANK; d++) base = (a == RANK + d) ? p.v[d] : base;
+  }
+  const u64 lo = (u64)(base + n0) & ~15ull, hi = (u64)(base + n1) & ~15ull;  // 16-byte units inside the run
+  if (hi > lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((unsigned)(hi - lo)) : "memory");
+}
+
+// PD: prefetch depth -- particles whose loads are in flight ahead of the one being processed (1: two
+// register sets alternate; 2: three sets rotate, 12 more registers).
+template <int RANK, bool COMOVING, int MINB, int PD>
 __global__ void __launch_bounds__(256, MINB)
 k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g, TileGeom tg, WorkList wl,
             const uint32_t* __restrict__ tile_off, const double* __restrict__ phi, PushParams pp, i64* __restrict__ red,
-            uint32_t* __restrict__ slow_list, u64* __restrict__ slow_count) {
+            uint32_t* __restrict__ slow_list, u64* __restrict__ slow_count, int pf) {
   extern __shared__ __align__(128) double box[];  // [BZ][BY][BX]
   __shared__ __align__(8) unsigned long long mbar;
   constexpr int BX = NNPM_BX, BY = NNPM_BY, BZ = (RANK == 3) ? NNPM_BZ : 1, BXY = BX * BY;
@@ -841,6 +863,19 @@ k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g
   if (n1 > (i64)tile_off[t + 1]) n1 = tile_off[t + 1];
   if (n1 > np) n1 = np;
   if (n0 >= n1) return;  // uniform across the block
+  if (pf == 1) {
+    l2_prefetch_particles<RANK, true>(p, n0, n1);  // this item's x, v
+  } else if (pf > 1 && threadIdx.x < 2 * RANK) {   // the item pf CTAs ahead (about one wave): in L2 before its CTA starts
+    const unsigned wa = blockIdx.x + (unsigned)pf;
+    if (wa < *wl.count) {
+      const int ta = (int)wl.tile[wa];
+      const i64 a0 = wl.beg[wa];
+      i64 a1 = a0 + NNPM_CHUNK;
+      if (a1 > (i64)tile_off[ta + 1]) a1 = tile_off[ta + 1];
+      if (a1 > np) a1 = np;
+      l2_prefetch_particles<RANK, true>(p, a0, a1);
+    }
+  }
   const int ttx = t % tg.ntx, tty = (t / tg.ntx) % tg.nty, ttz = t / (tg.ntx * tg.nty);
   const int N1 = (int)g.N1, N2 = (int)g.N2, N3 = (int)g.N3;
   const int ti0 = ttx * tg.tx, tj0 = tty * tg.ty, tk0 = ttz * tg.tz;  // tk0: plane within the slab
@@ -900,7 +935,9 @@ k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g
   };
   int q = threadIdx.x;
   double xa[3] = {0.0, 0.0, 0.0}, va[3] = {0.0, 0.0, 0.0}, xb[3] = {0.0, 0.0, 0.0}, vb[3] = {0.0, 0.0, 0.0};
+  double xc[3] = {0.0, 0.0, 0.0}, vc[3] = {0.0, 0.0, 0.0};
   fetch(xa, va, q);
+  if (PD == 2) fetch(xb, vb, q + 256);
   if (interior) {
     __syncthreads();        // mbarrier initialised by thread 0 before anyone polls it
     mbar_wait(&mbar, 0);
@@ -941,14 +978,30 @@ k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g
       push_finish_fast<RANK, COMOVING>(p, n0 + q, x, v, pa, pp, ra, mxa, mxv, mxp);
     }
   };
-  while (q < cnt) {
-    fetch(xb, vb, q + 256);
-    process(xa, va, q);
-    q += 256;
-    if (q >= cnt) break;
-    fetch(xa, va, q + 256);
-    process(xb, vb, q);
-    q += 256;
+  if (PD == 2) {
+    while (q < cnt) {
+      fetch(xc, vc, q + 512);
+      process(xa, va, q);
+      q += 256;
+      if (q >= cnt) break;
+      fetch(xa, va, q + 512);
+      process(xb, vb, q);
+      q += 256;
+      if (q >= cnt) break;
+      fetch(xb, vb, q + 512);
+      process(xc, vc, q);
+      q += 256;
+    }
+  } else {
+    while (q < cnt) {
+      fetch(xb, vb, q + 256);
+      process(xa, va, q);
+      q += 256;
+      if (q >= cnt) break;
+      fetch(xa, va, q + 256);
+      process(xb, vb, q);
+      q += 256;
+    }
   }
   block_max3(mxa, mxv, mxp, red);
 }
@@ -974,9 +1027,10 @@ template <int RANK, bool COMOVING, int NT>
 __global__ void __launch_bounds__(NT, 2)
 k_push_tile_p(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g, TileGeom tg, WorkList wl,
               const uint32_t* __restrict__ tile_off, const double* __restrict__ phi, PushParams pp, i64* __restrict__ red,
-              uint32_t* __restrict__ slow_list, u64* __restrict__ slow_count) {
+              uint32_t* __restrict__ slow_list, u64* __restrict__ slow_count, int flags, unsigned* __restrict__ work_ctr) {
   extern __shared__ __align__(128) double box[];  // 2 x [BZ][BY][BX], NNPM_BOXD doubles apart
   __shared__ __align__(8) unsigned long long mbar[2];
+  __shared__ unsigned s_w[2];  // dynamic schedule: work index thread 0 grabbed for the next-but-one item
   constexpr int BX = NNPM_BX, BY = NNPM_BY, BZ = (RANK == 3) ? NNPM_BZ : 1, BXY = BX * BY, BOXD = NNPM_BOXD(RANK);
   const unsigned nwork = *wl.count;
   const unsigned G = gridDim.x;
@@ -1006,7 +1060,7 @@ k_push_tile_p(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom
     double* dstb = box + b * BOXD;
     if (interior) {
       if (tid == 0) {
-        fence_proxy_async_smem();  // the buffer was last touched through the generic proxy
+        if (!(flags & 1)) fence_proxy_async_smem();  // the buffer was last touched through the generic proxy
         mbar_expect_tx(&mbar[b], (unsigned)(BX * BY * BZ * sizeof(double)));
         tma_load_3d(dstb, &tmap, bx0, by0, bz0, &mbar[b]);
       }
@@ -1039,12 +1093,18 @@ k_push_tile_p(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom
     return interior;
   };
 
-  unsigned w = blockIdx.x;
+  // Schedule.  Static (flags & 4 == 0): item blockIdx.x + i * G.  Dynamic: the first three rounds are static,
+  // then thread 0 takes indices from a global counter -- items start in list order across the GPU, as under
+  // the hardware block scheduler, so concurrently staged boxes stay neighbours (shared halo planes hit L2)
+  // however far the CTAs drift apart.  The index for round i+3 is fetched during round i.
+  const bool dyn = (flags & 4) != 0;
+  unsigned wf = blockIdx.x + 2 * G;  // index of the next-but-one item
+  unsigned round = 0;
   int ct, ccnt, nt, ncnt, ft, fcnt;  // current, next and next-but-one item
   i64 cn0, nn0, fn0;
-  load_item(w, ct, cn0, ccnt);
+  load_item(blockIdx.x, ct, cn0, ccnt);
   if (ct < 0) return;  // uniform: fewer items than CTAs
-  load_item(w + G, nt, nn0, ncnt);
+  load_item(blockIdx.x + G, nt, nn0, ncnt);
   if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
   __syncthreads();
   unsigned phase = 0;  // bit b: parity the next wait on mbar[b] expects
@@ -1063,12 +1123,16 @@ k_push_tile_p(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom
   if (tid < ccnt) load6(xa, va, cn0 + tid);
 
   for (;;) {
-    load_item(w + 2 * G, ft, fn0, fcnt);  // consumed at the top of the next iteration
+    load_item(wf, ft, fn0, fcnt);  // consumed at the top of the next iteration
+    unsigned grabbed = 0;
+    if (dyn && tid == 0) grabbed = atomicAdd(work_ctr, 1u) + 3u * G;  // published before this round's barrier
     bool nxt_tma = false;
     if (nt >= 0) nxt_tma = stage(nt, b ^ 1);
     else __pipeline_commit();
     // pull the next item's first 256 particles into L2: one 128-byte line per thread and array
-    if (nt >= 0 && tid < 2 * RANK * 16) {  // 16 lines of 16 doubles cover 256 particles; NT > 256 leaves the rest to the loads
+    if (flags & 8) {
+      if (nt >= 0) l2_prefetch_particles<RANK, true>(p, nn0, nn0 + ncnt);  // the whole next item, one bulk prefetch per array
+    } else if (nt >= 0 && tid < 2 * RANK * 16 && !(flags & 2)) {  // 16 lines of 16 doubles cover 256 particles; NT > 256 leaves the rest to the loads
       const int a = tid >> 4, l = tid & 15;
       const double* base = p.x[0];  // select chain: a dynamic index would put PartPtrs on the stack
 #pragma unroll
@@ -1131,12 +1195,14 @@ k_push_tile_p(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom
     }
     if (nt < 0) break;
     if (tid < ncnt) load6(xa, va, nn0 + tid);  // L2 hits (prefetched above), in flight across the barrier and the staging
+    if (dyn && tid == 0) s_w[round & 1] = grabbed;
     __syncthreads();  // every thread is done with buffer b before the next iteration's staging overwrites it
+    wf = dyn ? s_w[round & 1] : wf + G;
+    round++;
     ct = nt; cn0 = nn0; ccnt = ncnt;
     nt = ft; nn0 = fn0; ncnt = fcnt;
     cur_tma = nxt_tma;
     b ^= 1;
-    w += G;
   }
   block_max3(mxa, mxv, mxp, red);
 }
@@ -1395,7 +1461,7 @@ template <int RANK, bool FIXED, bool PRE, int UNR>
 __global__ void __launch_bounds__(256)
 k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, WorkList wl, const uint32_t* __restrict__ tile_off,
                double* __restrict__ mesh, double m, double fscale, uint32_t* __restrict__ slow_list,
-               u64* __restrict__ slow_count, int bulk) {
+               u64* __restrict__ slow_count, int bulk, int pf) {
   constexpr int DX = NNPM_DX, DY = NNPM_DY, DZ = (RANK == 3) ? NNPM_DZ : 1, DXY = DX * DY, NBOX = DXY * DZ;
   // accumulators: little-endian (lo, hi) uint32 pairs == one u64 per cell; converted in place to f64
   __shared__ __align__(16) uint32_t acc[2 * NBOX];
@@ -1406,6 +1472,7 @@ k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, WorkList wl, 
   if (n1 > (i64)tile_off[t + 1]) n1 = tile_off[t + 1];
   if (n1 > np) n1 = np;
   if (n0 >= n1) return;  // uniform across the block
+  if (pf) l2_prefetch_particles<RANK, PRE>(p, n0, n1);  // lands while the box is being zeroed
   const int ttx = t % tg.ntx, tty = (t / tg.ntx) % tg.nty, ttz = t / (tg.ntx * tg.nty);
   for (int c = threadIdx.x; c < NBOX / 2; c += 256) ((uint4*)acc)[c] = make_uint4(0u, 0u, 0u, 0u);
   if (threadIdx.x == 0 && (NBOX & 1)) { acc[2 * NBOX - 2] = 0u; acc[2 * NBOX - 1] = 0u; }

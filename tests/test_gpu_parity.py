@@ -280,7 +280,11 @@ def test_fused_step_matches_oracle(lib_built, O, dims, rank, comoving, sort):
 # kernel at 256 / 320 / 384 threads, also on a 3-CTA grid so that every CTA walks many work items through
 # both box buffers (the default grid of 2 * SMs - 1 gives each CTA at most one item at test sizes)
 PUSH_VARIANTS = [{}, {"push_tma": 1}, {"push_persist": 1}, {"push_persist": 1, "push_grid": 3},
-                 {"push_persist": 2, "push_grid": 2}, {"push_persist": 3, "push_grid": 5}]
+                 {"push_persist": 2, "push_grid": 2}, {"push_persist": 3, "push_grid": 5},
+                 {"push_persist": 1, "push_flags": 4, "push_grid": 3}, {"push_persist": 2, "push_flags": 12, "push_grid": 2},
+                 {"push_persist": 1, "push_flags": 12},
+                 {"push_depth": 2, "l2pf_push": 0}, {"l2pf_push": 1, "l2pf_deposit": 1, "deposit_unroll": 2},
+                 {"l2pf_push": 7, "l2pf_deposit": 0, "deposit_unroll": 1}]
 
 
 # (128, 32, 32) and (128, 64, 1) have tiles whose phi box lies inside the mesh (staged by one TMA tensor

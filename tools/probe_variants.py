@@ -29,13 +29,14 @@ for var in variants:
         dev.set_option(k, float(v))
     acc = {}
     walls = []
-    for it in range(5):
+    nsteps = int(os.environ.get('PROBE_STEPS', 5))
+    for it in range(nsteps):
         t = time.time()
         st = dev.step_comoving(0.2 / n, 1.0, 1.0, 0.8, 1.0)
         walls.append((time.time() - t) * 1e3)
         if it:
             for k, v in st.as_dict()["ms"].items():
-                acc[k] = acc.get(k, 0.0) + v / 4
+                acc[k] = acc.get(k, 0.0) + v / (nsteps - 1)
     d = st.as_dict()
     print("%-40s dep %.2f solve %.2f (z %.2f) push %.2f wall %.2f | untiled %d maxv %.6g maxpa %.6g" % (
-        var, acc["deposit"], acc["solve"], acc["fft_z"], acc["push"], sum(walls[1:]) / 4, d["n_untiled"], d["max_abs_v"], d["max_pa"]), flush=True)
+        var, acc["deposit"], acc["solve"], acc["fft_z"], acc["push"], sum(walls[1:]) / (nsteps - 1), d["n_untiled"], d["max_abs_v"], d["max_pa"]), flush=True)
