@@ -38,9 +38,13 @@ def main():
             errs.append(f"rank {rank}: {name} FAILED {detail}")
 
     # (deposit mode, sort cadence): sort_every > 0 runs the tiled shared-memory deposit / push on slabs
-    for mode, sort_every in (("atomic", 0), ("fixedpoint", 0), ("atomic", 1), ("fixedpoint", 2)):
+    # the last case runs the persistent push (3 CTAs, so that each walks many work items) on slabs with ghost planes
+    for mode, sort_every, opts in (("atomic", 0, {}), ("fixedpoint", 0, {}), ("atomic", 1, {}), ("fixedpoint", 2, {}),
+                                   ("atomic", 1, {"push_persist": 1, "push_grid": 3})):
         dev = DevicePM(dims, npart, rank=3, device=lr, nranks=P, rank_id=rank, deposit_mode=mode, timing=True,
                        sort_every=sort_every)
+        for k_, v_ in opts.items():
+            dev.set_option(k_, v_)
         uid = [DevicePM.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         dev.comm_init(uid[0])
