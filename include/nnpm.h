@@ -179,7 +179,7 @@ int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, in
 
 /* Runtime tuning knobs (new; no reference counterpart).  Unknown names -> NNPM_ERR_ARG.
  *   "fft3d"        1 = single cuFFT 3-D plan instead of 2-D + fused z pass (nranks == 1 only)
- *   "zfused"       2 = fused z-FFT * Green * z-iFFT kernel, persistent with TMA prefetch (default),
+ *   "zfused"       2 = fused z-FFT * Green * z-iFFT kernel, persistent with TMA prefetch (default; N3 = 64..2048),
  *                  1 = the same with one CTA per column group and register loads, 0 = cuFFT z + Green kernel
  *   "tile_deposit" 1 = shared-memory tiled deposit on tile-sorted particles (default), 0 = global atomics
  *   "tile_push"    1 = push gathers phi from a shared-memory tile on sorted particles, 0 = L2 gather
@@ -207,6 +207,8 @@ int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, in
  *                  8 = bulk L2 prefetch of the whole next item, 1 = skip the proxy fence before a TMA re-fill of a
  *                  box buffer (experiment), 2 = no per-line L2 prefetch; default 12
  *   "push_grid"    CTAs of the persistent push (0 = 2 * SMs - 1); small values make every CTA walk many items
+ *   "zsplit"       1 = run N3 in 128..1024 through the radix-2 wrapper of the persistent fused z pass (the path
+ *                  N3 = 2048 always takes); test hook
  *   "push_minb", "zcols", "cfrun_y", "cfrun_z"  launch-shape experiments */
 int nnpm_set_option(nnpm_ctx *ctx, const char *name, double value);
 

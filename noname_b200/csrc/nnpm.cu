@@ -115,8 +115,9 @@ struct nnpm_ctx {
   int opt_peer;   // 0 = NCCL send/recv, 1 = copy-engine peer copies (default), 2 = remote-store kernels
   int* bar_buf;
   // TMA-staged column FFT engine (nnpm_colfft.cuh)
-  CUtensorMap tm_y, tm_z, tm_z8;
-  bool have_tm_y, have_tm_z, have_tm_z8, have1;
+  CUtensorMap tm_y, tm_z, tm_z8, tm_z4;
+  bool have_tm_y, have_tm_z, have_tm_z8, have_tm_z4, have1;
+  int opt_zsplit;  // test hook: run N3 <= 1024 through the radix-2 wrapper of the persistent fused z pass
   double2* ytw;
   cufftHandle plan1f, plan1b;  // batched 1-D x transforms (r2c / c2r) over the owned rows
   cufftHandle plan1fc;         // the same over one chunk of planes (pipelined multi-GPU solve)
@@ -383,7 +384,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   for (int i = 0; i < 4; i++) { c->st2[i] = nullptr; c->ev_join[i] = nullptr; }
   c->have1c = false; c->opt_pipeline = 1;
   for (int i = 0; i < 4; i++) c->ev_chunk[i] = nullptr;
-  c->have_tm_y = c->have_tm_z = c->have_tm_z8 = c->have1 = false; c->ytw = nullptr; c->opt_push_tma = 0; c->opt_push_persist = 0; c->opt_push_grid = 0; c->opt_push_flags = 12; c->opt_push_depth = 1; c->opt_l2pf_push = 1; c->opt_l2pf_deposit = 1; c->opt_deposit_unroll = 2; c->opt_colfft = 1; c->opt_colfft_z = 0; c->opt_cfrun_y = 1; c->opt_cfrun_z = 1; c->nsm = 148;
+  c->have_tm_y = c->have_tm_z = c->have_tm_z8 = c->have_tm_z4 = c->have1 = false; c->opt_zsplit = 0; c->ytw = nullptr; c->opt_push_tma = 0; c->opt_push_persist = 0; c->opt_push_grid = 0; c->opt_push_flags = 12; c->opt_push_depth = 1; c->opt_l2pf_push = 1; c->opt_l2pf_deposit = 1; c->opt_deposit_unroll = 2; c->opt_colfft = 1; c->opt_colfft_z = 0; c->opt_cfrun_y = 1; c->opt_cfrun_z = 1; c->nsm = 148;
   c->mig_lo = nullptr; c->ghost_rx = nullptr; c->red_buf = nullptr;
   c->np = 0; c->m = 0.0; c->ids_dirty = false; c->field_state = 0;
   c->own_stream = false;
@@ -1310,6 +1311,7 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   else if (!strcmp(name, "push_grid")) ctx->opt_push_grid = v;
   else if (!strcmp(name, "push_flags")) ctx->opt_push_flags = v;
   else if (!strcmp(name, "push_depth")) ctx->opt_push_depth = v;
+  else if (!strcmp(name, "zsplit")) ctx->opt_zsplit = v;
   else if (!strcmp(name, "l2pf_push")) ctx->opt_l2pf_push = v;
   else if (!strcmp(name, "l2pf_deposit")) ctx->opt_l2pf_deposit = v;
   else if (!strcmp(name, "colfft_z")) ctx->opt_colfft_z = v;

@@ -288,18 +288,34 @@ k_colfft_z2(const __grid_constant__ CUtensorMap tmap, ColFftArgs a) {
 // as the last exchange read of group g is done (start of the final inverse pass), one thread issues the
 // tensor load of group g + gridDim.x, so the load latency and transfer run under the final pass'
 // arithmetic and its stores instead of in front of the next group's first pass.
-template <int R1, int R2>
+//
+// TWO: transform length NT = 2 * R1 * R2 (N3 = 2048 = 2 x 32 x 32, the fine mesh of BASELINE config 5) by one
+// extra radix-2 step around the two-pass engine, without a third pass over shared memory.  A group is 4 real
+// columns (64-byte rows, [NT][4] in shared memory = the same 128 KB); the 8 "virtual columns" the 8 thread
+// columns work on are (real column, parity): virtual column (cc, 0) transforms e[n] = a[n] + a[n + N] and
+// yields the even bins X[2q], (cc, 1) transforms o[n] = (a[n] - a[n + N]) W_NT^n and yields the odd bins
+// X[2q + 1] (decimation in frequency).  Pass A forms e / o on the fly from the landing zone (two reads instead
+// of one); the Green factor uses the true bin kz = 2q + parity; after the inverse passes the two parities of a
+// column sit in lanes l and l ^ 4 of one warp and are combined by one shuffle exchange:
+// x[n] = E[n] + W_NT^-n O[n],  x[n + N] = E[n] - W_NT^-n O[n].
+template <int R1, int R2, bool TWO>
 __global__ void __launch_bounds__(8 * (R1 > R2 ? R1 : R2), 1)
 k_zfused_p(const __grid_constant__ CUtensorMap tmap, double2* __restrict__ T, i64 ncol, ColFftArgs a) {
   constexpr int C = 8, N = R1 * R2, RM = R1 > R2 ? R1 : R2, B1 = zf_log2(R1), B2 = zf_log2(R2);
-  constexpr int RB = N < 256 ? N : 256, NOPS = N / RB;
+  constexpr int NT = TWO ? 2 * N : N;   // transform length
+  constexpr int CR = TWO ? 4 : 8;       // real columns per group
+  constexpr int TS = TWO ? 2 : 1;       // W_N^m = stw[TS * m]  (stw holds W_NT^m)
+  constexpr int RB = NT < 256 ? NT : 256, NOPS = NT / RB;
   extern __shared__ __align__(128) unsigned char cf_smem[];
-  double2* zsm = (double2*)cf_smem;  // [N][C]
-  double2* stw = zsm + N * C;
-  double* ss3 = (double*)(stw + N);
+  double2* zsm = (double2*)cf_smem;  // [NT][CR]
+  double2* stw = zsm + NT * CR;
+  double* ss3 = (double*)(stw + NT);
   __shared__ __align__(8) unsigned long long full;
   const int tid = threadIdx.x, c = tid % C, j = tid / C;
-  for (int t = tid; t < N; t += blockDim.x) {
+  const int cc = TWO ? (c & 3) : c, par = TWO ? (c >> 2) : 0;
+  // element (row r of the length-N sub-transform, virtual column c) of the exchange buffer
+  auto Z = [&](int r) { return TWO ? (r + N * par) * CR + cc : r * C + c; };
+  for (int t = tid; t < NT; t += blockDim.x) {
     stw[t] = __ldg(a.tw + t);
     ss3[t] = __ldg(a.s3 + t);
   }
@@ -307,9 +323,9 @@ k_zfused_p(const __grid_constant__ CUtensorMap tmap, double2* __restrict__ T, i6
   __syncthreads();
   auto issue_load = [&](int g) {  // thread 0 only
     const int og = g / a.nicg, icg = g - og * a.nicg;
-    mbar_expect_tx(&full, (unsigned)(N * C * sizeof(double2)));
+    mbar_expect_tx(&full, (unsigned)(NT * CR * sizeof(double2)));
 #pragma unroll
-    for (int o = 0; o < NOPS; o++) tma_load_3d(zsm + o * RB * C, &tmap, icg * 16, og + a.outer0, o * RB, &full);
+    for (int o = 0; o < NOPS; o++) tma_load_3d(zsm + o * RB * CR, &tmap, icg * (2 * CR), og + a.outer0, o * RB, &full);
   };
   int g = blockIdx.x;
   if (tid == 0 && g < a.ngroups) issue_load(g);
@@ -317,7 +333,7 @@ k_zfused_p(const __grid_constant__ CUtensorMap tmap, double2* __restrict__ T, i6
   double2 v[RM];
   for (; g < a.ngroups; g += gridDim.x) {
     const int og = g / a.nicg, icg = g - og * a.nicg, jl = og + a.outer0;
-    const int ic = icg * C + c;
+    const int ic = icg * CR + cc;
     const bool colok = ic < a.icn;
     double sxy = 1.0;
     if (colok) sxy = __ldg(a.s1 + ic) + __ldg(a.s2 + a.j0 + jl);
@@ -327,31 +343,44 @@ k_zfused_p(const __grid_constant__ CUtensorMap tmap, double2* __restrict__ T, i6
     // ---- forward pass A: radix R1 over rows j + r*R2 (from the landing zone)
     if (j < R2) {
 #pragma unroll
-      for (int r = 0; r < R1; r++) v[r] = zsm[(j + r * R2) * C + c];
+      for (int r = 0; r < R1; r++) {
+        const int rr = j + r * R2;
+        if (!TWO) {
+          v[r] = zsm[rr * C + c];
+        } else {
+          const double2 a0 = zsm[rr * CR + cc], a1 = zsm[(rr + N) * CR + cc];
+          if (par) {
+            const double2 w = stw[rr];
+            v[r] = zmul(zsub(a0, a1), w.x, w.y);
+          } else {
+            v[r] = zadd(a0, a1);
+          }
+        }
+      }
       ZDif<R1, 0, -1>::run(v);
     }
     __syncthreads();  // inputs are in registers: the buffer becomes the exchange
     if (j < R2) {
 #pragma unroll
-      for (int q = 0; q < R1; q++) zsm[(j * R1 + q) * C + c] = v[zf_brev(q, B1)];
+      for (int q = 0; q < R1; q++) zsm[Z(j * R1 + q)] = v[zf_brev(q, B1)];
     }
     __syncthreads();
     // ---- forward pass B, Green's function, inverse pass A'
     if (j < R1) {
 #pragma unroll
-      for (int r = 0; r < R2; r++) v[r] = zsm[(j + r * R1) * C + c];
+      for (int r = 0; r < R2; r++) v[r] = zsm[Z(j + r * R1)];
     }
     __syncthreads();
     if (j < R1) {
 #pragma unroll
       for (int r = 1; r < R2; r++) {
-        const double2 w = stw[r * j];
+        const double2 w = stw[TS * r * j];
         v[r] = zmul(v[r], w.x, w.y);
       }
       ZDif<R2, 0, -1>::run(v);
 #pragma unroll
-      for (int q = 0; q < R2; q++) {  // X[kz] *= scale / Ginv, kz = j + q*R1   (ParticleMesh.jl:494-501)
-        const int kz = j + q * R1;
+      for (int q = 0; q < R2; q++) {  // X[kz] *= scale / Ginv   (ParticleMesh.jl:494-501)
+        const int kz = TWO ? 2 * (j + q * R1) + par : j + q * R1;
         const double ginv = -4.0 * (sxy + ss3[kz]);
         double f = (ginv != 0.0) ? a.scale * zf_rcp(ginv) : a.scale;
         if (dc_col && kz == 0) f = 0.0;
@@ -361,27 +390,39 @@ k_zfused_p(const __grid_constant__ CUtensorMap tmap, double2* __restrict__ T, i6
       }
       ZDit<R2, 0, +1>::run(v);
 #pragma unroll
-      for (int r = 0; r < R2; r++) zsm[(j * R2 + r) * C + c] = v[r];
+      for (int r = 0; r < R2; r++) zsm[Z(j * R2 + r)] = v[r];
     }
     __syncthreads();
     // ---- inverse pass B': radix R1 -> rows j + q*R2, stored straight from registers
     if (j < R2) {
 #pragma unroll
-      for (int r = 0; r < R1; r++) v[r] = zsm[(j + r * R2) * C + c];
+      for (int r = 0; r < R1; r++) v[r] = zsm[Z(j + r * R2)];
     }
     __syncthreads();  // the exchange is consumed: the buffer is free for the next group's tensor load
     if (tid == 0 && g + (int)gridDim.x < a.ngroups) issue_load(g + gridDim.x);
-    if (j < R2) {
+    if (j < R2) {  // warp-uniform: R2 is a multiple of the 4 values of j a warp holds
 #pragma unroll
       for (int r = 1; r < R1; r++) {
-        const double2 w = stw[r * j];
+        const double2 w = stw[TS * r * j];
         v[r] = zmul(v[r], w.x, -w.y);
       }
       ZDif<R1, 0, +1>::run(v);
-      if (colok) {
-        double2* Tc = T + (i64)jl * a.icn + ic;
+      double2* Tc = T + (i64)jl * a.icn + ic;
 #pragma unroll
-        for (int q = 0; q < R1; q++) Tc[(i64)(j + q * R2) * ncol] = v[zf_brev(q, B1)];
+      for (int q = 0; q < R1; q++) {
+        const int n = j + q * R2;
+        double2 e = v[zf_brev(q, B1)];
+        if (TWO) {  // lanes l (parity 0: E[n]) and l ^ 4 (parity 1: O[n]) hold the same column
+          if (par) {
+            const double2 w = stw[n];
+            e = zmul(e, w.x, -w.y);
+          }
+          double2 o;
+          o.x = __shfl_xor_sync(0xffffffffu, e.x, 4);
+          o.y = __shfl_xor_sync(0xffffffffu, e.y, 4);
+          e = par ? zsub(o, e) : zadd(e, o);
+        }
+        if (colok) Tc[(i64)(n + N * par) * ncol] = e;
       }
     }
   }
@@ -510,16 +551,28 @@ static int colfft_z_green(nnpm_ctx* ctx, double2* T, double scale) {
 }
 
 // persistent k_zfused with TMA prefetch over the local rows jl in [jlbeg, jlend)
+static bool zfused_p_two(const nnpm_ctx* ctx) {  // N3 = 2 x (two-pass length): 2048 always, smaller lengths as a test hook
+  int r1, r2;
+  const i64 N3 = ctx->g.N3;
+  if (N3 % 2 || !zfused_factor(N3 / 2, &r1, &r2)) return false;
+  return !zfused_factor(N3, &r1, &r2) || ctx->opt_zsplit;
+}
 static int zfused_p_launch(nnpm_ctx* ctx, double2* T, double scale, i64 jlbeg, i64 jlend) {
   const Geom& g = ctx->g;
-  if (!ctx->have_tm_z8) {
+  const bool two = zfused_p_two(ctx);
+  const int cr = two ? 4 : 8;  // real columns per group
+  if (!two && !ctx->have_tm_z8) {
     CKR(colfft_tensor_map(ctx, &ctx->tm_z8, (double*)T, ctx->njl, g.N3, ctx->icn * 16, ctx->njl * ctx->icn * 16, false, g.N3, 16));
     ctx->have_tm_z8 = true;
+  }
+  if (two && !ctx->have_tm_z4) {
+    CKR(colfft_tensor_map(ctx, &ctx->tm_z4, (double*)T, ctx->njl, g.N3, ctx->icn * 16, ctx->njl * ctx->icn * 16, false, g.N3, 8));
+    ctx->have_tm_z4 = true;
   }
   CKR(colfft_twiddles(ctx, &ctx->ztw, g.N3));
   ColFftArgs a;
   memset(&a, 0, sizeof a);
-  a.nicg = (int)((ctx->icn + 7) / 8);
+  a.nicg = (int)((ctx->icn + cr - 1) / cr);
   a.ngroups = (int)((jlend - jlbeg) * a.nicg);
   a.outer0 = (int)jlbeg;
   a.icn = (int)ctx->icn;
@@ -528,22 +581,32 @@ static int zfused_p_launch(nnpm_ctx* ctx, double2* T, double scale, i64 jlbeg, i
   a.tw = ctx->ztw;
   a.scale = scale;
   const i64 ncol = ctx->njl * ctx->icn;
-#define ZP(R1_, R2_)                                                                                                   \
+#define ZP(R1_, R2_, TWO_)                                                                                             \
   do {                                                                                                                 \
-    const size_t smem = (size_t)R1_ * R2_ * (8 * 16 + 16 + 8);                                                           \
-    CK(cudaFuncSetAttribute(k_zfused_p<R1_, R2_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    const size_t smem = (size_t)R1_ * R2_ * (8 * 16 + (TWO_ ? 2 : 1) * (16 + 8));                                        \
+    CK(cudaFuncSetAttribute(k_zfused_p<R1_, R2_, TWO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
     const int grid = a.ngroups < ctx->nsm ? a.ngroups : ctx->nsm;                                                       \
-    k_zfused_p<R1_, R2_><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(ctx->tm_z8, T, ncol, a);                   \
+    k_zfused_p<R1_, R2_, TWO_><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(TWO_ ? ctx->tm_z4 : ctx->tm_z8, T, ncol, a); \
     LAUNCHED(ctx);                                                                                                     \
     KCHECK();                                                                                                          \
     return NNPM_OK;                                                                                                    \
   } while (0)
-  switch (g.N3) {
-    case 64: ZP(8, 8);
-    case 128: ZP(16, 8);
-    case 256: ZP(16, 16);
-    case 512: ZP(32, 16);
-    case 1024: ZP(32, 32);
+  if (two) {
+    switch (g.N3 / 2) {
+      case 64: ZP(8, 8, true);
+      case 128: ZP(16, 8, true);
+      case 256: ZP(16, 16, true);
+      case 512: ZP(32, 16, true);
+      case 1024: ZP(32, 32, true);
+    }
+  } else {
+    switch (g.N3) {
+      case 64: ZP(8, 8, false);
+      case 128: ZP(16, 8, false);
+      case 256: ZP(16, 16, false);
+      case 512: ZP(32, 16, false);
+      case 1024: ZP(32, 32, false);
+    }
   }
 #undef ZP
   return fail(ctx, NNPM_ERR_STATE, "persistent fused z pass does not support N3 = %lld", (long long)g.N3);

@@ -199,7 +199,10 @@ static bool zfused_factor(i64 N, int* r1, int* r2) {
 }
 static bool zfused_supported(nnpm_ctx* ctx) {
   int a, b;
-  return ctx->R == 3 && zfused_factor(ctx->g.N3, &a, &b);
+  if (ctx->R != 3) return false;
+  if (zfused_factor(ctx->g.N3, &a, &b)) return true;
+  // N3 = 2 x a two-pass length (2048): only the persistent kernel has the radix-2 wrapper (k_zfused_p<.., TWO>)
+  return ctx->opt_zfused == 2 && !ctx->opt_colfft_z && ctx->g.N3 % 2 == 0 && zfused_factor(ctx->g.N3 / 2, &a, &b);
 }
 
 template <int R1, int R2, int C>

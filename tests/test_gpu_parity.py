@@ -167,6 +167,32 @@ def test_potential_tma_column_fft(lib_built, O, dims):
     assert nlinf(out[0], ref) < TOL
 
 
+@pytest.mark.parametrize("dims", [(12, 10, 128), (32, 16, 256), (8, 8, 512), (10, 4, 1024), (8, 4, 2048), (34, 6, 2048)])
+def test_potential_fused_z_pass_radix2_wrapper(lib_built, O, dims):
+    """N3 = 2 x (two-pass length): the persistent fused z pass with one radix-2 step around the two-pass engine
+    (even / odd bins as two half-length transforms, parities recombined by a warp shuffle).  N3 = 2048 (the fine
+    mesh of BASELINE config 5) always takes it; N3 <= 1024 through the "zsplit" hook.  Against the oracle and
+    the cuFFT-composed z path; icn is never a multiple of the 4-column group (clipped last group)."""
+    from noname_b200 import DevicePM
+    rng = np.random.default_rng(37)
+    shape = (dims[2], dims[1], dims[0])
+    rho = rng.random(shape)
+    ref = np.empty(shape)
+    O.compute_potential(ref, rho - rho.mean(), np.zeros((shape[0], shape[1], shape[2] // 2 + 1), dtype=np.complex128))
+    out = {}
+    for zf in (2, 0):
+        with DevicePM(dims, 1, rank=3) as dev:
+            dev.set_option("zfused", zf)
+            dev.set_option("zsplit", 1)
+            for rep in range(2):
+                dev.set_field("rho", rho)
+                dev.solve()
+                out[zf] = dev.get_field("phi")
+    assert nlinf(out[0], ref) < TOL
+    assert nlinf(out[2], ref) < TOL
+    assert nlinf(out[2], out[0]) < 1e-13
+
+
 def test_potential_ignores_mean(PM, O):
     """evolvePM subtracts mean(rho) (:768-769); the DC bin is zeroed (:501) so it must not matter."""
     rng = np.random.default_rng(4)
