@@ -117,3 +117,15 @@ def test_product_package_never_imports_the_oracle():
                 txt = open(os.path.join(dp, f), encoding="utf-8").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "pmref_" not in txt and "libpmref" not in txt, f
+
+
+def test_every_runtime_option_is_documented_in_the_header():
+    """nnpm_set_option's accepted names (the strcmp chain in nnpm.cu) == the names the header documents"""
+    cu = open(os.path.join(ROOT, "noname_b200", "csrc", "nnpm.cu"), encoding="utf-8").read()
+    body = cu[cu.index('extern "C" int nnpm_set_option'):]
+    accepted = set(re.findall(r'!strcmp\(name, "([a-z0-9_]+)"\)', body))
+    hdr = open(HEADER, encoding="utf-8").read()
+    doc = hdr[hdr.index("Runtime tuning knobs"):hdr.index("int nnpm_set_option")]
+    documented = set(re.findall(r'"([a-z0-9_]+)"', doc))
+    assert accepted, "no options parsed from nnpm.cu"
+    assert accepted == documented, f"undocumented: {sorted(accepted - documented)}; stale: {sorted(documented - accepted)}"
