@@ -424,6 +424,56 @@ def test_clustered_state_matches_oracle(lib_built, O, mode, variant):
         assert nlinf(dev.get_field("rho"), ref) < TOL
 
 
+@pytest.mark.parametrize("sort_every", [0, 1])
+def test_edge_positions_pileups_and_empty_input(lib_built, O, sort_every):
+    """Domain edge cases through the fused step, tiled (sorted) and global (unsorted) kernels alike:
+    coordinates exactly 0.0, 1.0 (make_periodic leaves it, ParticleMesh.jl:411: cell index N folds to 0),
+    the largest double below 1, a denormal; 300 particles on one point (every atomic of a warp on the same
+    cells); a context with zero particles."""
+    import itertools
+    from noname_b200 import DevicePM
+    dims = (64, 32, 32)
+    edge = [0.0, 1.0, np.nextafter(1.0, 0.0), 5e-324, 0.5]
+    pts = np.array(list(itertools.product(edge, repeat=3)))
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.random((2000, 3)), np.tile([[0.5, 0.5, 0.5]], (300, 1)),
+                        np.tile([[0.999, 0.999, 0.999]], (300, 1)), pts])
+    v = (rng.random(x.shape) - 0.5) * 0.02
+    m = 0.7
+    npart = len(x)
+    shape = (dims[2], dims[1], dims[0])
+    f = O.Fields(dims, npart, 3)
+    xr, vr = x.copy(), v.copy()
+    sc = (1.0, 1.01, 0.8, 1.02)
+    with DevicePM(dims, npart, rank=3, sort_every=sort_every) as dev:
+        dev.upload(x, v, m)
+        if sort_every:
+            dev.sort()
+        dev.deposit()
+        ref = np.zeros(shape)
+        xw = x.copy()
+        O.make_periodic(xw)
+        O.deposit(ref, xw, m, interpolation="cic")
+        rho = dev.get_field("rho")
+        assert nlinf(rho, ref) < TOL
+        assert rho.sum() == pytest.approx(m * npart, rel=1e-12)
+        for it in range(2):
+            O.step_comoving(f, xr, vr, m, 0.01, *sc)
+            st = dev.step_comoving(0.01, *sc)
+            assert st.n_halo_violations == 0
+        xg, vg = dev.download()
+    assert np.max(np.abs(xg - xr)) < 1e-12 and nlinf(vg, vr) < 1e-11
+    assert xg.min() >= 0.0 and xg.max() <= 1.0
+    # zero particles: the step runs, the fields are zero, the reductions report an empty set
+    with DevicePM(dims, 16, rank=3, sort_every=sort_every) as dev:
+        dev.upload(np.zeros((0, 3)), np.zeros((0, 3)), 1.0)
+        st = dev.step_comoving(0.01, *sc)
+        assert st.npart_local == 0 and st.max_abs_v == 0.0
+        assert not dev.get_field("phi").any()
+        xg, vg = dev.download()
+        assert xg.shape == (0, 3) and vg.shape == (0, 3)
+
+
 def test_sort_keeps_particles_and_restores_order(lib_built):
     from noname_b200 import DevicePM
     x, v = make_particles(21, 10000, 3)
