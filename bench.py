@@ -46,6 +46,31 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa(index):
+    """N > 1: keep this rank's host thread -- and with it the pages of the pinned e2e buffers it allocates -- on
+    the CPUs local to its GPU (sysfs local_cpulist of the GPU's PCI function).  Eight ranks left to float put
+    most staging buffers on one socket: the 8-GPU e2e was slower than the 4-GPU one.  Any failure is a no-op."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if part:
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return f"{bdf}: {len(cpus)} of {len(allowed)} CPUs"
+        return f"{bdf}: no narrower CPU set ({txt or 'empty'})"
+    except Exception as ex:  # noqa: BLE001 -- placement is an optimisation, never a failure
+        return f"not bound ({ex!r})"
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -183,6 +208,9 @@ def main():
     scalars.cosmo = cos.Cosmology(**COSMO)
     torch.cuda.set_device(local_rank)
     if world > 1:
+        numa = bind_to_gpu_numa(local_rank)
+        if os.environ.get("NNPM_VERBOSE"):
+            print(f"[bench] rank {rank}: host placement {numa}", file=sys.stderr)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.current_stream()
     peak, peak_src = peaks()
