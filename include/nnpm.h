@@ -47,7 +47,11 @@ typedef enum {
 
 /* ParticleDepositInterpolation / ParticleBackInterpolation = none | cic  (src/default.conf:32-33) */
 enum { NNPM_INTERP_NONE = 0, NNPM_INTERP_CIC = 1 };
-/* deposit accumulation: f64 atomics (default) or deterministic int64 fixed point */
+/* deposit accumulation.  ATOMIC (default): f64 reductions into the mesh; on tile-sorted particles the tile's
+ * contributions are first summed in shared memory as 64-bit fixed point (unit-mass weights, 2^-fixed_bits resolution)
+ * and converted to f64 at the flush, so results differ from a pure f64 sum by <= 2^-fixed_bits per contribution
+ * (inside the 1e-12 single-step budget).  FIXED: the mesh itself accumulates int64 fixed point -- bit-exact run to
+ * run, under any particle order and any slab decomposition. */
 enum { NNPM_DEPOSIT_ATOMIC = 0, NNPM_DEPOSIT_FIXED = 1 };
 /* fields for nnpm_get_field / nnpm_set_field */
 enum { NNPM_FIELD_RHO = 0, NNPM_FIELD_PHI = 1, NNPM_FIELD_ACC = 2, NNPM_FIELD_PA = 3 };
@@ -177,39 +181,33 @@ int64_t nnpm_device_bytes(const nnpm_ctx *ctx);
  * Overwrites the mesh (rho/phi).  box = (1,1,1), the only domain the reference tests. */
 int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, int32_t lenk);
 
-/* Runtime tuning knobs (new; no reference counterpart).  Unknown names -> NNPM_ERR_ARG.
- *   "fft3d"        1 = single cuFFT 3-D plan instead of 2-D + fused z pass (nranks == 1 only)
- *   "zfused"       2 = fused z-FFT * Green * z-iFFT kernel, persistent with TMA prefetch (default; N3 = 64..2048),
- *                  1 = the same with one CTA per column group and register loads, 0 = cuFFT z + Green kernel
+/* Runtime tuning knobs (new; no reference counterpart).  Unknown names -> NNPM_ERR_ARG.  The defaults are the
+ * fastest measured paths; the other values are the library / un-fused compositions the tests cross-check against.
+ *   "rowfft"       1 = own row-FFT kernels for the x passes (r2c / c2r, bulk-copy staged; default when N1/2 is
+ *                  64..1024), 0 = cuFFT batched 1-D plans
+ *   "colfft"       1 = TMA-staged column FFT for the y passes (default when N2 is 64..1024), 0 = cuFFT 2-D plans
+ *   "zfused"       3 = fused z-FFT * Green * z-iFFT kernel, persistent, next column group loaded by TMA during the
+ *                  whole transform (separate landing zone + half-size split exchange; default; N3 = 64..1024),
+ *                  2 = the same with one buffer (load overlaps the last pass only; the only form for N3 = 2048),
+ *                  0 = cuFFT z + Green kernel
+ *   "fft3d"        1 = single cuFFT 3-D plan instead of the passes above (nranks == 1 only)
  *   "tile_deposit" 1 = shared-memory tiled deposit on tile-sorted particles (default), 0 = global atomics
  *   "tile_push"    1 = push gathers phi from a shared-memory tile on sorted particles, 0 = L2 gather
  *   "bulk_flush"   1 = tiled deposit flushes its box with cp.reduce.async.bulk (default), 0 = per-cell atomics
- *   "colfft"       1 = TMA-staged column FFT for the y passes (default), 0 = cuFFT 2-D plans
- *   "pipeline"     nranks > 1: 1 = overlap the transposes with chunked transforms when the chunks are
- *                  large enough (default), 2 = always, 0 = never
- *   "push_tma"     1 = tiled push streams x, v through shared memory with cp.async.bulk (DMA warp)
- *   "colfft_z"     1 = TMA-staged fused z pass instead of the register-resident one, 2 = the same at two
- *                  CTAs per SM (both measured slower than the default at 1024^3)
- *   "peer_transpose" nranks > 1: 1 = copy-engine peer copies over NVLink (default), 2 = remote-store
- *                  kernels, 0 = grouped ncclSend/ncclRecv
  *   "l2pf_push"    1 = each CTA of the tiled push pulls its work item's x, v runs into L2 with one
- *                  cp.async.bulk.prefetch.L2 per array before it stages its phi box (default); n > 1 = the item n
- *                  CTAs ahead instead (measured slower); 0 = off
+ *                  cp.async.bulk.prefetch.L2 per array before it stages its phi box (default), 0 = off
  *   "l2pf_deposit" 1 = the same in the tiled deposit (default), 0 = off
- *   "deposit_unroll" 2 = the tiled deposit issues the loads of two particles before scattering either (default), 1 = one
- *   "push_depth"   2 = the tiled push keeps two particles' loads in flight ahead of the one processed (three register
- *                  sets; measured equal to the default depth 1)
- *   "push_persist" 1 = persistent tiled push: 2 resident CTAs per SM walk the work list with double-buffered
- *                  phi boxes (next box staged by TMA while the current one is gathered from), 2 / 3 = the same
- *                  with 320 / 384 threads per CTA (96 / 80 registers); 0 = one CTA per work item (default:
- *                  measured equal at best)
- *   "push_flags"   persistent push only, bit mask: 4 = dynamic schedule (work indices from a global counter),
- *                  8 = bulk L2 prefetch of the whole next item, 1 = skip the proxy fence before a TMA re-fill of a
- *                  box buffer (experiment), 2 = no per-line L2 prefetch; default 12
- *   "push_grid"    CTAs of the persistent push (0 = 2 * SMs - 1); small values make every CTA walk many items
+ *   "fuse_transpose" nranks > 1: 1 = the slab transposes are fused into the transform kernels (default): the forward
+ *                  y pass stores each column group straight into the owning ranks' transposed spectra through
+ *                  per-peer TMA tensor maps, the z pass stores its rows straight into the owning ranks' slabs --
+ *                  NVLink peer memory, no separate all-to-all pass; 0 = separate transposes ("peer_transpose")
+ *   "peer_transpose" un-fused transposes: 1 = copy-engine peer copies over NVLink (default), 0 = grouped
+ *                  ncclSend/ncclRecv (also the fallback when CUDA IPC mapping of the peers' meshes fails)
+ *   "pipeline"     un-fused copy-engine transposes: 1 = overlap them with chunked transforms when the chunks are
+ *                  large enough (default), 2 = always, 0 = never
  *   "zsplit"       1 = run N3 in 128..1024 through the radix-2 wrapper of the persistent fused z pass (the path
  *                  N3 = 2048 always takes); test hook
- *   "push_minb", "zcols", "cfrun_y", "cfrun_z"  launch-shape experiments */
+ *   "cfrun_y"      launch-shape experiment of the y pass */
 int nnpm_set_option(nnpm_ctx *ctx, const char *name, double value);
 
 #ifdef __cplusplus

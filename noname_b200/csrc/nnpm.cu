@@ -51,6 +51,7 @@ struct nnpm_ctx {
   i64 cap, np;
   double m;
   bool ids_dirty;      // particle order != original order
+  i64 first_id;        // global index of the first uploaded particle (ids = first_id + upload position)
 
   // lazily allocated parity buffers
   double* acc;
@@ -65,7 +66,6 @@ struct nnpm_ctx {
   // sort scratch
   uint32_t *hist, *bsum, *bsum2, *skey, *srnk;
   uint32_t *wcnt, *wtile, *wbeg;  // work list of the tiled kernels (k_work_count / k_work_fill)
-  unsigned* wctr;                 // work counter of the persistent push's dynamic schedule
   i64 wcap;
   TileGeom tg;
   i64 ntiles;
@@ -82,7 +82,7 @@ struct nnpm_ctx {
   // cuFFT
   cufftHandle plan2f, plan2b, planz, plan3f, plan3b;
   bool have2, havez, have3;
-  int opt_fft3d, opt_zfused, opt_tile_deposit, opt_tile_push, opt_push_minb, opt_bulk_flush;
+  int opt_fft3d, opt_zfused, opt_tile_deposit, opt_tile_push, opt_bulk_flush;
   void* fftwork;
   size_t fftwork_bytes;
 
@@ -107,24 +107,23 @@ struct nnpm_ctx {
   i64 last_migrated;
   double* pk_buf;
   double2* ztw;  // z-FFT twiddles W_N3^m
-  int opt_zcols;
   // NVLink peer-memory transposes (nranks > 1): every rank's mesh / meshT mapped through CUDA IPC
   double* peer_mesh[64];
   double* peer_meshT[64];
   bool peer_ok;
-  int opt_peer;   // 0 = NCCL send/recv, 1 = copy-engine peer copies (default), 2 = remote-store kernels
+  int opt_peer;   // un-fused transposes: 0 = NCCL send/recv, 1 = copy-engine peer copies (default)
   int* bar_buf;
   // TMA-staged column FFT engine (nnpm_colfft.cuh)
-  CUtensorMap tm_y, tm_z, tm_z8, tm_z4;
-  bool have_tm_y, have_tm_z, have_tm_z8, have_tm_z4, have1;
+  CUtensorMap tm_y, tm_z8, tm_z4;
+  bool have_tm_y, have_tm_z8, have_tm_z4, have1;
   int opt_zsplit;  // test hook: run N3 <= 1024 through the radix-2 wrapper of the persistent fused z pass
   double2* ytw;
   cufftHandle plan1f, plan1b;  // batched 1-D x transforms (r2c / c2r) over the owned rows
-  cufftHandle plan1fc;         // the same over one chunk of planes (pipelined multi-GPU solve)
-  bool have1c;
   int opt_pipeline;
   cudaEvent_t ev_chunk[4];
-  int opt_l2pf_push, opt_l2pf_deposit, opt_push_depth, opt_push_tma, opt_push_persist, opt_push_grid, opt_push_flags, opt_deposit_unroll, opt_colfft, opt_colfft_z, opt_cfrun_y, opt_cfrun_z, nsm;
+  int opt_l2pf_push, opt_l2pf_deposit, opt_colfft, opt_cfrun_y, opt_rowfft, opt_fuse_transpose, nsm;
+  double2 *xtwM, *xtwN;         // x-pass twiddles W_M^m, W_N^k (nnpm_rowfft.cuh)
+  struct PeerMaps* peer_maps;   // tensor maps over every rank's transposed spectrum (fused forward transpose)
   cudaStream_t st2[4];    // side streams: the blocks of a transpose go out on several copy engines at once
   cudaEvent_t ev_fork, ev_join[4];
 };
@@ -180,6 +179,7 @@ static int dalloc(nnpm_ctx* ctx, T** p, size_t count) {
 #include "nnpm_comm.cuh"
 #include "nnpm_zfft.cuh"
 #include "nnpm_colfft.cuh"
+#include "nnpm_rowfft.cuh"
 
 // ------------------------------------------------------------------------------------------
 // lifetime
@@ -203,9 +203,9 @@ static int grow_fftwork(nnpm_ctx* ctx, size_t need) {
   ctx->fftwork = q;
   ctx->fftwork_bytes = need;
   ctx->dev_bytes += need;
-  cufftHandle hs[8] = {ctx->plan2f, ctx->plan2b, ctx->planz, ctx->plan3f, ctx->plan3b, ctx->plan1f, ctx->plan1b, ctx->plan1fc};
-  bool on[8] = {ctx->have2, ctx->have2, ctx->havez, ctx->have3, ctx->have3, ctx->have1, ctx->have1, ctx->have1c};
-  for (int i = 0; i < 8; i++)
+  cufftHandle hs[7] = {ctx->plan2f, ctx->plan2b, ctx->planz, ctx->plan3f, ctx->plan3b, ctx->plan1f, ctx->plan1b};
+  bool on[7] = {ctx->have2, ctx->have2, ctx->havez, ctx->have3, ctx->have3, ctx->have1, ctx->have1};
+  for (int i = 0; i < 7; i++)
     if (on[i]) CKF(cufftSetWorkArea(hs[i], ctx->fftwork));
   return NNPM_OK;
 }
@@ -367,26 +367,28 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->acc_valid = c->pa_valid = false;
   c->stage = nullptr; c->stage_elems = 0;
   c->hist = c->bsum = c->bsum2 = c->skey = c->srnk = nullptr;
-  c->wcnt = c->wtile = c->wbeg = nullptr; c->wcap = 0; c->wctr = nullptr;
+  c->wcnt = c->wtile = c->wbeg = nullptr; c->wcap = 0;
   c->have2 = c->havez = c->have3 = false;
   c->have_tmap = false;
-  c->opt_fft3d = 0; c->opt_zfused = 2; c->opt_tile_deposit = 1; c->opt_tile_push = 1; c->opt_push_minb = 2; c->opt_bulk_flush = 1;
+  c->opt_fft3d = 0; c->opt_zfused = 3; c->opt_tile_deposit = 1; c->opt_tile_push = 1; c->opt_bulk_flush = 1;
   c->fftwork = nullptr; c->fftwork_bytes = 0;
   c->step_count = 0; c->launches = 0;
   c->nccl = nullptr; c->comm = nullptr;
   c->mig_send = c->mig_recv = nullptr; c->mig_cap = 0; c->mig_holes = nullptr; c->mig_cnt = nullptr; c->h_cnt = nullptr;
   c->last_migrated = 0;
   c->pk_buf = nullptr;
-  c->ztw = nullptr; c->opt_zcols = 8;
+  c->ztw = nullptr;
   for (int i = 0; i < 64; i++) { c->peer_mesh[i] = nullptr; c->peer_meshT[i] = nullptr; }
   c->peer_ok = false; c->opt_peer = 1; c->bar_buf = nullptr;
   c->ev_fork = nullptr;
   for (int i = 0; i < 4; i++) { c->st2[i] = nullptr; c->ev_join[i] = nullptr; }
-  c->have1c = false; c->opt_pipeline = 1;
+  c->opt_pipeline = 1;
   for (int i = 0; i < 4; i++) c->ev_chunk[i] = nullptr;
-  c->have_tm_y = c->have_tm_z = c->have_tm_z8 = c->have_tm_z4 = c->have1 = false; c->opt_zsplit = 0; c->ytw = nullptr; c->opt_push_tma = 0; c->opt_push_persist = 0; c->opt_push_grid = 0; c->opt_push_flags = 12; c->opt_push_depth = 1; c->opt_l2pf_push = 1; c->opt_l2pf_deposit = 1; c->opt_deposit_unroll = 2; c->opt_colfft = 1; c->opt_colfft_z = 0; c->opt_cfrun_y = 1; c->opt_cfrun_z = 1; c->nsm = 148;
+  c->have_tm_y = c->have_tm_z8 = c->have_tm_z4 = c->have1 = false; c->opt_zsplit = 0; c->ytw = nullptr;
+  c->opt_l2pf_push = 1; c->opt_l2pf_deposit = 1; c->opt_colfft = 1; c->opt_cfrun_y = 1; c->opt_rowfft = 1; c->opt_fuse_transpose = 1;
+  c->xtwM = c->xtwN = nullptr; c->peer_maps = nullptr; c->nsm = 148;
   c->mig_lo = nullptr; c->ghost_rx = nullptr; c->red_buf = nullptr;
-  c->np = 0; c->m = 0.0; c->ids_dirty = false; c->field_state = 0;
+  c->np = 0; c->m = 0.0; c->ids_dirty = false; c->field_state = 0; c->first_id = 0;
   c->own_stream = false;
   c->h_red = nullptr;
   for (int i = 0; i < 16; i++) c->ev[i] = nullptr;
@@ -419,7 +421,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   CKB(CKR(dalloc(c, &c->ids, (size_t)c->cap)));
   CKB(CKR(dalloc(c, &c->d_red, 8)));
   CKB(CK(cudaHostAlloc((void**)&c->h_red, 8 * sizeof(i64), cudaHostAllocDefault)));
-  CKB(CK(cudaHostAlloc((void**)&c->h_cnt, 24 * 64 * sizeof(i64), cudaHostAllocDefault)));
+  CKB(CK(cudaHostAlloc((void**)&c->h_cnt, 72 * 64 * sizeof(i64), cudaHostAllocDefault)));  // MC_REC * 64 (nnpm_comm.cuh)
   {
     std::vector<double> t1, t2, t3;
     sin2_table(t1, N1, false, false);
@@ -458,11 +460,12 @@ extern "C" int nnpm_destroy(nnpm_ctx* ctx) {
   comm_destroy(ctx);
   if (ctx->have2) { cufftDestroy(ctx->plan2f); cufftDestroy(ctx->plan2b); }
   if (ctx->have1) { cufftDestroy(ctx->plan1f); cufftDestroy(ctx->plan1b); }
-  if (ctx->have1c) cufftDestroy(ctx->plan1fc);
   for (int i = 0; i < 4; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
   if (ctx->havez) cufftDestroy(ctx->planz);
   if (ctx->have3) { cufftDestroy(ctx->plan3f); cufftDestroy(ctx->plan3b); }
   for (void* p : ctx->allocs) cudaFree(p);
+  if (ctx->fftwork) cudaFree(ctx->fftwork);  // allocated outside ctx->allocs (grow_fftwork)
+  delete ctx->peer_maps;
   if (ctx->h_red) cudaFreeHost(ctx->h_red);
   if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
   for (int i = 0; i < 16; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -539,6 +542,7 @@ extern "C" int nnpm_upload_particles(nnpm_ctx* ctx, const double* x_aos, const d
   if (n) { k_iota_u32<<<nblk(n, 256), 256, 0, ctx->st>>>(ctx->ids, n, (u64)first_id); LAUNCHED(ctx); KCHECK(); }
   ctx->np = n;
   ctx->m = m;
+  ctx->first_id = first_id;
   ctx->sorted_np = 0;
   ctx->ids_dirty = false;
   ctx->acc_valid = ctx->pa_valid = false;
@@ -577,13 +581,11 @@ extern "C" int nnpm_download_particles(nnpm_ctx* ctx, double* x_aos, double* v_a
   CKR(ensure_stage(ctx));
   const i64 np = ctx->np;
   if (!ids_out && ctx->P == 1 && ctx->ids_dirty && np) {
-    // restore the reference's particle order: out[id[n]] = in[n]  (ids are a permutation of 0..np-1)
-    CKR(ensure_spare(ctx));
-    CK(cudaMemcpyAsync(ctx->ids_spare, ctx->ids, (size_t)np * 4, cudaMemcpyDeviceToDevice, ctx->st));
-    uint32_t* dest = ctx->ids_spare;
-    // permute_all swaps ids_spare; keep the destination list in the sort scratch instead
+    // restore the reference's particle order: out[id[n] - first_id] = in[n]  (ids are a permutation of
+    // first_id .. first_id + np - 1); permute_all rotates ids_spare, so the destination list lives in the sort scratch
     if (!ctx->skey) CKR(dalloc(ctx, &ctx->skey, (size_t)ctx->cap));
-    CK(cudaMemcpyAsync(ctx->skey, dest, (size_t)np * 4, cudaMemcpyDeviceToDevice, ctx->st));
+    k_ids_to_dest<<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->skey, ctx->ids, (uint32_t)ctx->first_id, np);
+    LAUNCHED(ctx);
     CKR(permute_all(ctx, ctx->skey));
     ctx->ids_dirty = false;
     ctx->sorted_np = 0;
@@ -666,6 +668,7 @@ extern "C" int nnpm_init_synthetic(nnpm_ctx* ctx, int kind, const int64_t pdims[
   }
   ctx->np = per;
   ctx->m = m;
+  ctx->first_id = 0;
   ctx->sorted_np = 0;
   ctx->ids_dirty = ctx->P > 1;
   ctx->acc_valid = ctx->pa_valid = false;
@@ -777,7 +780,7 @@ static void launch_deposit(nnpm_ctx* ctx, bool pre, double c0, u64* viol, i64 ba
   const bool stragglers = base < 0;  // the tiled kernel's device-side list instead of a range
   const uint32_t* list = stragglers ? ctx->srnk : nullptr;
   const u64* lcount = (const u64*)(ctx->d_red + 5);
-  const unsigned grid = stragglers ? 148 * 4 : nblk(cnt, 256);
+  const unsigned grid = stragglers ? (unsigned)ctx->nsm * 4 : nblk(cnt, 256);
   if (stragglers) q = ctx->pp;
   if (pre) k_deposit<RANK, INTERP, FIXED, true><<<grid, 256, 0, ctx->st>>>(q, cnt, list, lcount, c0, ctx->g, ctx->mesh, ctx->m, fscale, viol);
   else k_deposit<RANK, INTERP, FIXED, false><<<grid, 256, 0, ctx->st>>>(q, cnt, list, lcount, c0, ctx->g, ctx->mesh, ctx->m, fscale, viol);
@@ -801,12 +804,7 @@ static int do_deposit(nnpm_ctx* ctx, bool pre, double c0) {
     const WorkList wl = {ctx->wtile, ctx->wbeg, ctx->wcnt + ctx->ntiles};
     const unsigned wgrid = (unsigned)(ctx->ntiles + ctx->sorted_np / NNPM_CHUNK + 1);  // >= number of chunks
 #define DT(RK, FX, PR)                                                                                                   \
-  do {                                                                                                                   \
-    if (ctx->opt_deposit_unroll == 2)                                                                                    \
-      k_deposit_tile<RK, FX, PR, 2><<<wgrid, 256, 0, ctx->st>>>(ctx->pp, covered, c0, ctx->g, ctx->tg, wl, ctx->hist, ctx->mesh, ctx->m, fscale, ctx->srnk, (u64*)(ctx->d_red + 5), bulk, ctx->opt_l2pf_deposit); \
-    else                                                                                                                 \
-      k_deposit_tile<RK, FX, PR, 1><<<wgrid, 256, 0, ctx->st>>>(ctx->pp, covered, c0, ctx->g, ctx->tg, wl, ctx->hist, ctx->mesh, ctx->m, fscale, ctx->srnk, (u64*)(ctx->d_red + 5), bulk, ctx->opt_l2pf_deposit); \
-  } while (0)
+  k_deposit_tile<RK, FX, PR, 2><<<wgrid, 256, 0, ctx->st>>>(ctx->pp, covered, c0, ctx->g, ctx->tg, wl, ctx->hist, ctx->mesh, ctx->m, fscale, ctx->srnk, (u64*)(ctx->d_red + 5), bulk, ctx->opt_l2pf_deposit)
     if (ctx->R == 3) { if (fixed) { if (pre) DT(3, true, true); else DT(3, true, false); } else { if (pre) DT(3, false, true); else DT(3, false, false); } }
     else { if (fixed) { if (pre) DT(2, true, true); else DT(2, true, false); } else { if (pre) DT(2, false, true); else DT(2, false, false); } }
 #undef DT
@@ -848,9 +846,27 @@ extern "C" int nnpm_deposit(nnpm_ctx* ctx) {
   return do_deposit(ctx, false, 0.0);
 }
 
+// x pass over (a sub-range of) the owned planes: own row-FFT kernels, or cuFFT's batched 1-D plans
+static int fft_x(nnpm_ctx* ctx, bool inverse) {
+  const Geom& g = ctx->g;
+  double* own = ctx->mesh + g.plane * g.glo;
+  if (ctx->opt_rowfft && rowfft_supported_n(g.N1)) return rowfft_x(ctx, inverse);
+  if (inverse) CKF(cufftExecZ2D(ctx->plan1b, (cufftDoubleComplex*)own, own));
+  else CKF(cufftExecD2Z(ctx->plan1f, own, (cufftDoubleComplex*)own));
+  LAUNCHED(ctx);
+  return NNPM_OK;
+}
+
+// the fused z pass [z-FFT, Green's function, z-iFFT] over the local rows [jlbeg, jlend) of T
+static int fft_z_green(nnpm_ctx* ctx, double2* T, double scale, i64 jlbeg, i64 jlend, const ZDst* dst) {
+  if (ctx->opt_zfused == 3 && !zfused_p_two(ctx)) return zfused_s_launch(ctx, T, scale, jlbeg, jlend, dst);
+  return zfused_p_launch(ctx, T, scale, jlbeg, jlend, dst);
+}
+
 // forward transform of the owned planes, in place: rho -> spectrum.  Returns the spectrum
 // pointer T with layout [k][jl][ic] (jl = local j range of this rank; all of j when P == 1).
-static int fft_forward(nnpm_ctx* ctx, double2** Tout, bool z_too, cudaEvent_t* comm_t) {
+// fuse (nranks > 1): the y pass stores straight into the peers' transposed spectra (no separate all-to-all).
+static int fft_forward(nnpm_ctx* ctx, double2** Tout, bool z_too, cudaEvent_t* comm_t, bool fuse) {
   const Geom& g = ctx->g;
   double* own = ctx->mesh + g.plane * g.glo;
   if (ctx->opt_fft3d && ctx->P == 1 && g.N3 > 1) {
@@ -861,9 +877,8 @@ static int fft_forward(nnpm_ctx* ctx, double2** Tout, bool z_too, cudaEvent_t* c
     return NNPM_OK;
   }
   if (ctx->opt_colfft && colfft_supported_n(g.N2)) {
-    CKF(cufftExecD2Z(ctx->plan1f, own, (cufftDoubleComplex*)own));
-    LAUNCHED(ctx);
-    CKR(colfft_y(ctx, false));
+    CKR(fft_x(ctx, false));
+    CKR(colfft_y(ctx, false, 0, -1, fuse));
   } else {
     CKF(cufftExecD2Z(ctx->plan2f, own, (cufftDoubleComplex*)own));
     LAUNCHED(ctx);
@@ -871,7 +886,8 @@ static int fft_forward(nnpm_ctx* ctx, double2** Tout, bool z_too, cudaEvent_t* c
   double2* T = (double2*)own;
   if (ctx->P > 1) {
     if (comm_t) CK(cudaEventRecord(comm_t[0], ctx->st));
-    CKR(comm_transpose_fwd(ctx));
+    if (fuse) CKR(comm_barrier(ctx));   // every rank's remote stores have landed
+    else CKR(comm_transpose_fwd(ctx));
     if (comm_t) CK(cudaEventRecord(comm_t[1], ctx->st));
     T = (double2*)ctx->meshT;
   }
@@ -880,7 +896,8 @@ static int fft_forward(nnpm_ctx* ctx, double2** Tout, bool z_too, cudaEvent_t* c
   return NNPM_OK;
 }
 
-static int fft_inverse(nnpm_ctx* ctx, bool z_too, cudaEvent_t* comm_t) {
+// fused_bwd: the z pass already stored its output into the owners' slabs; only the barrier remains
+static int fft_inverse(nnpm_ctx* ctx, bool z_too, cudaEvent_t* comm_t, bool fused_bwd) {
   const Geom& g = ctx->g;
   double* own = ctx->mesh + g.plane * g.glo;
   if (ctx->opt_fft3d && ctx->P == 1 && g.N3 > 1) {
@@ -892,13 +909,13 @@ static int fft_inverse(nnpm_ctx* ctx, bool z_too, cudaEvent_t* comm_t) {
   if (z_too && ctx->havez) { CKF(cufftExecZ2Z(ctx->planz, (cufftDoubleComplex*)T, (cufftDoubleComplex*)T, CUFFT_INVERSE)); LAUNCHED(ctx); }
   if (ctx->P > 1) {
     if (comm_t) CK(cudaEventRecord(comm_t[2], ctx->st));
-    CKR(comm_transpose_bwd(ctx));
+    if (fused_bwd) CKR(comm_barrier(ctx));
+    else CKR(comm_transpose_bwd(ctx));
     if (comm_t) CK(cudaEventRecord(comm_t[3], ctx->st));
   }
   if (ctx->opt_colfft && colfft_supported_n(g.N2)) {
     CKR(colfft_y(ctx, true));
-    CKF(cufftExecZ2D(ctx->plan1b, (cufftDoubleComplex*)own, own));
-    LAUNCHED(ctx);
+    CKR(fft_x(ctx, true));
   } else {
     CKF(cufftExecZ2D(ctx->plan2b, (cufftDoubleComplex*)own, own));
     LAUNCHED(ctx);
@@ -906,30 +923,18 @@ static int fft_inverse(nnpm_ctx* ctx, bool z_too, cudaEvent_t* comm_t) {
   return NNPM_OK;
 }
 
-// Multi-GPU solve with the NVLink transposes overlapped with the transforms: the owned planes are
-// transformed in NCH chunks, and as soon as a chunk's 2-D transform is done its block of the forward
-// transpose goes out on the copy engines (side streams) while the next chunk is computed; the fused
-// z pass is chunked over jl the same way for the backward transpose.  Only the last chunk's copies
-// (and the barrier) remain exposed.
+// Un-fused multi-GPU solve with the copy-engine transposes overlapped with the transforms ("fuse_transpose" = 0,
+// "pipeline" >= 1): the owned planes are transformed in NCH chunks, and as soon as a chunk's 2-D transform is done its
+// block of the forward transpose goes out on the copy engines (side streams) while the next chunk is computed; the
+// fused z pass is chunked over jl the same way for the backward transpose.
 static int do_solve_pipelined(nnpm_ctx* ctx, cudaEvent_t* ev, double scale) {
   const Geom& g = ctx->g;
   const int NCH = 4;
-  double* own = ctx->mesh + g.plane * g.glo;
   const i64 pc = g.nzl / NCH, jc = ctx->njl / NCH;
-  if (!ctx->have1c) {
-    size_t ws = 0;
-    long long n1[1] = {g.N1};
-    long long e1[1] = {g.rowp}, e2[1] = {ctx->icn};
-    CKR(new_plan(ctx, &ctx->plan1fc, 1, n1, e1, 1, g.rowp, e2, 1, ctx->icn, CUFFT_D2Z, g.N2 * pc, &ws));
-    ctx->have1c = true;
-    if (ws > ctx->fftwork_bytes) CKR(grow_fftwork(ctx, ws));
-    CKF(cufftSetWorkArea(ctx->plan1fc, ctx->fftwork));
+  if (!ctx->ev_chunk[0])
     for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
-  }
   for (int c = 0; c < NCH; c++) {
-    double* pl = own + g.plane * pc * c;
-    CKF(cufftExecD2Z(ctx->plan1fc, pl, (cufftDoubleComplex*)pl));
-    LAUNCHED(ctx);
+    CKR(rowfft_x(ctx, false, pc * c, pc));
     CKR(colfft_y(ctx, false, pc * c, pc));
     CK(cudaEventRecord(ctx->ev_chunk[c], ctx->st));
     CKR(comm_chunk_ce(ctx, true, c, NCH, ctx->ev_chunk[c]));
@@ -937,10 +942,8 @@ static int do_solve_pipelined(nnpm_ctx* ctx, cudaEvent_t* ev, double scale) {
   if (ev) CK(cudaEventRecord(ev[0], ctx->st));
   CKR(comm_join_barrier(ctx));
   if (ev) { CK(cudaEventRecord(ev[1], ctx->st)); CK(cudaEventRecord(ev[4], ctx->st)); }
-  const i64 cols = jc * ctx->icn;
   for (int c = 0; c < NCH; c++) {
-    if (ctx->opt_zfused == 2) CKR(zfused_p_launch(ctx, (double2*)ctx->meshT, scale, jc * c, jc * (c + 1)));
-    else CKR(zfused_launch(ctx, (double2*)ctx->meshT, scale, cols * c, cols * (c + 1)));
+    CKR(fft_z_green(ctx, (double2*)ctx->meshT, scale, jc * c, jc * (c + 1), nullptr));
     CK(cudaEventRecord(ctx->ev_chunk[c], ctx->st));
     CKR(comm_chunk_ce(ctx, false, c, NCH, ctx->ev_chunk[c]));
   }
@@ -948,25 +951,33 @@ static int do_solve_pipelined(nnpm_ctx* ctx, cudaEvent_t* ev, double scale) {
   CKR(comm_join_barrier(ctx));
   if (ev) CK(cudaEventRecord(ev[3], ctx->st));
   CKR(colfft_y(ctx, true));
-  CKF(cufftExecZ2D(ctx->plan1b, (cufftDoubleComplex*)own, own));
-  LAUNCHED(ctx);
+  CKR(fft_x(ctx, true));
   return NNPM_OK;
 }
 
 // compute_potential, ParticleMesh.jl:417-505: rho (in the mesh) -> phi (in the mesh).
-// ev (optional, 8 events): [0..3] around the transposes, [4],[5] around the z pass.
+// ev (optional, 8 events): [0..3] around the transposes (fused: around the barriers that close them), [4],[5]
+// around the z pass.
 static int do_solve(nnpm_ctx* ctx, cudaEvent_t* ev) {
   const Geom& g = ctx->g;
   const double scale = 1.0 / ((double)g.N1 * (double)g.N2 * (double)g.N3) * 1 / ((double)g.N1 * (double)g.N1);
   const bool fft3d = ctx->opt_fft3d && ctx->P == 1 && g.N3 > 1;
   const bool fusedz = !fft3d && ctx->opt_zfused && g.N3 > 1 && zfused_supported(ctx);
-  // chunking pays only while a chunk's copy to one peer stays large (measured at 1024^3: P = 2, 537 MB
-  // per copy: solve 17.5 -> 15.5 ms; P = 8, 34 MB per copy: 6.3 -> 7.0 ms); "pipeline" = 2 forces it
+  const bool ycol = ctx->opt_colfft && colfft_supported_n(g.N2);
+  if (ctx->P > 1) NEED_COMM();
+  // NVLink transposes fused into the transform kernels: forward into the y pass' tensor stores (needs the TMA
+  // column engine), backward into the z pass' register stores (needs the fused z pass and a power-of-two slab)
+  ZDst zd;
+  const bool fuse = ctx->P > 1 && ctx->opt_fuse_transpose && ctx->peer_ok && ctx->P <= 8;
+  const bool fuse_fwd = fuse && ycol;
+  const bool fuse_bwd = fuse && fusedz && zdst_peers(ctx, &zd);
+  if (fuse_fwd) CKR(colfft_peer_maps(ctx));
+  // chunked copy-engine pipeline (un-fused path only): pays while a chunk's copy to one peer stays large (measured at
+  // 1024^3 in round 1: P = 2, 537 MB per copy: solve 17.5 -> 15.5 ms; P = 8, 34 MB per copy: 6.3 -> 7.0 ms)
   const double chunk_copy_mb = (double)g.nzl * ctx->njl * ctx->icn * 16.0 / 4.0 / 1048576.0;
   const bool pipe = ctx->opt_pipeline == 2 || (ctx->opt_pipeline == 1 && chunk_copy_mb >= 256.0);
-  if (ctx->P > 1 && pipe && ctx->peer_ok && ctx->opt_peer == 1 && fusedz && !ctx->opt_colfft_z && ctx->opt_colfft &&
-      colfft_supported_n(g.N2) && g.nzl % 4 == 0 && ctx->njl % 4 == 0) {
-    NEED_COMM();
+  if (ctx->P > 1 && !fuse && pipe && ctx->peer_ok && ctx->opt_peer == 1 && fusedz && ycol && rowfft_supported_n(g.N1) &&
+      g.nzl % 4 == 0 && ctx->njl % 4 == 0) {
     CKR(do_solve_pipelined(ctx, ev, scale));
     CKR(comm_fill_phi_ghosts(ctx));
     ctx->field_state = 2;
@@ -974,14 +985,10 @@ static int do_solve(nnpm_ctx* ctx, cudaEvent_t* ev) {
     return NNPM_OK;
   }
   double2* T = nullptr;
-  CKR(fft_forward(ctx, &T, !fusedz, ev));
+  CKR(fft_forward(ctx, &T, !fusedz, ev, fuse_fwd));
   if (ev) CK(cudaEventRecord(ev[4], ctx->st));
   if (fusedz) {
-    // measured at 1024^3: the register-resident k_zfused (128-byte rows, exact DRAM traffic) 7.0 ms;
-    // the TMA-staged variant (64-byte rows, 4 warps per SM) 7.6 ms -> k_zfused is the default
-    if (ctx->opt_colfft_z) CKR(colfft_z_green(ctx, T, scale));
-    else if (ctx->opt_zfused == 2) CKR(zfused_p_launch(ctx, T, scale, 0, ctx->njl));
-    else CKR(zfused_launch(ctx, T, scale));
+    CKR(fft_z_green(ctx, T, scale, 0, ctx->njl, fuse_bwd ? &zd : nullptr));
   } else {
     dim3 grid(nblk(ctx->icn, 128), (unsigned)ctx->njl, (unsigned)(g.N3 < 64 ? g.N3 : 64));
     k_green<<<grid, 128, 0, ctx->st>>>(T, ctx->icn, ctx->njl, ctx->njl * ctx->r, g.N3, ctx->s1, ctx->s2, ctx->s3, ctx->R == 3, scale);
@@ -989,7 +996,7 @@ static int do_solve(nnpm_ctx* ctx, cudaEvent_t* ev) {
     KCHECK();
   }
   if (ev && fusedz) CK(cudaEventRecord(ev[5], ctx->st));
-  CKR(fft_inverse(ctx, !fusedz, ev));
+  CKR(fft_inverse(ctx, !fusedz, ev, fuse_bwd));
   if (ev && !fusedz) CK(cudaEventRecord(ev[5], ctx->st));
   if (ctx->P > 1) CKR(comm_fill_phi_ghosts(ctx));
   ctx->field_state = 2;
@@ -1127,11 +1134,8 @@ static int launch_push(nnpm_ctx* ctx, bool comoving, const PushParams& pp) {
   u64* viol = (u64*)(ctx->d_red + 3);
   u64* slow_count = (u64*)(ctx->d_red + 4);
   auto global_push = [&](i64 base, i64 count, const uint32_t* list, unsigned grid) {
-#define LP(CM, MB) k_push<RANK, INTERP, CM, MB><<<grid, 256, 0, ctx->st>>>(ctx->pp, base, count, list, slow_count, ctx->g, ctx->mesh, pp, ctx->d_red, viol)
-    if (ctx->opt_push_minb >= 4) { if (comoving) LP(true, 4); else LP(false, 4); }
-    else if (ctx->opt_push_minb == 3) { if (comoving) LP(true, 3); else LP(false, 3); }
-    else { if (comoving) LP(true, 2); else LP(false, 2); }
-#undef LP
+    if (comoving) k_push<RANK, INTERP, true><<<grid, 256, 0, ctx->st>>>(ctx->pp, base, count, list, slow_count, ctx->g, ctx->mesh, pp, ctx->d_red, viol);
+    else k_push<RANK, INTERP, false><<<grid, 256, 0, ctx->st>>>(ctx->pp, base, count, list, slow_count, ctx->g, ctx->mesh, pp, ctx->d_red, viol);
     LAUNCHED(ctx);
   };
   const bool tiled = INTERP == 1 && ctx->opt_tile_push && ctx->sorted_np > 0 && !ctx->cfg.bugcompat_interp_z;
@@ -1140,56 +1144,23 @@ static int launch_push(nnpm_ctx* ctx, bool comoving, const PushParams& pp) {
     KCHECK();
     return NNPM_OK;
   }
+  // one CTA per work item, phi box staged by TMA, x / v by register loads behind a bulk L2 prefetch.  The variants
+  // measured slower in round 1 (DMA-warp particle streams, persistent double-buffered boxes, deeper register
+  // prefetch; profiles/r01_probe_logs) are no longer compiled.
   const size_t smem = (size_t)NNPM_BX * NNPM_BY * (RANK == 3 ? NNPM_BZ : 1) * sizeof(double);
   const i64 covered = ctx->sorted_np < np ? ctx->sorted_np : np;
   const WorkList wl = {ctx->wtile, ctx->wbeg, ctx->wcnt + ctx->ntiles};
   const unsigned wgrid = (unsigned)(ctx->ntiles + ctx->sorted_np / NNPM_CHUNK + 1);  // >= number of chunks
-  // measured at 1024^3 (B200): register-load k_push_tile 25.3 ms; bulk-copy k_push_tma 26.8 ms -- the kernel
-  // is bound by instruction issue (FP64 + shared-memory gather), not by bytes in flight, so the
-  // DMA-warp variant stays an option ("push_tma") and the register-load kernel is the default
-  if (ctx->opt_push_tma) {
-    const size_t box_d = ((size_t)NNPM_BX * NNPM_BY * (RANK == 3 ? NNPM_BZ : 1) + 15) & ~(size_t)15;
-    const size_t smem2 = (box_d + (size_t)2 * 2 * RANK * NNPM_PS) * sizeof(double);
-#define LM(CM)                                                                                                      \
-  do {                                                                                                              \
-    CK(cudaFuncSetAttribute(k_push_tma<RANK, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));         \
-    k_push_tma<RANK, CM><<<wgrid, 288, smem2, ctx->st>>>(ctx->tmap_phi, ctx->pp, covered, ctx->g, ctx->tg, wl, ctx->hist, \
-                                                         ctx->mesh, pp, ctx->d_red, ctx->srnk, slow_count);          \
+#define LT(CM)                                                                                                 \
+  do {                                                                                                         \
+    CK(cudaFuncSetAttribute(k_push_tile<RANK, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    k_push_tile<RANK, CM><<<wgrid, 256, smem, ctx->st>>>(ctx->tmap_phi, ctx->pp, covered, ctx->g, ctx->tg, wl, ctx->hist, \
+                                                         ctx->mesh, pp, ctx->d_red, ctx->srnk, slow_count, ctx->opt_l2pf_push); \
   } while (0)
-    if (comoving) LM(true); else LM(false);
-#undef LM
-  } else if (ctx->opt_push_persist) {
-    // persistent variant: 2 CTAs per SM walk the work list with double-buffered boxes (k_push_tile_p)
-    const size_t smem2 = (size_t)2 * NNPM_BOXD(RANK) * sizeof(double);
-    // odd grid: the round-robin walk then visits every tile column equally often (tiles per row are a power of
-    // two on the usual meshes; an even stride would pin the costlier wrapping edge tiles on a few CTAs)
-    if (!ctx->wctr) CKR(dalloc(ctx, &ctx->wctr, 1));
-    CK(cudaMemsetAsync(ctx->wctr, 0, sizeof(unsigned), ctx->st));
-    const unsigned pgrid = ctx->opt_push_grid > 0 ? (unsigned)ctx->opt_push_grid : (unsigned)(2 * ctx->nsm - 1);
-#define LQ(CM, NT)                                                                                                  \
-  do {                                                                                                              \
-    CK(cudaFuncSetAttribute(k_push_tile_p<RANK, CM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));  \
-    k_push_tile_p<RANK, CM, NT><<<pgrid, NT, smem2, ctx->st>>>(ctx->tmap_phi, ctx->pp, covered, ctx->g, ctx->tg, wl, ctx->hist, \
-                                                               ctx->mesh, pp, ctx->d_red, ctx->srnk, slow_count, ctx->opt_push_flags, ctx->wctr); \
-  } while (0)
-    if (ctx->opt_push_persist == 3) { if (comoving) LQ(true, 384); else LQ(false, 384); }
-    else if (ctx->opt_push_persist == 2) { if (comoving) LQ(true, 320); else LQ(false, 320); }
-    else { if (comoving) LQ(true, 256); else LQ(false, 256); }
-#undef LQ
-  } else {
-#define LT(CM, MB, PD)                                                                                              \
-  do {                                                                                                              \
-    CK(cudaFuncSetAttribute(k_push_tile<RANK, CM, MB, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_push_tile<RANK, CM, MB, PD><<<wgrid, 256, smem, ctx->st>>>(ctx->tmap_phi, ctx->pp, covered, ctx->g, ctx->tg, wl, ctx->hist, \
-                                                                 ctx->mesh, pp, ctx->d_red, ctx->srnk, slow_count, ctx->opt_l2pf_push); \
-  } while (0)
-  if (ctx->opt_push_minb >= 3) { if (comoving) LT(true, 3, 1); else LT(false, 3, 1); }
-  else if (ctx->opt_push_depth == 2) { if (comoving) LT(true, 2, 2); else LT(false, 2, 2); }
-  else { if (comoving) LT(true, 2, 1); else LT(false, 2, 1); }
+  if (comoving) LT(true); else LT(false);
 #undef LT
-  }
   LAUNCHED(ctx);
-  global_push(0, 0, ctx->srnk, 148 * 4);                       // stragglers (device-side count)
+  global_push(0, 0, ctx->srnk, (unsigned)ctx->nsm * 4);         // stragglers (device-side count)
   if (np > covered) global_push(covered, np - covered, nullptr, nblk(np - covered, 256));  // arrivals since the sort
   KCHECK();
   return NNPM_OK;
@@ -1300,24 +1271,16 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   } else if (!strcmp(name, "zfused")) ctx->opt_zfused = v;
   else if (!strcmp(name, "tile_deposit")) ctx->opt_tile_deposit = v;
   else if (!strcmp(name, "tile_push")) ctx->opt_tile_push = v;
-  else if (!strcmp(name, "push_minb")) ctx->opt_push_minb = v;
-  else if (!strcmp(name, "zcols")) ctx->opt_zcols = v;
   else if (!strcmp(name, "bulk_flush")) ctx->opt_bulk_flush = v;
   else if (!strcmp(name, "colfft")) ctx->opt_colfft = v;
+  else if (!strcmp(name, "rowfft")) ctx->opt_rowfft = v;
   else if (!strcmp(name, "pipeline")) ctx->opt_pipeline = v;
-  else if (!strcmp(name, "push_tma")) ctx->opt_push_tma = v;
-  else if (!strcmp(name, "push_persist")) ctx->opt_push_persist = v;
-  else if (!strcmp(name, "deposit_unroll")) ctx->opt_deposit_unroll = v;
-  else if (!strcmp(name, "push_grid")) ctx->opt_push_grid = v;
-  else if (!strcmp(name, "push_flags")) ctx->opt_push_flags = v;
-  else if (!strcmp(name, "push_depth")) ctx->opt_push_depth = v;
+  else if (!strcmp(name, "fuse_transpose")) ctx->opt_fuse_transpose = v;
+  else if (!strcmp(name, "peer_transpose")) ctx->opt_peer = v;
   else if (!strcmp(name, "zsplit")) ctx->opt_zsplit = v;
   else if (!strcmp(name, "l2pf_push")) ctx->opt_l2pf_push = v;
   else if (!strcmp(name, "l2pf_deposit")) ctx->opt_l2pf_deposit = v;
-  else if (!strcmp(name, "colfft_z")) ctx->opt_colfft_z = v;
   else if (!strcmp(name, "cfrun_y")) ctx->opt_cfrun_y = v < 1 ? 1 : v;
-  else if (!strcmp(name, "cfrun_z")) ctx->opt_cfrun_z = v < 1 ? 1 : v;
-  else if (!strcmp(name, "peer_transpose")) ctx->opt_peer = v;
   else return fail(ctx, NNPM_ERR_ARG, "unknown option '%s'", name);
   return NNPM_OK;
 }

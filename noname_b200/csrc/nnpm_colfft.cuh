@@ -23,14 +23,14 @@
 // with 4 columns per row (quarter-warps touch two rows whose indices differ by an odd number).
 #pragma once
 
-enum { CF_FWD = 0, CF_INV = 1, CF_GREEN = 2 };
+enum { CF_FWD = 0, CF_INV = 1 };
 
 struct ColFftArgs {
   int ngroups;        // column groups = n_outer_cols * nicg
-  int nicg;           // groups per outer index = ceil(icn / 4)
+  int nicg;           // groups per outer index = ceil(icn / columns per group)
   int icn;
   int run;            // adjacent groups a CTA processes back to back (1 or 2)
-  int outer0;         // first outer index (plane) of this launch: the y pass can run on a sub-range of planes
+  int outer0;         // first outer index (plane / local row) of this launch: a pass can run on a sub-range
   i64 j0;             // global j of local row-block start (Green's function, z pass)
   const double* s1;   // sin^2 tables (z pass)
   const double* s2;
@@ -45,26 +45,28 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* 
                : "memory");
 }
 
-// YPASS: rows run along tensor dimension 1 (j), the outer column index along dimension 2 (plane);
-// otherwise rows along dimension 2 (k), outer index along dimension 1 (jl).
-template <int R1, int R2, int MODE, bool YPASS>
+// y pass: rows run along tensor dimension 1 (j), the outer column index along dimension 2 (plane).
+// PEERS > 1 (forward pass of the slab-decomposed solve): the transformed group is not stored back in place but
+// straight into the slab-transposed spectrum T_d[k][jl][ic] of the rank d = j / njl that owns row block d -- one
+// TMA tensor store per destination through that peer's tensor map (NVLink peer memory, or local memory for
+// d == this rank), i.e. the y pass and the forward all-to-all are ONE kernel and the NVLink transfer of group g
+// overlaps the arithmetic of group g + 1.
+struct PeerMaps { CUtensorMap m[8]; };
+
+template <int R1, int R2, int MODE, bool PEER>
 __global__ void __launch_bounds__(4 * (R1 > R2 ? R1 : R2), 1)
-k_colfft(const __grid_constant__ CUtensorMap tmap, ColFftArgs a) {
+k_colfft(const __grid_constant__ CUtensorMap tmap, ColFftArgs a, const __grid_constant__ PeerMaps pm, int npeers, int njl, int kz0) {
   constexpr int C = 4, N = R1 * R2, RM = R1 > R2 ? R1 : R2, B1 = zf_log2(R1), B2 = zf_log2(R2);
   constexpr int RB = N < 256 ? N : 256, NOPS = N / RB;         // rows per TMA operation (box limit 256)
   constexpr int EST = R2 + 1;                                   // padded exchange row
-  constexpr int SIGN = (MODE == CF_INV) ? +1 : -1;              // sign of the (first) transform
+  constexpr int SIGN = (MODE == CF_INV) ? +1 : -1;              // sign of the transform
   extern __shared__ __align__(128) unsigned char cf_smem[];
   double2* buf0 = (double2*)cf_smem;                            // [2][N][C]
   double2* E = buf0 + 2 * N * C;                                // [R1][EST][C]
   double2* stw = E + R1 * EST * C;                              // [N]
-  double* ss3 = (double*)(stw + N);                             // [N] (CF_GREEN)
   __shared__ __align__(8) unsigned long long full[2];
   const int tid = threadIdx.x, c = tid % C, j = tid / C;
-  for (int t = tid; t < N; t += blockDim.x) {
-    stw[t] = __ldg(a.tw + t);
-    if (MODE == CF_GREEN) ss3[t] = __ldg(a.s3 + t);
-  }
+  for (int t = tid; t < N; t += blockDim.x) stw[t] = __ldg(a.tw + t);
   if (tid == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
@@ -72,19 +74,14 @@ k_colfft(const __grid_constant__ CUtensorMap tmap, ColFftArgs a) {
   __syncthreads();
   // Group schedule: CTA b works on runs of `a.run` adjacent groups, runs dealt round-robin to the CTAs:
   //   g(b, it) = ((it / run) * gridDim + b) * run + it % run.
-  // At any time the CTAs together cover one contiguous stretch of every row (DRAM page locality);
-  // with run = 2 the two 64-byte halves of a 128-byte line are requested by the same CTA in
-  // consecutive iterations, so the half that L2 over-fetches is still resident when it is needed.
+  // At any time the CTAs together cover one contiguous stretch of every row (DRAM page locality).
   const int run = a.run;
   auto group_of = [&](int it) { return ((it / run) * (int)gridDim.x + (int)blockIdx.x) * run + it % run; };
   auto issue_load = [&](int g, int b) {  // thread 0 only
     const int og = g / a.nicg, icg = g - og * a.nicg, outer = og + a.outer0;
     mbar_expect_tx(&full[b], (unsigned)(N * C * sizeof(double2)));
 #pragma unroll
-    for (int o = 0; o < NOPS; o++) {
-      if (YPASS) tma_load_3d(buf0 + (b * N + o * RB) * C, &tmap, icg * 8, o * RB, outer, &full[b]);
-      else tma_load_3d(buf0 + (b * N + o * RB) * C, &tmap, icg * 8, outer, o * RB, &full[b]);
-    }
+    for (int o = 0; o < NOPS; o++) tma_load_3d(buf0 + (b * N + o * RB) * C, &tmap, icg * 8, o * RB, outer, &full[b]);
   };
   int g = group_of(0);
   if (tid == 0 && g < a.ngroups) issue_load(g, 0);
@@ -99,14 +96,6 @@ k_colfft(const __grid_constant__ CUtensorMap tmap, ColFftArgs a) {
     if (tid == 0 && gnext < a.ngroups) {
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       issue_load(gnext, b ^ 1);
-    }
-    // Green's function column factors, requested before the wait so their latency hides behind it
-    double sxy = 1.0;
-    bool dc_col = false;
-    if (MODE == CF_GREEN) {
-      const int ic = icg * C + c;
-      if (ic < a.icn) sxy = __ldg(a.s1 + ic) + __ldg(a.s2 + a.j0 + outer);
-      dc_col = (ic == 0 && a.j0 + outer == 0);
     }
     double2* B = buf0 + b * N * C;
     mbar_wait(&full[b], phase[b]);
@@ -130,157 +119,41 @@ k_colfft(const __grid_constant__ CUtensorMap tmap, ColFftArgs a) {
         v[r] = zmul(v[r], w.x, SIGN < 0 ? w.y : -w.y);
       }
       ZDif<R2, 0, SIGN>::run(v);  // v[brev(q)] = X[j + q*R1]
-      if (MODE != CF_GREEN) {
 #pragma unroll
-        for (int q = 0; q < R2; q++) B[(j + q * R1) * C + c] = v[zf_brev(q, B2)];
-      } else {
-        // Green's function on the bit-reversed registers: X[kz] *= scale / Ginv(i, j, kz)
-        //   Ginv = -4 (sin^2(kx/2) + sin^2(ky/2) + sin^2(kz/2)), rt[1,1,1] = 0   ParticleMesh.jl:494-501
-#pragma unroll
-        for (int q = 0; q < R2; q++) {
-          const int kz = j + q * R1;
-          const double ginv = -4.0 * (sxy + ss3[kz]);
-          double f = (ginv != 0.0) ? a.scale * zf_rcp(ginv) : a.scale;
-          if (dc_col && kz == 0) f = 0.0;
-          double2& e = v[zf_brev(q, B2)];
-          e.x *= f;
-          e.y *= f;
-        }
-        // ---- inverse pass A': radix R2 DIT (bit-reversed in, natural out) -> E in place
-        ZDit<R2, 0, +1>::run(v);
-#pragma unroll
-        for (int r = 0; r < R2; r++) E[(j * EST + r) * C + c] = v[r];
-      }
-    }
-    if (MODE == CF_GREEN) {
-      __syncthreads();
-      // ---- inverse pass B': radix R1 over k1 for n' = j -> rows j + q*R2
-      if (j < R2) {
-#pragma unroll
-        for (int r = 0; r < R1; r++) v[r] = E[(r * EST + j) * C + c];
-#pragma unroll
-        for (int r = 1; r < R1; r++) {
-          const double2 w = stw[r * j];
-          v[r] = zmul(v[r], w.x, -w.y);
-        }
-        ZDif<R1, 0, +1>::run(v);
-#pragma unroll
-        for (int q = 0; q < R1; q++) B[(j + q * R2) * C + c] = v[zf_brev(q, B1)];
-      }
+      for (int q = 0; q < R2; q++) B[(j + q * R1) * C + c] = v[zf_brev(q, B2)];
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> TMA store reads
     __syncthreads();
     if (tid == 0) {
+      if (PEER) {
+        // rows [d*njl, (d+1)*njl) of the transformed group belong to rank d: T_d[kz0 + outer][jl][ic]
+        const int rbp = njl < 256 ? njl : 256;
+        for (int d = 0; d < npeers; d++)
+          for (int o = 0; o < njl; o += rbp) tma_store_3d(&pm.m[d], B + (d * njl + o) * C, icg * 8, o, kz0 + outer);
+      } else {
 #pragma unroll
-      for (int o = 0; o < NOPS; o++) {
-        if (YPASS) tma_store_3d(&tmap, B + o * RB * C, icg * 8, o * RB, outer);
-        else tma_store_3d(&tmap, B + o * RB * C, icg * 8, outer, o * RB);
+        for (int o = 0; o < NOPS; o++) tma_store_3d(&tmap, B + o * RB * C, icg * 8, o * RB, outer);
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     g = gnext;
   }
-  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete (also the remote ones) before exit
 }
 
-// Fused z pass, two CTAs per SM: ONE shared-memory buffer per CTA holds the column group in natural
-// order (TMA load / store side) and, aliased onto it, the padded exchange layout; the memory phases
-// of one CTA (store drain, next load) are covered by the compute phases of its sibling on the same SM.
-template <int R1, int R2>
-__global__ void __launch_bounds__(4 * (R1 > R2 ? R1 : R2), 2)
-k_colfft_z2(const __grid_constant__ CUtensorMap tmap, ColFftArgs a) {
-  constexpr int C = 4, N = R1 * R2, RM = R1 > R2 ? R1 : R2, B1 = zf_log2(R1), B2 = zf_log2(R2);
-  constexpr int RB = N < 256 ? N : 256, NOPS = N / RB;
-  constexpr int EST = R2 + 1;
-  extern __shared__ __align__(128) unsigned char cf_smem[];
-  double2* B = (double2*)cf_smem;        // natural [N][C]   /   exchange [R1][EST][C]  (aliased)
-  double2* E = B;
-  double2* stw = B + R1 * EST * C;
-  double* ss3 = (double*)(stw + N);
-  __shared__ __align__(8) unsigned long long full;
-  const int tid = threadIdx.x, c = tid % C, j = tid / C;
-  for (int t = tid; t < N; t += blockDim.x) {
-    stw[t] = __ldg(a.tw + t);
-    ss3[t] = __ldg(a.s3 + t);
-  }
-  if (tid == 0) mbar_init(&full, 1);
-  __syncthreads();
-  unsigned phase = 0u;
-  double2 v[RM];
-  for (int g = blockIdx.x; g < a.ngroups; g += gridDim.x) {
-    const int outer = g / a.nicg, icg = g - outer * a.nicg;
-    if (tid == 0) {
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous store has read the buffer
-      mbar_expect_tx(&full, (unsigned)(N * C * sizeof(double2)));
-#pragma unroll
-      for (int o = 0; o < NOPS; o++) tma_load_3d(B + o * RB * C, &tmap, icg * 8, outer, o * RB, &full);
-    }
-    const int ic = icg * C + c;
-    double sxy = 1.0;
-    if (ic < a.icn) sxy = __ldg(a.s1 + ic) + __ldg(a.s2 + a.j0 + outer);
-    const bool dc_col = (ic == 0 && a.j0 + outer == 0);
-    mbar_wait(&full, phase);
-    phase ^= 1u;
-    if (j < R2) {
-#pragma unroll
-      for (int r = 0; r < R1; r++) v[r] = B[(j + r * R2) * C + c];
-      ZDif<R1, 0, -1>::run(v);
-    }
-    __syncthreads();  // every thread has its rows in registers: the buffer may take the exchange layout
-    if (j < R2) {
-#pragma unroll
-      for (int q = 0; q < R1; q++) E[(q * EST + j) * C + c] = v[zf_brev(q, B1)];
-    }
-    __syncthreads();
-    if (j < R1) {
-#pragma unroll
-      for (int r = 0; r < R2; r++) v[r] = E[(j * EST + r) * C + c];
-#pragma unroll
-      for (int r = 1; r < R2; r++) {
-        const double2 w = stw[r * j];
-        v[r] = zmul(v[r], w.x, w.y);
-      }
-      ZDif<R2, 0, -1>::run(v);
-#pragma unroll
-      for (int q = 0; q < R2; q++) {
-        const int kz = j + q * R1;
-        const double ginv = -4.0 * (sxy + ss3[kz]);
-        double f = (ginv != 0.0) ? a.scale * zf_rcp(ginv) : a.scale;
-        if (dc_col && kz == 0) f = 0.0;
-        double2& e = v[zf_brev(q, B2)];
-        e.x *= f;
-        e.y *= f;
-      }
-      ZDit<R2, 0, +1>::run(v);
-#pragma unroll
-      for (int r = 0; r < R2; r++) E[(j * EST + r) * C + c] = v[r];
-    }
-    __syncthreads();
-    if (j < R2) {
-#pragma unroll
-      for (int r = 0; r < R1; r++) v[r] = E[(r * EST + j) * C + c];
-#pragma unroll
-      for (int r = 1; r < R1; r++) {
-        const double2 w = stw[r * j];
-        v[r] = zmul(v[r], w.x, -w.y);
-      }
-      ZDif<R1, 0, +1>::run(v);
-    }
-    __syncthreads();  // exchange layout fully consumed: back to natural order
-    if (j < R2) {
-#pragma unroll
-      for (int q = 0; q < R1; q++) B[(j + q * R2) * C + c] = v[zf_brev(q, B1)];
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-#pragma unroll
-      for (int o = 0; o < NOPS; o++) tma_store_3d(&tmap, B + o * RB * C, icg * 8, outer, o * RB);
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-  }
-  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
+// Destination of the fused z pass' output rows.  Row n (global plane k = n) of column (jl, ic) is written to
+//   base[n >> shift] + (n & mask) * plane_c + (row0 + jl) * icn + ic                       (complex elements)
+// * in place (single GPU, or the un-fused multi-GPU path on meshT): shift = 31, base[0] = T, plane_c = njl * icn,
+//   row0 = 0 -- the same element the column was read from;
+// * fused backward slab transpose (nranks > 1, peer memory): base[d] = rank d's mesh slab mapped over NVLink (or
+//   the local one), shift = log2(nzl), plane_c = plane / 2, row0 = njl * rank: the z pass stores every row
+//   straight into the [kl][j][ic] layout of the rank that owns plane k, so the inverse all-to-all costs no extra
+//   pass over HBM and its NVLink transfer runs under the arithmetic of the next column group.
+struct ZDst {
+  double2* base[8];
+  int shift, mask;
+  i64 plane_c, row0;
+};
 
 // Persistent form of k_zfused (nnpm_zfft.cuh) with the NEXT column group prefetched by TMA: 8 adjacent
 // columns per group (128-byte rows: exact DRAM traffic), 8 warps, the [N][8] shared-memory buffer is
@@ -300,7 +173,7 @@ k_colfft_z2(const __grid_constant__ CUtensorMap tmap, ColFftArgs a) {
 // x[n] = E[n] + W_NT^-n O[n],  x[n + N] = E[n] - W_NT^-n O[n].
 template <int R1, int R2, bool TWO>
 __global__ void __launch_bounds__(8 * (R1 > R2 ? R1 : R2), 1)
-k_zfused_p(const __grid_constant__ CUtensorMap tmap, double2* __restrict__ T, i64 ncol, ColFftArgs a) {
+k_zfused_p(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ZDst dst, ColFftArgs a) {
   constexpr int C = 8, N = R1 * R2, RM = R1 > R2 ? R1 : R2, B1 = zf_log2(R1), B2 = zf_log2(R2);
   constexpr int NT = TWO ? 2 * N : N;   // transform length
   constexpr int CR = TWO ? 4 : 8;       // real columns per group
@@ -407,7 +280,7 @@ k_zfused_p(const __grid_constant__ CUtensorMap tmap, double2* __restrict__ T, i6
         v[r] = zmul(v[r], w.x, -w.y);
       }
       ZDif<R1, 0, +1>::run(v);
-      double2* Tc = T + (i64)jl * a.icn + ic;
+      const i64 col = (dst.row0 + jl) * (i64)a.icn + ic;
 #pragma unroll
       for (int q = 0; q < R1; q++) {
         const int n = j + q * R2;
@@ -422,9 +295,140 @@ k_zfused_p(const __grid_constant__ CUtensorMap tmap, double2* __restrict__ T, i6
           o.y = __shfl_xor_sync(0xffffffffu, e.y, 4);
           e = par ? zsub(o, e) : zadd(e, o);
         }
-        if (colok) Tc[(i64)(n + N * par) * ncol] = e;
+        const int nn = n + N * par;
+        if (colok) dst.base[nn >> dst.shift][(i64)(nn & dst.mask) * dst.plane_c + col] = e;
       }
     }
+  }
+}
+
+// k_zfused_p with the landing zone and the exchange buffer SEPARATED, so that the tensor load of the next column
+// group is in flight during the whole transform of the current one instead of during its last pass only.  Round 1's
+// ncu capture of k_zfused_p showed the FP64 pipe and DRAM each ~45 % busy but never at the same time: one [N][8]
+// double2 buffer (128 KB at N = 1024) was both, and a second one does not fit.  Here the exchange moves real and
+// imaginary parts in two half-steps through a [N][8] buffer of DOUBLES (64 KB): 128 KB landing zone + 64 KB
+// exchange + 24 KB tables = 216 KB.  The exchange rows are skewed by 8 doubles per 32 rows so that the four rows a
+// warp touches in the scatter half-step fall on two bank groups (2 wavefronts per 256 bytes: the minimum).
+template <int R1, int R2>
+__global__ void __launch_bounds__(8 * (R1 > R2 ? R1 : R2), 1)
+k_zfused_s(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ZDst dst, ColFftArgs a) {
+  constexpr int C = 8, N = R1 * R2, RM = R1 > R2 ? R1 : R2, B1 = zf_log2(R1), B2 = zf_log2(R2);
+  constexpr int RB = N < 256 ? N : 256, NOPS = N / RB;
+  extern __shared__ __align__(128) unsigned char cf_smem[];
+  double2* L = (double2*)cf_smem;                 // landing zone [N][C]
+  double* E = (double*)(L + N * C);               // exchange [N][C] doubles, skewed
+  double2* stw = (double2*)(E + N * C + C * (N / 32));
+  double* ss3 = (double*)(stw + N);
+  __shared__ __align__(8) unsigned long long full;
+  const int tid = threadIdx.x, c = tid % C, j = tid / C;
+  auto EZ = [&](int r) { return r * C + c + C * (r >> 5); };
+  for (int t = tid; t < N; t += blockDim.x) {
+    stw[t] = __ldg(a.tw + t);
+    ss3[t] = __ldg(a.s3 + t);
+  }
+  if (tid == 0) mbar_init(&full, 1);
+  __syncthreads();
+  auto issue_load = [&](int g) {  // thread 0 only
+    const int og = g / a.nicg, icg = g - og * a.nicg;
+    mbar_expect_tx(&full, (unsigned)(N * C * sizeof(double2)));
+#pragma unroll
+    for (int o = 0; o < NOPS; o++) tma_load_3d(L + o * RB * C, &tmap, icg * (2 * C), og + a.outer0, o * RB, &full);
+  };
+  int g = blockIdx.x;
+  if (tid == 0 && g < a.ngroups) issue_load(g);
+  unsigned phase = 0u;
+  double2 v[RM];
+  for (; g < a.ngroups; g += gridDim.x) {
+    const int og = g / a.nicg, icg = g - og * a.nicg, jl = og + a.outer0;
+    const int ic = icg * C + c;
+    const bool colok = ic < a.icn;
+    double sxy = 1.0;
+    if (colok) sxy = __ldg(a.s1 + ic) + __ldg(a.s2 + a.j0 + jl);
+    const bool dc_col = (ic == 0 && a.j0 + jl == 0);
+    mbar_wait(&full, phase);
+    phase ^= 1u;
+    // ---- forward pass A: radix R1 over rows j + r*R2, read from the landing zone
+    if (j < R2) {
+#pragma unroll
+      for (int r = 0; r < R1; r++) v[r] = L[(j + r * R2) * C + c];
+    }
+    __syncthreads();  // the landing zone is in registers: the next group's tensor load may overwrite it
+    if (tid == 0 && g + (int)gridDim.x < a.ngroups) issue_load(g + gridDim.x);
+    if (j < R2) ZDif<R1, 0, -1>::run(v);
+    // ---- exchange 1 (two half-steps): pass-A thread j' writes (j'*R1 + q), pass-B thread j reads (j + r*R1)
+    if (j < R2) {
+#pragma unroll
+      for (int q = 0; q < R1; q++) E[EZ(j * R1 + q)] = v[zf_brev(q, B1)].x;
+    }
+    __syncthreads();
+    if (j < R1) {
+#pragma unroll
+      for (int r = 0; r < R2; r++) v[r].x = E[EZ(j + r * R1)];
+    }
+    __syncthreads();
+    if (j < R2) {
+#pragma unroll
+      for (int q = 0; q < R1; q++) E[EZ(j * R1 + q)] = v[zf_brev(q, B1)].y;
+    }
+    __syncthreads();
+    if (j < R1) {
+#pragma unroll
+      for (int r = 0; r < R2; r++) v[r].y = E[EZ(j + r * R1)];
+      // ---- forward pass B, Green's function, inverse pass A'
+#pragma unroll
+      for (int r = 1; r < R2; r++) {
+        const double2 w = stw[r * j];
+        v[r] = zmul(v[r], w.x, w.y);
+      }
+      ZDif<R2, 0, -1>::run(v);
+#pragma unroll
+      for (int q = 0; q < R2; q++) {  // X[kz] *= scale / Ginv   (ParticleMesh.jl:494-501)
+        const int kz = j + q * R1;
+        const double ginv = -4.0 * (sxy + ss3[kz]);
+        double f = (ginv != 0.0) ? a.scale * zf_rcp(ginv) : a.scale;
+        if (dc_col && kz == 0) f = 0.0;
+        double2& e = v[zf_brev(q, B2)];
+        e.x *= f;
+        e.y *= f;
+      }
+      ZDit<R2, 0, +1>::run(v);
+    }
+    __syncthreads();  // every read of exchange 1 is done
+    // ---- exchange 2: pass-A' thread j' writes (j'*R2 + r), pass-B' thread j reads (j + r*R2)
+    if (j < R1) {
+#pragma unroll
+      for (int r = 0; r < R2; r++) E[EZ(j * R2 + r)] = v[r].x;
+    }
+    __syncthreads();
+    if (j < R2) {
+#pragma unroll
+      for (int r = 0; r < R1; r++) v[r].x = E[EZ(j + r * R2)];
+    }
+    __syncthreads();
+    if (j < R1) {
+#pragma unroll
+      for (int r = 0; r < R2; r++) E[EZ(j * R2 + r)] = v[r].y;
+    }
+    __syncthreads();
+    // ---- inverse pass B': radix R1 -> rows j + q*R2, stored straight from registers
+    if (j < R2) {
+#pragma unroll
+      for (int r = 0; r < R1; r++) v[r].y = E[EZ(j + r * R2)];
+#pragma unroll
+      for (int r = 1; r < R1; r++) {
+        const double2 w = stw[r * j];
+        v[r] = zmul(v[r], w.x, -w.y);
+      }
+      ZDif<R1, 0, +1>::run(v);
+      const i64 col = (dst.row0 + jl) * (i64)a.icn + ic;
+#pragma unroll
+      for (int q = 0; q < R1; q++) {
+        const int n = j + q * R2;
+        if (colok) dst.base[n >> dst.shift][(i64)(n & dst.mask) * dst.plane_c + col] = v[zf_brev(q, B1)];
+      }
+    }
+    // the next iteration's first barrier (after its landing-zone reads) separates these exchange reads from the
+    // next exchange writes
   }
 }
 
@@ -462,34 +466,36 @@ static int colfft_twiddles(nnpm_ctx* ctx, double2** tw, i64 N) {
   return NNPM_OK;
 }
 
-template <int R1, int R2, int MODE, bool YPASS>
-static int colfft_go(nnpm_ctx* ctx, const CUtensorMap& tm, const ColFftArgs& a) {
+template <int R1, int R2, int MODE, bool PEER>
+static int colfft_go(nnpm_ctx* ctx, const CUtensorMap& tm, const ColFftArgs& a, const PeerMaps* pm) {
   constexpr int N = R1 * R2, RM = R1 > R2 ? R1 : R2;
-  const size_t smem = (size_t)2 * N * 4 * 16 + (size_t)R1 * (R2 + 1) * 4 * 16 + (size_t)N * 16 + (size_t)N * 8;
-  CK(cudaFuncSetAttribute(k_colfft<R1, R2, MODE, YPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = (size_t)2 * N * 4 * 16 + (size_t)R1 * (R2 + 1) * 4 * 16 + (size_t)N * 16;
+  CK(cudaFuncSetAttribute(k_colfft<R1, R2, MODE, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = a.ngroups < ctx->nsm ? a.ngroups : ctx->nsm;
-  k_colfft<R1, R2, MODE, YPASS><<<grid, 4 * RM, smem, ctx->st>>>(tm, a);
+  k_colfft<R1, R2, MODE, PEER><<<grid, 4 * RM, smem, ctx->st>>>(tm, a, *pm, ctx->P, (int)ctx->njl, (int)ctx->g.kz0);
   LAUNCHED(ctx);
   KCHECK();
   return NNPM_OK;
 }
 
-template <int MODE, bool YPASS>
-static int colfft_dispatch(nnpm_ctx* ctx, i64 N, const CUtensorMap& tm, const ColFftArgs& a) {
+template <int MODE, bool PEER>
+static int colfft_dispatch(nnpm_ctx* ctx, i64 N, const CUtensorMap& tm, const ColFftArgs& a, const PeerMaps* pm) {
   switch (N) {
-    case 64: return colfft_go<8, 8, MODE, YPASS>(ctx, tm, a);
-    case 128: return colfft_go<16, 8, MODE, YPASS>(ctx, tm, a);
-    case 256: return colfft_go<16, 16, MODE, YPASS>(ctx, tm, a);
-    case 512: return colfft_go<32, 16, MODE, YPASS>(ctx, tm, a);
-    case 1024: return colfft_go<32, 32, MODE, YPASS>(ctx, tm, a);
+    case 64: return colfft_go<8, 8, MODE, PEER>(ctx, tm, a, pm);
+    case 128: return colfft_go<16, 8, MODE, PEER>(ctx, tm, a, pm);
+    case 256: return colfft_go<16, 16, MODE, PEER>(ctx, tm, a, pm);
+    case 512: return colfft_go<32, 16, MODE, PEER>(ctx, tm, a, pm);
+    case 1024: return colfft_go<32, 32, MODE, PEER>(ctx, tm, a, pm);
   }
   return fail(ctx, NNPM_ERR_STATE, "column FFT does not support N = %lld", (long long)N);
 }
 
 static bool colfft_supported_n(i64 N) { int r1, r2; return zfused_factor(N, &r1, &r2); }
 
-// y pass over the owned planes, in place in the mesh (forward after the x r2c, inverse before the x c2r)
-static int colfft_y(nnpm_ctx* ctx, bool inverse, i64 plane0 = 0, i64 nplanes = -1) {
+// y pass over the owned planes, in place in the mesh (forward after the x r2c, inverse before the x c2r).
+// to_peers (forward only, nranks > 1): the output goes straight into every rank's slab-transposed spectrum
+// (ctx->peer_maps) instead -- the forward all-to-all fused into the pass.
+static int colfft_y(nnpm_ctx* ctx, bool inverse, i64 plane0 = 0, i64 nplanes = -1, bool to_peers = false) {
   const Geom& g = ctx->g;
   if (!ctx->have_tm_y) {
     CKR(colfft_tensor_map(ctx, &ctx->tm_y, ctx->mesh + g.plane * g.glo, g.N2, g.nzl, ctx->icn * 16, g.plane * 8, true, g.N2));
@@ -506,48 +512,26 @@ static int colfft_y(nnpm_ctx* ctx, bool inverse, i64 plane0 = 0, i64 nplanes = -
   a.tw = ctx->ytw;
   a.scale = 1.0;
   a.run = ctx->opt_cfrun_y;
-  return inverse ? colfft_dispatch<CF_INV, true>(ctx, g.N2, ctx->tm_y, a) : colfft_dispatch<CF_FWD, true>(ctx, g.N2, ctx->tm_y, a);
+  static const PeerMaps no_peers = {};
+  if (to_peers) {
+    if (inverse || !ctx->peer_maps) return fail(ctx, NNPM_ERR_STATE, "fused forward transpose: peer tensor maps missing");
+    return colfft_dispatch<CF_FWD, true>(ctx, g.N2, ctx->tm_y, a, ctx->peer_maps);
+  }
+  return inverse ? colfft_dispatch<CF_INV, false>(ctx, g.N2, ctx->tm_y, a, &no_peers)
+                 : colfft_dispatch<CF_FWD, false>(ctx, g.N2, ctx->tm_y, a, &no_peers);
 }
 
-// fused z pass on T[k][jl][ic] (the mesh itself when nranks == 1, meshT otherwise)
-static int colfft_z_green(nnpm_ctx* ctx, double2* T, double scale) {
+// tensor maps over every rank's transposed spectrum T_d[k][jl][ic] (peer memory), box = (4 columns, <= 256 rows jl, 1 plane)
+static int colfft_peer_maps(nnpm_ctx* ctx) {
+  if (ctx->peer_maps) return NNPM_OK;
   const Geom& g = ctx->g;
-  if (!ctx->have_tm_z) {
-    CKR(colfft_tensor_map(ctx, &ctx->tm_z, (double*)T, ctx->njl, g.N3, ctx->icn * 16, ctx->njl * ctx->icn * 16, false, g.N3));
-    ctx->have_tm_z = true;
-  }
-  CKR(colfft_twiddles(ctx, &ctx->ztw, g.N3));
-  ColFftArgs a;
-  memset(&a, 0, sizeof a);
-  a.nicg = (int)((ctx->icn + 3) / 4);
-  a.ngroups = (int)(ctx->njl * a.nicg);
-  a.icn = (int)ctx->icn;
-  a.j0 = ctx->njl * ctx->r;
-  a.s1 = ctx->s1; a.s2 = ctx->s2; a.s3 = ctx->s3;
-  a.tw = ctx->ztw;
-  a.scale = scale;
-  a.run = ctx->opt_cfrun_z;
-  if (ctx->opt_colfft_z == 2) {  // two CTAs per SM, single aliased buffer
-#define Z2(R1_, R2_)                                                                                                   \
-  do {                                                                                                                 \
-    const size_t smem = (size_t)R1_ * (R2_ + 1) * 4 * 16 + (size_t)R1_ * R2_ * 24;                                        \
-    CK(cudaFuncSetAttribute(k_colfft_z2<R1_, R2_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-    const int grid = a.ngroups < 2 * ctx->nsm ? a.ngroups : 2 * ctx->nsm;                                               \
-    k_colfft_z2<R1_, R2_><<<grid, 4 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(ctx->tm_z, a);                            \
-    LAUNCHED(ctx);                                                                                                     \
-    KCHECK();                                                                                                          \
-    return NNPM_OK;                                                                                                    \
-  } while (0)
-    switch (g.N3) {
-      case 64: Z2(8, 8);
-      case 128: Z2(16, 8);
-      case 256: Z2(16, 16);
-      case 512: Z2(32, 16);
-      case 1024: Z2(32, 32);
-    }
-#undef Z2
-  }
-  return colfft_dispatch<CF_GREEN, false>(ctx, g.N3, ctx->tm_z, a);
+  if (ctx->P > 8) return fail(ctx, NNPM_ERR_STATE, "fused transposes support nranks <= 8");
+  ctx->peer_maps = new PeerMaps();
+  memset(ctx->peer_maps, 0, sizeof(PeerMaps));
+  const i64 njl = ctx->njl;
+  for (int d = 0; d < ctx->P; d++)
+    CKR(colfft_tensor_map(ctx, &ctx->peer_maps->m[d], ctx->peer_meshT[d], njl, g.N3, ctx->icn * 16, njl * ctx->icn * 16, true, njl));
+  return NNPM_OK;
 }
 
 // persistent k_zfused with TMA prefetch over the local rows jl in [jlbeg, jlend)
@@ -557,7 +541,30 @@ static bool zfused_p_two(const nnpm_ctx* ctx) {  // N3 = 2 x (two-pass length): 
   if (N3 % 2 || !zfused_factor(N3 / 2, &r1, &r2)) return false;
   return !zfused_factor(N3, &r1, &r2) || ctx->opt_zsplit;
 }
-static int zfused_p_launch(nnpm_ctx* ctx, double2* T, double scale, i64 jlbeg, i64 jlend) {
+static void zdst_inplace(nnpm_ctx* ctx, double2* T, ZDst* d) {
+  memset(d, 0, sizeof *d);
+  d->base[0] = T;
+  d->shift = 31;
+  d->mask = 0x7fffffff;
+  d->plane_c = ctx->njl * ctx->icn;
+  d->row0 = 0;
+}
+// fused backward slab transpose: rows go straight into the owning rank's mesh slab (peer memory)
+static bool zdst_peers(nnpm_ctx* ctx, ZDst* d) {
+  const Geom& g = ctx->g;
+  if (!ctx->peer_ok || ctx->P > 8 || (g.nzl & (g.nzl - 1))) return false;
+  memset(d, 0, sizeof *d);
+  for (int r = 0; r < ctx->P; r++) d->base[r] = (double2*)(ctx->peer_mesh[r] + g.plane * g.glo);
+  int sh = 0;
+  while ((1ll << sh) < g.nzl) sh++;
+  d->shift = sh;
+  d->mask = (int)g.nzl - 1;
+  d->plane_c = g.plane / 2;
+  d->row0 = ctx->njl * ctx->r;
+  return true;
+}
+
+static int zfused_p_launch(nnpm_ctx* ctx, double2* T, double scale, i64 jlbeg, i64 jlend, const ZDst* dst = nullptr) {
   const Geom& g = ctx->g;
   const bool two = zfused_p_two(ctx);
   const int cr = two ? 4 : 8;  // real columns per group
@@ -580,13 +587,14 @@ static int zfused_p_launch(nnpm_ctx* ctx, double2* T, double scale, i64 jlbeg, i
   a.s1 = ctx->s1; a.s2 = ctx->s2; a.s3 = ctx->s3;
   a.tw = ctx->ztw;
   a.scale = scale;
-  const i64 ncol = ctx->njl * ctx->icn;
+  ZDst d;
+  if (dst) d = *dst; else zdst_inplace(ctx, T, &d);
 #define ZP(R1_, R2_, TWO_)                                                                                             \
   do {                                                                                                                 \
     const size_t smem = (size_t)R1_ * R2_ * (8 * 16 + (TWO_ ? 2 : 1) * (16 + 8));                                        \
     CK(cudaFuncSetAttribute(k_zfused_p<R1_, R2_, TWO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
     const int grid = a.ngroups < ctx->nsm ? a.ngroups : ctx->nsm;                                                       \
-    k_zfused_p<R1_, R2_, TWO_><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(TWO_ ? ctx->tm_z4 : ctx->tm_z8, T, ncol, a); \
+    k_zfused_p<R1_, R2_, TWO_><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(TWO_ ? ctx->tm_z4 : ctx->tm_z8, d, a); \
     LAUNCHED(ctx);                                                                                                     \
     KCHECK();                                                                                                          \
     return NNPM_OK;                                                                                                    \
@@ -610,4 +618,47 @@ static int zfused_p_launch(nnpm_ctx* ctx, double2* T, double scale, i64 jlbeg, i
   }
 #undef ZP
   return fail(ctx, NNPM_ERR_STATE, "persistent fused z pass does not support N3 = %lld", (long long)g.N3);
+}
+
+// split-exchange persistent fused z pass (k_zfused_s) over the local rows jl in [jlbeg, jlend); N3 = 64 .. 1024.
+// dst == nullptr: in place in T.
+static int zfused_s_launch(nnpm_ctx* ctx, double2* T, double scale, i64 jlbeg, i64 jlend, const ZDst* dst = nullptr) {
+  const Geom& g = ctx->g;
+  if (!ctx->have_tm_z8) {
+    CKR(colfft_tensor_map(ctx, &ctx->tm_z8, (double*)T, ctx->njl, g.N3, ctx->icn * 16, ctx->njl * ctx->icn * 16, false, g.N3, 16));
+    ctx->have_tm_z8 = true;
+  }
+  CKR(colfft_twiddles(ctx, &ctx->ztw, g.N3));
+  ColFftArgs a;
+  memset(&a, 0, sizeof a);
+  a.nicg = (int)((ctx->icn + 7) / 8);
+  a.ngroups = (int)((jlend - jlbeg) * a.nicg);
+  a.outer0 = (int)jlbeg;
+  a.icn = (int)ctx->icn;
+  a.j0 = ctx->njl * ctx->r;
+  a.s1 = ctx->s1; a.s2 = ctx->s2; a.s3 = ctx->s3;
+  a.tw = ctx->ztw;
+  a.scale = scale;
+  ZDst d;
+  if (dst) d = *dst; else zdst_inplace(ctx, T, &d);
+#define ZS(R1_, R2_)                                                                                                   \
+  do {                                                                                                                 \
+    constexpr int N_ = R1_ * R2_;                                                                                      \
+    const size_t smem = (size_t)N_ * 8 * 16 + ((size_t)N_ * 8 + 8 * (N_ / 32)) * 8 + (size_t)N_ * 24;                    \
+    CK(cudaFuncSetAttribute(k_zfused_s<R1_, R2_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    const int grid = a.ngroups < ctx->nsm ? a.ngroups : ctx->nsm;                                                       \
+    k_zfused_s<R1_, R2_><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(ctx->tm_z8, d, a);                         \
+    LAUNCHED(ctx);                                                                                                     \
+    KCHECK();                                                                                                          \
+    return NNPM_OK;                                                                                                    \
+  } while (0)
+  switch (g.N3) {
+    case 64: ZS(8, 8);
+    case 128: ZS(16, 8);
+    case 256: ZS(16, 16);
+    case 512: ZS(32, 16);
+    case 1024: ZS(32, 32);
+  }
+#undef ZS
+  return fail(ctx, NNPM_ERR_STATE, "split-exchange fused z pass does not support N3 = %lld", (long long)g.N3);
 }

@@ -152,7 +152,7 @@ extern "C" int nnpm_comm_init(nnpm_ctx* ctx, const uint8_t id[128]) {
   CKR(dalloc(ctx, &ctx->mig_recv, (size_t)ctx->mig_cap * MIG_REC));
   CKR(dalloc(ctx, &ctx->mig_holes, (size_t)ctx->mig_cap));
   CKR(dalloc(ctx, &ctx->mig_lo, (size_t)ctx->mig_cap));
-  CKR(dalloc(ctx, &ctx->mig_cnt, (size_t)(80 + 24 * 64)));  // [0..P) per-dest counts, [16] holes, [17] overflow, [18] nlo, [19] nfill, [24..) scratch, [80..) allgather
+  CKR(dalloc(ctx, &ctx->mig_cnt, (size_t)(MC_ALL + MC_REC * 64)));  // local record (MC_* slots), then the all-gathered records of every rank
   CKR(dalloc(ctx, &ctx->bar_buf, 4));
   CK(cudaMemsetAsync(ctx->bar_buf, 0, 16, ctx->st));
   CKR(peer_setup(ctx));
@@ -253,28 +253,6 @@ static int comm_all_to_all(nnpm_ctx* ctx, const double* src, double* dst) {
   return NNPM_OK;
 }
 
-// ---- fused pack + all-to-all over NVLink peer memory -------------------------------------------
-// forward:  A[kl][j][ic] (this rank's planes, all j) is stored straight into the owner of row block
-//           d = j / njl:  T_d[kz0 + kl][jl][ic].   backward:  T[k][jl][ic] (all k, this rank's j block)
-//           goes to the owner of plane k:  A_d[kl][j0 + jl][ic].  One kernel reads local HBM once and
-//           writes the remote (or local) destination once -- no staging buffer, no pack/unpack pass.
-struct PeerPtrs { double2* p[64]; };
-__global__ void __launch_bounds__(128)
-k_transpose_fwd_peer(const double2* __restrict__ A, PeerPtrs T, int icn, int njl, int nzl, i64 aplane_c, int kz0) {
-  const int j = blockIdx.y, kl = blockIdx.z;
-  const int d = j / njl, jl = j - d * njl;
-  const double2* src = A + (i64)icn * j + aplane_c * kl;
-  double2* dst = T.p[d] + (i64)icn * (jl + (i64)njl * (kz0 + kl));
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < icn; i += gridDim.x * blockDim.x) dst[i] = src[i];
-}
-__global__ void __launch_bounds__(128)
-k_transpose_bwd_peer(PeerPtrs A, const double2* __restrict__ T, int icn, int njl, int nzl, i64 aplane_c, int j0) {
-  const int jl = blockIdx.y, k = blockIdx.z;
-  const int d = k / nzl, kl = k - d * nzl;
-  const double2* src = T + (i64)icn * (jl + (i64)njl * k);
-  double2* dst = A.p[d] + (i64)icn * (j0 + jl) + aplane_c * kl;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < icn; i += gridDim.x * blockDim.x) dst[i] = src[i];
-}
 // stream-ordered barrier over all ranks: remote stores of the kernels before it are complete (kernel
 // boundary) before any rank's later work starts
 static int comm_barrier(nnpm_ctx* ctx) {
@@ -359,17 +337,7 @@ static int comm_join_barrier(nnpm_ctx* ctx) {
 static int comm_transpose_fwd(nnpm_ctx* ctx) {
   NEED_COMM();
   const Geom& g = ctx->g;
-  if (ctx->peer_ok && ctx->opt_peer == 1) return comm_transpose_ce(ctx, true);
-  if (ctx->peer_ok && ctx->opt_peer) {
-    PeerPtrs T;
-    for (int d = 0; d < ctx->P; d++) T.p[d] = (double2*)ctx->peer_meshT[d];
-    dim3 grid(nblk(ctx->icn, 256), (unsigned)g.N2, (unsigned)g.nzl);
-    k_transpose_fwd_peer<<<grid, 128, 0, ctx->st>>>((const double2*)(ctx->mesh + g.plane * g.glo), T, (int)ctx->icn, (int)ctx->njl,
-                                                    (int)g.nzl, g.plane / 2, (int)g.kz0);
-    LAUNCHED(ctx);
-    KCHECK();
-    return comm_barrier(ctx);
-  }
+  if (ctx->peer_ok && ctx->opt_peer) return comm_transpose_ce(ctx, true);
   const double2* A = (const double2*)(ctx->mesh + g.plane * g.glo);
   dim3 grid(nblk(ctx->icn, 128), (unsigned)g.N2, (unsigned)g.nzl);
   k_pack_fwd<<<grid, 128, 0, ctx->st>>>(A, (double2*)ctx->meshS, ctx->icn, g.N2, ctx->njl, g.nzl, g.plane / 2);
@@ -381,17 +349,7 @@ static int comm_transpose_fwd(nnpm_ctx* ctx) {
 static int comm_transpose_bwd(nnpm_ctx* ctx) {
   NEED_COMM();
   const Geom& g = ctx->g;
-  if (ctx->peer_ok && ctx->opt_peer == 1) return comm_transpose_ce(ctx, false);
-  if (ctx->peer_ok && ctx->opt_peer) {
-    PeerPtrs A;
-    for (int d = 0; d < ctx->P; d++) A.p[d] = (double2*)(ctx->peer_mesh[d] + g.plane * g.glo);
-    dim3 grid(nblk(ctx->icn, 256), (unsigned)ctx->njl, (unsigned)g.N3);
-    k_transpose_bwd_peer<<<grid, 128, 0, ctx->st>>>(A, (const double2*)ctx->meshT, (int)ctx->icn, (int)ctx->njl, (int)g.nzl,
-                                                    g.plane / 2, (int)(ctx->njl * ctx->r));
-    LAUNCHED(ctx);
-    KCHECK();
-    return comm_barrier(ctx);
-  }
+  if (ctx->peer_ok && ctx->opt_peer) return comm_transpose_ce(ctx, false);
   CKR(comm_all_to_all(ctx, ctx->meshT, ctx->meshS));
   double2* A = (double2*)(ctx->mesh + g.plane * g.glo);
   dim3 grid(nblk(ctx->icn, 128), (unsigned)g.N2, (unsigned)g.nzl);
@@ -437,7 +395,13 @@ extern "C" int nnpm_reduce_stats(nnpm_ctx* ctx, nnpm_stats* s) {
 // particle migration
 // ------------------------------------------------------------------------------------------
 #define MIG_HOLE 0xFFFFFFFFu
-enum { MC_HOLES = 16, MC_OVER = 17, MC_NLO = 18, MC_NFILL = 19, MC_ALL = 80 };
+// counter record of one rank: [0, 64) particles packed per destination, then the slots below; MC_REC entries of it
+// are all-gathered (one row per rank) behind the local record
+enum { MC_HOLES = 64, MC_OVER = 65, MC_NLO = 66, MC_NFILL = 67, MC_NP = 68, MC_CAP = 69, MC_REC = 72, MC_ALL = 80 };
+__global__ void k_mig_set(unsigned long long* cnt, unsigned long long np, unsigned long long cap) {
+  cnt[MC_NP] = np;
+  cnt[MC_CAP] = cap;
+}
 
 // owner slab of every particle; leavers are packed into the per-destination segment of `send`,
 // their slot is recorded as a hole and their id set to MIG_HOLE.
@@ -489,30 +453,38 @@ static int migrate_round(nnpm_ctx* ctx, i64* leftover) {
   const int P = ctx->P, r = ctx->r;
   const i64 seg_cap = ctx->mig_cap / P;
   unsigned long long* cnt = (unsigned long long*)ctx->mig_cnt;
-  CK(cudaMemsetAsync(cnt, 0, 80 * 8, ctx->st));
+  CK(cudaMemsetAsync(cnt, 0, MC_ALL * 8, ctx->st));
   const i64 np = ctx->np;
+  k_mig_set<<<1, 1, 0, ctx->st>>>(cnt, (unsigned long long)np, (unsigned long long)ctx->cap);
   if (np) {
     k_mig_classify<<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->pp, ctx->ids, np, g, P, r, seg_cap, ctx->mig_send, ctx->mig_holes, cnt);
     LAUNCHED(ctx);
     KCHECK();
   }
-  // everyone learns everyone's per-destination counts: row s of the matrix = counts sent by rank s
-  CKN(ctx->nccl->AllGather(cnt, cnt + MC_ALL / 1 * 0 + MC_ALL, 24, ncclUint64, COMM, ctx->st));
+  // everyone learns everyone's record: row s of the matrix = counts sent by rank s, its holes, np and capacity
+  CKN(ctx->nccl->AllGather(cnt, cnt + MC_ALL, MC_REC, ncclUint64, COMM, ctx->st));
   LAUNCHED(ctx);
-  i64* h = ctx->h_cnt;  // pinned, >= 24*P entries
-  CK(cudaMemcpyAsync(h, cnt + MC_ALL, (size_t)24 * P * 8, cudaMemcpyDeviceToHost, ctx->st));
+  i64* h = ctx->h_cnt;  // pinned, MC_REC * 64 entries
+  CK(cudaMemcpyAsync(h, cnt + MC_ALL, (size_t)MC_REC * P * 8, cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
-  auto sent = [&](int s, int d) { i64 c = h[24 * s + d]; return c < seg_cap ? c : seg_cap; };
+  auto sent = [&](int s, int d) { i64 c = h[MC_REC * s + d]; return c < seg_cap ? c : seg_cap; };
   i64 over = 0;
-  for (int s = 0; s < P; s++) over += h[24 * s + MC_OVER];
+  for (int s = 0; s < P; s++) over += h[MC_REC * s + MC_OVER];
   *leftover = over;
-  const i64 nholes = h[24 * r + MC_HOLES];
+  // capacity is decided COLLECTIVELY from the gathered records, before any rank posts a send or a receive: a rank
+  // bailing out on its own would leave its peers hanging in NCCL
+  for (int t = 0; t < P; t++) {
+    i64 rx = 0;
+    for (int s = 0; s < P; s++) if (s != t) rx += sent(s, t);
+    const i64 after = h[MC_REC * t + MC_NP] - h[MC_REC * t + MC_HOLES] + rx;
+    if (after > h[MC_REC * t + MC_CAP])
+      return fail(ctx, NNPM_ERR_CAPACITY, "rank %d would hold %lld particles after migration, capacity %lld (every rank stops here; raise part_capacity)",
+                  t, (long long)after, (long long)h[MC_REC * t + MC_CAP]);
+  }
+  const i64 nholes = h[MC_REC * r + MC_HOLES];
   i64 nrecv = 0;
   for (int s = 0; s < P; s++) if (s != r) nrecv += sent(s, r);
   const i64 np_keep = np - nholes;
-  if (np_keep + nrecv > ctx->cap)
-    return fail(ctx, NNPM_ERR_CAPACITY, "rank %d: %lld particles after migration exceed capacity %lld", r,
-                (long long)(np_keep + nrecv), (long long)ctx->cap);
   // data exchange
   CKN(ctx->nccl->GroupStart());
   i64 roff = 0;

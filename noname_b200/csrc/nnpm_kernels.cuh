@@ -1,10 +1,12 @@
 // nnpm_kernels.cuh -- device kernels of the particle-mesh step (sm_100a).
 //
-// Arithmetic follows src/ParticleMesh.jl of the reference operation by operation; the
-// __dmul_rn/__dadd_rn/__dsub_rn/__ddiv_rn intrinsics pin the reference's evaluation order
-// (they are never contracted into FMAs), so every per-particle quantity is bit-identical to
-// the Julia/oracle value for the same inputs.  Only summation order (atomics) and the FFT
-// differ from the reference at rounding level.
+// Arithmetic follows src/ParticleMesh.jl of the reference operation by operation.  In the un-fused operator kernels
+// (k_deposit weights, k_accel, k_interp_acc, k_axpy_rn, k_kick_comoving, k_push) the __dmul_rn/__dadd_rn/__dsub_rn/
+// __ddiv_rn intrinsics pin the reference's evaluation order (they are never contracted into FMAs), so every
+// per-particle quantity is bit-identical to the Julia/oracle value for the same inputs.  The tiled hot kernels relax
+// this in two documented places, both inside the 1e-12 single-step budget: k_deposit_tile sums unit-mass weights in
+// 2^-44 fixed point before the flush, and k_push_tile's gather (cic_grad_gather_fma) forms each corner weight once and
+// accumulates with FMAs (a few ulp).  Summation order (atomics) and the FFT differ from the reference at rounding level.
 #pragma once
 #include <cuda.h>
 #include <cuda_pipeline.h>
@@ -171,6 +173,10 @@ __global__ void k_soa2aos(double* __restrict__ aos, const double* d0, const doub
 __global__ void k_iota_u32(uint32_t* ids, i64 n, u64 first) {
   i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   if (t < n) ids[t] = (uint32_t)(first + (u64)t);
+}
+__global__ void k_ids_to_dest(uint32_t* dest, const uint32_t* ids, uint32_t first, i64 n) {
+  i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t < n) dest[t] = ids[t] - first;
 }
 __global__ void k_u32_to_i64(i64* out, const uint32_t* in, i64 n) {
   i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
@@ -560,8 +566,8 @@ __device__ __forceinline__ void push_finish(const PartPtrs& p, i64 n, const doub
 
 // Global-gather push.  Work items: particles [base, base+count) or, when list != nullptr, the
 // particle indices list[0 .. *list_count) (the tiled push's stragglers).
-template <int RANK, int INTERP, bool COMOVING, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+template <int RANK, int INTERP, bool COMOVING>
+__global__ void __launch_bounds__(256, 2)
 k_push(PartPtrs p, i64 base, i64 count, const uint32_t* __restrict__ list, const u64* __restrict__ list_count, Geom g,
        const double* __restrict__ phi, PushParams pp, i64* __restrict__ red, u64* __restrict__ viol) {
   double mxa = -INFINITY, mxv = -INFINITY, mxp = -INFINITY;
@@ -851,10 +857,8 @@ __device__ __forceinline__ void l2_prefetch_particles(const PartPtrs& p, i64 n0,
   if (hi > lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((unsigned)(hi - lo)) : "memory");
 }
 
-// PD: prefetch depth -- particles whose loads are in flight ahead of the one being processed (1: two
-// register sets alternate; 2: three sets rotate, 12 more registers).
-template <int RANK, bool COMOVING, int MINB, int PD>
-__global__ void __launch_bounds__(256, MINB)
+template <int RANK, bool COMOVING>
+__global__ void __launch_bounds__(256, 2)
 k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g, TileGeom tg, WorkList wl,
             const uint32_t* __restrict__ tile_off, const double* __restrict__ phi, PushParams pp, i64* __restrict__ red,
             uint32_t* __restrict__ slow_list, u64* __restrict__ slow_count, int pf) {
@@ -868,19 +872,7 @@ k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g
   if (n1 > (i64)tile_off[t + 1]) n1 = tile_off[t + 1];
   if (n1 > np) n1 = np;
   if (n0 >= n1) return;  // uniform across the block
-  if (pf == 1) {
-    l2_prefetch_particles<RANK, true>(p, n0, n1);  // this item's x, v
-  } else if (pf > 1 && threadIdx.x < 2 * RANK) {   // the item pf CTAs ahead (about one wave): in L2 before its CTA starts
-    const unsigned wa = blockIdx.x + (unsigned)pf;
-    if (wa < *wl.count) {
-      const int ta = (int)wl.tile[wa];
-      const i64 a0 = wl.beg[wa];
-      i64 a1 = a0 + NNPM_CHUNK;
-      if (a1 > (i64)tile_off[ta + 1]) a1 = tile_off[ta + 1];
-      if (a1 > np) a1 = np;
-      l2_prefetch_particles<RANK, true>(p, a0, a1);
-    }
-  }
+  if (pf) l2_prefetch_particles<RANK, true>(p, n0, n1);  // this item's x, v
   const int ttx = t % tg.ntx, tty = (t / tg.ntx) % tg.nty, ttz = t / (tg.ntx * tg.nty);
   const int N1 = (int)g.N1, N2 = (int)g.N2, N3 = (int)g.N3;
   const int ti0 = ttx * tg.tx, tj0 = tty * tg.ty, tk0 = ttz * tg.tz;  // tk0: plane within the slab
@@ -940,9 +932,7 @@ k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g
   };
   int q = threadIdx.x;
   double xa[3] = {0.0, 0.0, 0.0}, va[3] = {0.0, 0.0, 0.0}, xb[3] = {0.0, 0.0, 0.0}, vb[3] = {0.0, 0.0, 0.0};
-  double xc[3] = {0.0, 0.0, 0.0}, vc[3] = {0.0, 0.0, 0.0};
   fetch(xa, va, q);
-  if (PD == 2) fetch(xb, vb, q + 256);
   if (interior) {
     __syncthreads();        // mbarrier initialised by thread 0 before anyone polls it
     mbar_wait(&mbar, 0);
@@ -983,454 +973,18 @@ k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g
       push_finish_fast<RANK, COMOVING>(p, n0 + q, x, v, pa, pp, ra, mxa, mxv, mxp);
     }
   };
-  if (PD == 2) {
-    while (q < cnt) {
-      fetch(xc, vc, q + 512);
-      process(xa, va, q);
-      q += 256;
-      if (q >= cnt) break;
-      fetch(xa, va, q + 512);
-      process(xb, vb, q);
-      q += 256;
-      if (q >= cnt) break;
-      fetch(xb, vb, q + 512);
-      process(xc, vc, q);
-      q += 256;
-    }
-  } else {
-    while (q < cnt) {
-      fetch(xb, vb, q + 256);
-      process(xa, va, q);
-      q += 256;
-      if (q >= cnt) break;
-      fetch(xa, va, q + 256);
-      process(xb, vb, q);
-      q += 256;
-    }
+  while (q < cnt) {
+    fetch(xb, vb, q + 256);
+    process(xa, va, q);
+    q += 256;
+    if (q >= cnt) break;
+    fetch(xa, va, q + 256);
+    process(xb, vb, q);
+    q += 256;
   }
   block_max3(mxa, mxv, mxp, red);
 }
 
-// ------------------------------------------------------------------------------------------
-// Persistent tiled push.  Per-particle arithmetic is k_push_tile's, statement for statement; what
-// changes is the schedule.  k_push_tile starts one CTA per work item: every item pays the phi box
-// load (51 KB, ~2 us), the first particle's load latency, a block reduction and three global
-// atomics, with only one other CTA on the SM to cover it (ncu: 25 % occupancy, long_scoreboard and
-// barrier stalls).  Here 2 CTAs per SM stay resident and walk the work list (in list order from a global
-// counter by default -- see "Schedule" below; statically round-robin with flags & 4 == 0):
-//   * two box buffers: the box of item i+1 is staged (one TMA tensor copy for interior tiles, cp.async
-//     rows for tiles whose box wraps) while item i is processed;
-//   * the particles of item i+1 are prefetched into L2 at the start of item i (flags & 8: the whole item by
-//     one bulk prefetch per array, else its first 256 particles line by line) and its first particle is
-//     loaded into registers before the end-of-item barrier, so the loop of item i+1 starts on resident data;
-//   * work-list entries are read two items ahead, so no descriptor load is ever waited on;
-//   * one block reduction per CTA instead of one per item.
-// Measured at 1024^3: 24.9 ms against 24.5 ms for k_push_tile with the same L2 prefetch -- the
-// prologue it removes was being covered by the SM's other CTA; k_push_tile stays the default ("push_persist").
-// ------------------------------------------------------------------------------------------
-#define NNPM_BOXD(RK) ((NNPM_BX * NNPM_BY * ((RK) == 3 ? NNPM_BZ : 1) + 15) & ~15)  // doubles per box buffer (128 B multiple)
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-template <int RANK, bool COMOVING, int NT>
-__global__ void __launch_bounds__(NT, 2)
-k_push_tile_p(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g, TileGeom tg, WorkList wl,
-              const uint32_t* __restrict__ tile_off, const double* __restrict__ phi, PushParams pp, i64* __restrict__ red,
-              uint32_t* __restrict__ slow_list, u64* __restrict__ slow_count, int flags, unsigned* __restrict__ work_ctr) {
-  extern __shared__ __align__(128) double box[];  // 2 x [BZ][BY][BX], NNPM_BOXD doubles apart
-  __shared__ __align__(8) unsigned long long mbar[2];
-  __shared__ unsigned s_w[2];  // dynamic schedule: work index thread 0 grabbed for the next-but-one item
-  constexpr int BX = NNPM_BX, BY = NNPM_BY, BZ = (RANK == 3) ? NNPM_BZ : 1, BXY = BX * BY, BOXD = NNPM_BOXD(RANK);
-  const unsigned nwork = *wl.count;
-  const unsigned G = gridDim.x;
-  const int tid = threadIdx.x;
-  const int N1 = (int)g.N1, N2 = (int)g.N2, N3 = (int)g.N3;
-  // work item: tile t (< 0: none), particles [n0, n0 + cnt)
-  auto load_item = [&](unsigned w, int& t, i64& n0, int& cnt) {
-    t = -1; n0 = 0; cnt = 0;
-    if (w < nwork) {
-      t = (int)wl.tile[w];
-      n0 = wl.beg[w];
-      i64 n1 = n0 + NNPM_CHUNK;
-      const i64 te = tile_off[t + 1];
-      if (n1 > te) n1 = te;
-      if (n1 > np) n1 = np;
-      cnt = n1 > n0 ? (int)(n1 - n0) : 0;
-    }
-  };
-  // stage the phi box of tile t into buffer b; returns whether it went through the TMA engine
-  // (completion on mbar[b]) or through this thread's cp.async group (always committed, maybe empty)
-  auto stage = [&](int t, int b) -> bool {
-    const int ttx = t % tg.ntx, tty = (t / tg.ntx) % tg.nty, ttz = t / (tg.ntx * tg.nty);
-    const int bx0 = ttx * tg.tx - NNPM_TH - 1, by0 = tty * tg.ty - NNPM_TH - 1;
-    const int bz0 = (RANK == 3) ? ttz * tg.tz - NNPM_TH - 1 + g.glo : g.glo;  // local plane of the box origin
-    const bool interior = bx0 >= 0 && bx0 + BX - 1 <= N1 && by0 >= 0 && by0 + BY <= N2 &&
-                          (RANK == 2 || g.glo != 0 || (bz0 >= 0 && bz0 + BZ <= N3));
-    double* dstb = box + b * BOXD;
-    if (interior) {
-      if (tid == 0) {
-        if (!(flags & 1)) fence_proxy_async_smem();  // the buffer was last touched through the generic proxy
-        mbar_expect_tx(&mbar[b], (unsigned)(BX * BY * BZ * sizeof(double)));
-        tma_load_3d(dstb, &tmap, bx0, by0, bz0, &mbar[b]);
-      }
-    } else {
-      const int lane = tid & 31, warp = tid >> 5;
-      const int gi0 = wrap_small(bx0 + lane, N1);
-      const int gi1 = wrap_small(bx0 + lane + 32, N1);
-      for (int row = warp; row < BY * BZ; row += NT / 32) {
-        const int byi = row % BY, bzi = row / BY;  // compile-time divisors
-        const int gj = wrap_small(by0 + byi, N2);
-        int lp = g.glo;
-        bool valid = true;
-        if (RANK == 3) {
-          lp = bz0 + bzi;
-          if (g.glo) valid = lp >= 0 && lp < g.nplanes;
-          else lp = wrap_small(lp, N3);
-        }
-        const double* src = phi + g.plane * (i64)lp + (unsigned)((int)g.rowp * gj);
-        double* dst = dstb + row * BX;
-        if (valid) {
-          __pipeline_memcpy_async(dst + lane, src + gi0, 8);
-          if (lane + 32 < BX - 1) __pipeline_memcpy_async(dst + lane + 32, src + gi1, 8);
-        } else {
-          dst[lane] = 0.0;
-          if (lane + 32 < BX - 1) dst[lane + 32] = 0.0;
-        }
-      }
-    }
-    __pipeline_commit();
-    return interior;
-  };
-
-  // Schedule.  Static (flags & 4 == 0): item blockIdx.x + i * G.  Dynamic: the first three rounds are static,
-  // then thread 0 takes indices from a global counter -- items start in list order across the GPU, as under
-  // the hardware block scheduler, so concurrently staged boxes stay neighbours (shared halo planes hit L2)
-  // however far the CTAs drift apart.  The index for round i+3 is fetched during round i.
-  const bool dyn = (flags & 4) != 0;
-  unsigned wf = blockIdx.x + 2 * G;  // index of the next-but-one item
-  unsigned round = 0;
-  int ct, ccnt, nt, ncnt, ft, fcnt;  // current, next and next-but-one item
-  i64 cn0, nn0, fn0;
-  load_item(blockIdx.x, ct, cn0, ccnt);
-  if (ct < 0) return;  // uniform: fewer items than CTAs
-  load_item(blockIdx.x + G, nt, nn0, ncnt);
-  if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
-  __syncthreads();
-  unsigned phase = 0;  // bit b: parity the next wait on mbar[b] expects
-  int b = 0;
-  bool cur_tma = stage(ct, 0);
-
-  const double gfac = -0.5 * g.fN1;
-  const double ra = 1.0 / pp.a;
-  const unsigned fx = tg.tx + 2 * NNPM_TH, fy = tg.ty + 2 * NNPM_TH, fz = tg.tz + 2 * NNPM_TH;
-  double mxa = -INFINITY, mxv = -INFINITY, mxp = -INFINITY;
-  double xa[3] = {0.0, 0.0, 0.0}, va[3] = {0.0, 0.0, 0.0}, xb[3] = {0.0, 0.0, 0.0}, vb[3] = {0.0, 0.0, 0.0};
-  auto load6 = [&](double* x, double* v, i64 idx) {
-    x[0] = p.x[0][idx]; x[1] = p.x[1][idx]; v[0] = p.v[0][idx]; v[1] = p.v[1][idx];
-    if (RANK == 3) { x[2] = p.x[2][idx]; v[2] = p.v[2][idx]; }
-  };
-  if (tid < ccnt) load6(xa, va, cn0 + tid);
-
-  for (;;) {
-    load_item(wf, ft, fn0, fcnt);  // consumed at the top of the next iteration
-    unsigned grabbed = 0;
-    if (dyn && tid == 0) grabbed = atomicAdd(work_ctr, 1u) + 3u * G;  // published before this round's barrier
-    bool nxt_tma = false;
-    if (nt >= 0) nxt_tma = stage(nt, b ^ 1);
-    else __pipeline_commit();
-    // pull the next item's first 256 particles into L2: one 128-byte line per thread and array
-    if (flags & 8) {
-      if (nt >= 0) l2_prefetch_particles<RANK, true>(p, nn0, nn0 + ncnt);  // the whole next item, one bulk prefetch per array
-    } else if (nt >= 0 && tid < 2 * RANK * 16 && !(flags & 2)) {  // 16 lines of 16 doubles cover 256 particles; NT > 256 leaves the rest to the loads
-      const int a = tid >> 4, l = tid & 15;
-      const double* base = p.x[0];  // select chain: a dynamic index would put PartPtrs on the stack
-#pragma unroll
-      for (int d = 1; d < RANK; d++) base = (a == d) ? p.x[d] : base;
-#pragma unroll
-      for (int d = 0; d < RANK; d++) base = (a == RANK + d) ? p.v[d] : base;
-      if (l * 16 < ncnt) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + nn0 + l * 16));
-    }
-    // box of the current item: its cp.async group is the last but one of this thread
-    __pipeline_wait_prior(1);
-    if (cur_tma) {
-      mbar_wait(&mbar[b], (phase >> b) & 1u);
-      phase ^= 1u << b;
-    } else {
-      __syncthreads();
-    }
-    const double* __restrict__ cbox = box + b * BOXD;
-    const int ttx = ct % tg.ntx, tty = (ct / tg.ntx) % tg.nty, ttz = ct / (tg.ntx * tg.nty);
-    const int oi = ttx * tg.tx - NNPM_TH, oj = tty * tg.ty - NNPM_TH, ok = (int)g.kz0 + ttz * tg.tz - NNPM_TH;  // mesh cell of halo cell 0
-    auto fetch = [&](double* x, double* v, int qn) {
-      if (qn < ccnt) load6(x, v, cn0 + qn);
-    };
-    auto process = [&](double* x, double* v, int q) {
-      double pa[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-      for (int d = 0; d < RANK; d++) {
-        if (COMOVING) x[d] = __dadd_rn(x[d], __dmul_rn(pp.c0, v[d]));
-        x[d] = wrap01_sel(x[d]);
-      }
-      int i, j, k = 0;
-      double dx, dy, dz = 0.0;
-      cell_fast(x[0], g.fN1, i, dx);
-      cell_fast(x[1], g.fN2, j, dy);
-      const unsigned ri = (unsigned)tile_rel(i, oi, N1), rj = (unsigned)tile_rel(j, oj, N2);
-      unsigned rk = 0;
-      bool fast = ri < fx && rj < fy;
-      if (RANK == 3) {
-        cell_fast(x[2], g.fN3, k, dz);
-        rk = (unsigned)tile_rel(k, ok, N3);
-        fast = fast && rk < fz;
-      }
-      if (!fast) {
-        slow_list[atomicAdd(slow_count, 1ull)] = (uint32_t)(cn0 + q);
-      } else {
-        const double* b0 = cbox + (rk * BXY + rj * BX + ri);
-        if (RANK == 2) cic_grad_gather_fma<2>([&](int a, int bb, int) { return b0[bb * BX + a]; }, dx, dy, 0.0, gfac, pa);
-        else cic_grad_gather_fma<3>([&](int a, int bb, int c) { return b0[c * BXY + bb * BX + a]; }, dx, dy, dz, gfac, pa);
-        push_finish_fast<RANK, COMOVING>(p, cn0 + q, x, v, pa, pp, ra, mxa, mxv, mxp);
-      }
-    };
-    int q = tid;
-    while (q < ccnt) {
-      fetch(xb, vb, q + NT);
-      process(xa, va, q);
-      q += NT;
-      if (q >= ccnt) break;
-      fetch(xa, va, q + NT);
-      process(xb, vb, q);
-      q += NT;
-    }
-    if (nt < 0) break;
-    if (tid < ncnt) load6(xa, va, nn0 + tid);  // L2 hits (prefetched above), in flight across the barrier and the staging
-    if (dyn && tid == 0) s_w[round & 1] = grabbed;
-    __syncthreads();  // every thread is done with buffer b before the next iteration's staging overwrites it
-    wf = dyn ? s_w[round & 1] : wf + G;
-    round++;
-    ct = nt; cn0 = nn0; ccnt = ncnt;
-    nt = ft; nn0 = fn0; ncnt = fcnt;
-    cur_tma = nxt_tma;
-    b ^= 1;
-  }
-  block_max3(mxa, mxv, mxp, red);
-}
-// ------------------------------------------------------------------------------------------
-// Tiled push with the particle streams on the TMA engine.  Same arithmetic as k_push_tile; what changes
-// is who talks to HBM: a dedicated DMA warp streams the work item's six arrays through two
-// shared-memory stages of NNPM_PS particles with cp.async.bulk (global -> shared, mbarrier
-// completion) and writes the updated x, v back with cp.async.bulk (shared -> global), while the eight
-// compute warps only ever touch shared memory.  Register loads keep too few bytes in flight per SM
-// for this kernel (ncu: 57 % of DRAM peak at 25 % occupancy, long_scoreboard stalls); the bulk
-// copies keep ~48 KB per CTA in flight regardless of occupancy.
-//   Bulk copies move 16-byte units: stages start at even particle indices; a work item whose first
-//   (last) particle has an odd (even) index shares a unit with the neighbouring item -- those single
-//   edge elements are excluded from the bulk store and written by ordinary stores.
-//   Particles that left the tile's box keep their original values in the stage (the bulk store writes
-//   them back unchanged) and go to the slow list, as in k_push_tile.
-// ------------------------------------------------------------------------------------------
-#define NNPM_PS 512  // particles per stage: 6 arrays x 4 KB
-__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-template <int RANK, bool COMOVING>
-__global__ void __launch_bounds__(288, 2)
-k_push_tma(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g, TileGeom tg, WorkList wl,
-           const uint32_t* __restrict__ tile_off, const double* __restrict__ phi, PushParams pp, i64* __restrict__ red,
-           uint32_t* __restrict__ slow_list, u64* __restrict__ slow_count) {
-  extern __shared__ __align__(128) double sm_push[];  // box [BZ][BY][BX], then stages [2][2*RANK][NNPM_PS]
-  __shared__ __align__(8) unsigned long long mbar, full[2], done[2];
-  constexpr int BX = NNPM_BX, BY = NNPM_BY, BZ = (RANK == 3) ? NNPM_BZ : 1, BXY = BX * BY, NA = 2 * RANK, S = NNPM_PS;
-  double* box = sm_push;
-  double* stage = sm_push + ((BXY * BZ + 15) & ~15);
-  if (blockIdx.x >= *wl.count) return;  // the grid is sized for the worst case
-  const int t = (int)wl.tile[blockIdx.x];
-  const i64 n0 = wl.beg[blockIdx.x];
-  i64 n1 = n0 + NNPM_CHUNK;
-  if (n1 > (i64)tile_off[t + 1]) n1 = tile_off[t + 1];
-  if (n1 > np) n1 = np;
-  if (n0 >= n1) return;  // uniform across the block
-  const int ttx = t % tg.ntx, tty = (t / tg.ntx) % tg.nty, ttz = t / (tg.ntx * tg.nty);
-  const int N1 = (int)g.N1, N2 = (int)g.N2, N3 = (int)g.N3;
-  const int ti0 = ttx * tg.tx, tj0 = tty * tg.ty, tk0 = ttz * tg.tz;
-  const int bx0 = ti0 - NNPM_TH - 1, by0 = tj0 - NNPM_TH - 1;
-  const int bz0 = (RANK == 3) ? tk0 - NNPM_TH - 1 + g.glo : g.glo;
-  const bool interior = bx0 >= 0 && bx0 + BX - 1 <= N1 && by0 >= 0 && by0 + BY <= N2 &&
-                        (RANK == 2 || g.glo != 0 || (bz0 >= 0 && bz0 + BZ <= N3));
-  const i64 base = n0 & ~1ll;                       // even: 16-byte aligned in every array
-  const int span = (int)(n1 - base);                // particles from base to the end of the item
-  const int nst = (span + S - 1) / S;               // stages
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    mbar_init(&mbar, 1);
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-    mbar_init(&done[0], 256); mbar_init(&done[1], 256);
-  }
-  __syncthreads();
-  const double* gin[6] = {p.x[0], p.x[1], RANK == 3 ? p.x[2] : p.v[0], RANK == 3 ? p.v[0] : p.v[1], p.v[1], p.v[2]};
-  double* gout[6] = {p.x[0], p.x[1], RANK == 3 ? p.x[2] : p.v[0], RANK == 3 ? p.v[0] : p.v[1], p.v[1], p.v[2]};
-  // array a of the stage: a < RANK -> x[a], else v[a - RANK]
-  auto stage_len = [&](int s) { int l = span - s * S; l = l < S ? l : S; return (l + 1) & ~1; };  // even, may read 1 past n1
-  if (warp == 8) {
-    // ------------------------------------------------ DMA warp (lane 0 issues, the warp stays converged)
-    if (lane == 0) {
-      if (interior) {
-        mbar_expect_tx(&mbar, (unsigned)(BX * BY * BZ * sizeof(double)));
-        tma_load_3d(box, &tmap, bx0, by0, bz0, &mbar);
-      }
-      auto load_stage = [&](int s) {
-        const int b = s & 1, len = stage_len(s);
-        mbar_expect_tx(&full[b], (unsigned)(NA * len * 8));
-#pragma unroll
-        for (int a = 0; a < NA; a++) bulk_load(stage + (b * NA + a) * S, gin[a] + base + (i64)s * S, (unsigned)len * 8u, &full[b]);
-      };
-      load_stage(0);
-      if (nst > 1) load_stage(1);
-      unsigned dph[2] = {0u, 0u};
-      for (int s = 0; s < nst; s++) {
-        const int b = s & 1;
-        mbar_wait(&done[b], dph[b]);   // all 256 compute threads finished stage s (their writes fenced)
-        dph[b] ^= 1u;
-        // bulk-store the units fully inside [n0, n1)
-        i64 lo = base + (i64)s * S, hi = lo + S;
-        if (lo < n0) lo = n0 + 1;                       // n0 odd: unit (n0-1, n0) is shared with the previous item
-        if (hi > n1) hi = n1 & ~1ll;                    // n1 odd: unit (n1-1, n1) is shared with the next item
-        if (hi > lo) {
-          const int off = (int)(lo - (base + (i64)s * S));
-#pragma unroll
-          for (int a = 0; a < NA; a++) bulk_store(gout[a] + lo, stage + (b * NA + a) * S + off, (unsigned)(hi - lo) * 8u);
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        if (s + 2 < nst) {
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage may be overwritten now
-          load_stage(s + 2);
-        }
-      }
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
-    return;
-  }
-  // ---------------------------------------------------- compute warps (256 threads)
-  if (!interior) {
-    int gi0 = wrap_small(bx0 + lane, N1);
-    int gi1 = wrap_small(bx0 + lane + 32, N1);
-    for (int row = warp; row < BY * BZ; row += 8) {
-      const int byi = row % BY, bzi = row / BY;  // compile-time divisors
-      const int gj = wrap_small(by0 + byi, N2);
-      int lp = g.glo;
-      bool valid = true;
-      if (RANK == 3) {
-        lp = bz0 + bzi;
-        if (g.glo) valid = lp >= 0 && lp < g.nplanes;
-        else lp = wrap_small(lp, N3);
-      }
-      const double* src = phi + g.plane * (i64)lp + (unsigned)((int)g.rowp * gj);
-      double* dst = box + row * BX;
-      if (valid) {
-        __pipeline_memcpy_async(dst + lane, src + gi0, 8);
-        if (lane + 32 < BX - 1) __pipeline_memcpy_async(dst + lane + 32, src + gi1, 8);
-      } else {
-        dst[lane] = 0.0;
-        if (lane + 32 < BX - 1) dst[lane + 32] = 0.0;
-      }
-    }
-    __pipeline_commit();
-    __pipeline_wait_prior(0);
-    asm volatile("bar.sync 1, 256;" ::: "memory");  // compute warps only (the DMA warp never joins)
-  } else {
-    mbar_wait(&mbar, 0);
-  }
-  const double gfac = -0.5 * g.fN1;
-  const double ra = 1.0 / pp.a;
-  const int oi = ti0 - NNPM_TH, oj = tj0 - NNPM_TH, ok = (int)g.kz0 + tk0 - NNPM_TH;
-  const unsigned fx = tg.tx + 2 * NNPM_TH, fy = tg.ty + 2 * NNPM_TH, fz = tg.tz + 2 * NNPM_TH;
-  double mxa = -INFINITY, mxv = -INFINITY, mxp = -INFINITY;
-  unsigned fph[2] = {0u, 0u};
-  for (int s = 0; s < nst; s++) {
-    const int b = s & 1;
-    double* sx = stage + b * NA * S;
-    mbar_wait(&full[b], fph[b]);
-    fph[b] ^= 1u;
-#pragma unroll
-    for (int h = 0; h < S / 256; h++) {
-      const int q = threadIdx.x + 256 * h;
-      const i64 n = base + (i64)s * S + q;
-      if (n < n0 || n >= n1) continue;
-      double x[3] = {0.0, 0.0, 0.0}, v[3] = {0.0, 0.0, 0.0}, pa[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-      for (int d = 0; d < RANK; d++) {
-        x[d] = sx[d * S + q];
-        v[d] = sx[(RANK + d) * S + q];
-        if (COMOVING) x[d] = __dadd_rn(x[d], __dmul_rn(pp.c0, v[d]));
-        x[d] = wrap01_sel(x[d]);
-      }
-      int i, j, k = 0;
-      double dx, dy, dz = 0.0;
-      cell_fast(x[0], g.fN1, i, dx);
-      cell_fast(x[1], g.fN2, j, dy);
-      const unsigned ri = (unsigned)tile_rel(i, oi, N1), rj = (unsigned)tile_rel(j, oj, N2);
-      unsigned rk = 0;
-      bool fast = ri < fx && rj < fy;
-      if (RANK == 3) {
-        cell_fast(x[2], g.fN3, k, dz);
-        rk = (unsigned)tile_rel(k, ok, N3);
-        fast = fast && rk < fz;
-      }
-      if (!fast) {
-        slow_list[atomicAdd(slow_count, 1ull)] = (uint32_t)n;
-        continue;
-      }
-      const double* b0 = box + (rk * BXY + rj * BX + ri);
-      if (RANK == 2) cic_grad_gather_fma<2>([&](int a, int bb, int) { return b0[bb * BX + a]; }, dx, dy, 0.0, gfac, pa);
-      else cic_grad_gather_fma<3>([&](int a, int bb, int c) { return b0[c * BXY + bb * BX + a]; }, dx, dy, dz, gfac, pa);
-      const bool edge = (n == n0 && (n0 & 1)) || (n == n1 - 1 && (n1 & 1));  // unit shared with a neighbouring item
-#pragma unroll
-      for (int d = 0; d < RANK; d++) {
-        double vn, xn;
-        if (COMOVING) {
-          const double vmid = __dadd_rn(v[d], __dmul_rn(__dmul_rn(pa[d], pp.dt), 0.5));
-          const double tt = __dadd_rn(__dmul_rn(-vmid, pp.hub), div_by_scalar(pa[d], pp.a, ra));
-          vn = __dadd_rn(v[d], __dmul_rn(tt, pp.dt));
-          xn = wrap01_sel(__dadd_rn(x[d], __dmul_rn(pp.c2, vn)));
-        } else {
-          const double x1 = __dadd_rn(x[d], __dmul_rn(pp.c1, v[d]));
-          vn = __dadd_rn(v[d], __dmul_rn(pp.dt, pa[d]));
-          xn = __dadd_rn(x1, __dmul_rn(pp.c1, vn));
-        }
-        sx[d * S + q] = xn;
-        sx[(RANK + d) * S + q] = vn;
-        if (edge) { p.x[d][n] = xn; p.v[d][n] = vn; }
-        mxa = dmax_nn(mxa, fabs(vn));
-        mxv = dmax_nn(mxv, vn);
-        mxp = dmax_nn(mxp, pa[d]);
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // stage writes -> bulk store reads
-    mbar_arrive(&done[b]);
-  }
-  // block_max3 uses __syncthreads: not available with the DMA warp gone -> named barrier version
-  {
-    __shared__ i64 smax[3];
-    if (threadIdx.x < 3) smax[threadIdx.x] = (i64)0x8000000000000000ull;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const i64 ka = warp_max_key(ord_encode(mxa)), kb = warp_max_key(ord_encode(mxv)), kc = warp_max_key(ord_encode(mxp));
-    if (lane == 0) {
-      atomicMax(&smax[0], ka);
-      atomicMax(&smax[1], kb);
-      atomicMax(&smax[2], kc);
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (threadIdx.x < 3) atomicMax(&red[threadIdx.x], smax[threadIdx.x]);
-  }
-}
 #undef PHI
 
 // ------------------------------------------------------------------------------------------

@@ -96,7 +96,7 @@ extern "C" int nnpm_power_spectrum(nnpm_ctx* ctx, double* karray_out, double* po
   k_delta<<<nblk(ncl, 256), 256, 0, ctx->st>>>(own, g, mean);
   LAUNCHED(ctx);
   double2* T = nullptr;
-  CKR(fft_forward(ctx, &T, true, nullptr));
+  CKR(fft_forward(ctx, &T, true, nullptr, false));
   const double ncell = (double)g.N1 * (double)g.N2 * (double)g.N3;
   const double fac = 1.0 / (ncell * ncell);  // prod(box)/prod(dims)^2 with box = 1  :77
   k_pk_bin<<<148 * 2, 256, (size_t)2 * lenk * 8, ctx->st>>>(T, ctx->icn, ctx->njl, ctx->njl * ctx->r, g, dk, lenk, fac,

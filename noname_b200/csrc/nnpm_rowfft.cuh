@@ -1,0 +1,213 @@
+// nnpm_rowfft.cuh -- x passes of the 3-D transform: batched real-to-complex / complex-to-real FFTs along the
+// contiguous mesh rows, in place in the padded r2c layout (row = N1 doubles + 2 of padding = N1/2+1 complex).
+// Replaces cuFFT's batched 1-D D2Z / Z2D plans in compute_potential (src/ParticleMesh.jl:481, :502): the library
+// kernels reach 0.72-0.75 of the measured HBM copy peak at 1024^3 (profiles/r01_ncu_summary.txt).
+//
+// A real transform of length N = 2M is one complex transform of length M on z[n] = x[2n] + i x[2n+1] plus an
+// O(M) butterfly between bins k and M-k:
+//   forward   X[k]   = E[k] + W_N^k O[k],  E[k] = (Z[k] + conj Z[M-k]) / 2,  O[k] = -i (Z[k] - conj Z[M-k]) / 2,  k = 0 .. M
+//   inverse   Z'[k]  = (X[k] + conj X[M-k]) + i conj(W_N^k) (X[k] - conj X[M-k]),   z' = IDFT_M(Z') = N x   (unnormalised,
+//             like cuFFT's Z2D: the 1/(N1 N2 N3) sits in the Green's-function factor of the z pass)
+//
+// Data movement: every CTA owns a shared-memory slot per row (C = 4 rows at a time); the rows arrive by ONE bulk
+// asynchronous copy each (cp.async.bulk, 8 KB at N1 = 1024, completion on an mbarrier) and leave by one bulk copy
+// each -- the threads never touch global memory.  A slot holds the row, then (aliased) the padded exchange buffer of
+// the two register-resident radix passes (ZDif of nnpm_zfft.cuh), then the spectrum.  CTAs are small (4 warps, 51 KB
+// at N1 = 1024) and persistent, four per SM, so the load / store phases of one CTA run under the arithmetic of its
+// siblings: ~128 KB per SM in flight without any intra-CTA pipelining.
+#pragma once
+
+__device__ __forceinline__ void bulk_load_1d(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+
+struct RowFftArgs {
+  double* mesh;        // first row
+  i64 rowp;            // row pitch in doubles (2 * (N1/2 + 1))
+  i64 nrows;           // rows to transform (rows are contiguous: row r at mesh + r * rowp)
+  const double2* twM;  // W_M^m, m < M
+  const double2* twN;  // W_N^k, k < M
+};
+
+// complex FFT of length M = R1 * R2 on the C rows held in the slots, natural order in and out, in place.
+//   pass A  thread j (< R2): elements j + r*R2 -> radix-R1 DIF -> exchange E[q*(R2+1) + j]   (padded: both sides of
+//           the exchange are bank-conflict free for 16-byte elements)
+//   pass B  thread j (< R1): E[j*(R2+1) + r] * W_M^(r j) -> radix-R2 DIF -> element j + q*R1
+template <int R1, int R2, int SIGN>
+__device__ __forceinline__ void rowfft_core(double2* slot, const double2* stwM, int j) {
+  constexpr int RM = R1 > R2 ? R1 : R2, B1 = zf_log2(R1), B2 = zf_log2(R2), EST = R2 + 1;
+  double2 v[RM];
+  if (j < R2) {
+#pragma unroll
+    for (int r = 0; r < R1; r++) v[r] = slot[j + r * R2];
+    ZDif<R1, 0, SIGN>::run(v);
+  }
+  __syncthreads();  // the row is in registers: the slot becomes the exchange buffer
+  if (j < R2) {
+#pragma unroll
+    for (int q = 0; q < R1; q++) slot[q * EST + j] = v[zf_brev(q, B1)];
+  }
+  __syncthreads();
+  if (j < R1) {
+#pragma unroll
+    for (int r = 0; r < R2; r++) v[r] = slot[j * EST + r];
+#pragma unroll
+    for (int r = 1; r < R2; r++) {
+      const double2 w = stwM[r * j];
+      v[r] = zmul(v[r], w.x, SIGN < 0 ? w.y : -w.y);
+    }
+    ZDif<R2, 0, SIGN>::run(v);
+  }
+  __syncthreads();  // the exchange is consumed: the slot takes the result in natural order
+  if (j < R1) {
+#pragma unroll
+    for (int q = 0; q < R2; q++) slot[j + q * R1] = v[zf_brev(q, B2)];
+  }
+  __syncthreads();
+}
+
+// INVERSE = false: real rows -> half spectrum (r2c, forward sign);  true: half spectrum -> real rows (c2r, unnormalised)
+template <int R1, int R2, bool INVERSE>
+__global__ void __launch_bounds__(4 * (R1 > R2 ? R1 : R2), (R1 * R2 > 512 ? 2 : R1 * R2 == 512 ? 3 : 4))
+k_rowfft(RowFftArgs a) {
+  constexpr int C = 4, M = R1 * R2, RM = R1 > R2 ? R1 : R2;
+  constexpr int SLOT = R1 * (R2 + 1) > M + 1 ? R1 * (R2 + 1) : M + 1;   // complex elements per row slot
+  extern __shared__ __align__(128) unsigned char rf_smem[];
+  double2* slots = (double2*)rf_smem;       // [C][SLOT]
+  double2* stwM = slots + C * SLOT;         // [M]
+  double2* stwN = stwM + M;                 // [M]
+  __shared__ __align__(8) unsigned long long full;
+  const int tid = threadIdx.x, c = tid / RM, j = tid % RM;
+  for (int t = tid; t < M; t += blockDim.x) {
+    stwM[t] = __ldg(a.twM + t);
+    stwN[t] = __ldg(a.twN + t);
+  }
+  if (tid == 0) mbar_init(&full, 1);
+  __syncthreads();
+  constexpr unsigned IN_BYTES = INVERSE ? (M + 1) * 16u : M * 16u;
+  constexpr unsigned OUT_BYTES = INVERSE ? M * 16u : (M + 1) * 16u;
+  const i64 ngroups = (a.nrows + C - 1) / C;
+  unsigned phase = 0u;
+  double2* slot = slots + c * SLOT;
+  for (i64 g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const i64 row0 = g * C;
+    const int nr = (int)((a.nrows - row0) < C ? (a.nrows - row0) : C);
+    if (tid == 0) {
+      // the previous group's bulk stores must have finished READING the slots before they are refilled
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      mbar_expect_tx(&full, (unsigned)nr * IN_BYTES);
+      for (int r = 0; r < nr; r++) bulk_load_1d(slots + r * SLOT, a.mesh + (row0 + r) * a.rowp, IN_BYTES, &full);
+    }
+    mbar_wait(&full, phase);
+    phase ^= 1u;
+    if (INVERSE) {
+      // Z'[k] = (X[k] + conj X[M-k]) + i conj(W_N^k) (X[k] - conj X[M-k]), pairs (k, M-k) in place; k = 0 also consumes X[M]
+      for (int k = j; k <= M / 2; k += RM) {
+        double2 xa = slot[k], xb = slot[M - k];
+        if (k == 0) { xa.y = 0.0; xb.y = 0.0; }                      // the DC and Nyquist bins of a real signal are real
+        const double2 w = stwN[k];                                   // W_N^k = (wr, wi)
+        const double2 e = make_double2(xa.x + xb.x, xa.y - xb.y);    // X[k] + conj X[M-k]
+        const double2 d = make_double2(xa.x - xb.x, xa.y + xb.y);    // X[k] - conj X[M-k]
+        // i * conj(w) * d = i (wr - i wi)(dx + i dy) = i [(wr dx + wi dy) + i (wr dy - wi dx)]
+        const double tr = w.x * d.x + w.y * d.y, ti = w.x * d.y - w.y * d.x;
+        const double2 za = make_double2(e.x - ti, e.y + tr);
+        // bin M-k: X[M-k] + conj X[k] = conj(e);  X[M-k] - conj X[k] = -conj(d);  W_N^(M-k) = -conj(W_N^k)
+        //   i conj(-conj w) (-conj d) = i w conj(d) = i [(wr dx + wi dy) + i (wi dx - wr dy)] = i (tr - i ti)
+        const double2 zb = make_double2(e.x + ti, -e.y + tr);
+        slot[k] = za;
+        if (k != 0 && k != M - k) slot[M - k] = zb;
+      }
+      __syncthreads();
+      rowfft_core<R1, R2, +1>(slot, stwM, j);
+    } else {
+      rowfft_core<R1, R2, -1>(slot, stwM, j);
+      // X[k] = E + W_N^k O,  X[M-k] = conj(E) - conj(W_N^k) conj(O) ... evaluated from Z[k], Z[M-k] in place
+      for (int k = j; k <= M / 2; k += RM) {
+        const double2 za = slot[k], zb = slot[k == 0 ? 0 : M - k];
+        const double2 w = stwN[k];
+        const double2 e = make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y));   // E[k]
+        const double2 o = make_double2(0.5 * (za.y + zb.y), -0.5 * (za.x - zb.x));  // O[k] = -i (Z[k] - conj Z[M-k]) / 2
+        const double tr = w.x * o.x - w.y * o.y, ti = w.x * o.y + w.y * o.x;        // W_N^k O[k]
+        slot[k] = make_double2(e.x + tr, e.y + ti);
+        // X[M-k] = conj(E[k]) - conj(W_N^k O[k])   (E[M-k] = conj E[k], O[M-k] = conj O[k], W_N^(M-k) = -conj W_N^k)
+        slot[M - k] = make_double2(e.x - tr, -e.y + ti);
+      }
+      __syncthreads();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> bulk-copy reads
+    __syncthreads();
+    if (tid == 0) {
+      for (int r = 0; r < nr; r++) bulk_store_1d(a.mesh + (row0 + r) * a.rowp, slots + r * SLOT, OUT_BYTES);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---- host side -------------------------------------------------------------------------------
+static bool rowfft_supported_n(i64 N1) {
+  int r1, r2;
+  return N1 % 2 == 0 && zfused_factor(N1 / 2, &r1, &r2);
+}
+
+static int rowfft_tables(nnpm_ctx* ctx) {
+  if (ctx->xtwM) return NNPM_OK;
+  const i64 N = ctx->g.N1, M = N / 2;
+  std::vector<double2> hM((size_t)M), hN((size_t)M);
+  const long double tau = 2.0L * 3.14159265358979323846264338327950288L;
+  for (i64 m = 0; m < M; m++) {
+    const long double aM = -tau * (long double)m / (long double)M, aN = -tau * (long double)m / (long double)N;
+    hM[m] = make_double2((double)cosl(aM), (double)sinl(aM));
+    hN[m] = make_double2((double)cosl(aN), (double)sinl(aN));
+  }
+  CKR(dalloc(ctx, &ctx->xtwM, (size_t)M));
+  CKR(dalloc(ctx, &ctx->xtwN, (size_t)M));
+  CK(cudaMemcpyAsync(ctx->xtwM, hM.data(), (size_t)M * sizeof(double2), cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaMemcpyAsync(ctx->xtwN, hN.data(), (size_t)M * sizeof(double2), cudaMemcpyHostToDevice, ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return NNPM_OK;
+}
+
+template <int R1, int R2, bool INVERSE>
+static int rowfft_go(nnpm_ctx* ctx, const RowFftArgs& a) {
+  constexpr int M = R1 * R2, RM = R1 > R2 ? R1 : R2;
+  constexpr int SLOT = R1 * (R2 + 1) > M + 1 ? R1 * (R2 + 1) : M + 1;
+  const size_t smem = (size_t)4 * SLOT * 16 + (size_t)2 * M * 16;
+  CK(cudaFuncSetAttribute(k_rowfft<R1, R2, INVERSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const i64 ngroups = (a.nrows + 3) / 4;
+  const i64 maxg = (i64)ctx->nsm * (M > 512 ? 2 : M == 512 ? 3 : 4);
+  const unsigned grid = (unsigned)(ngroups < maxg ? ngroups : maxg);
+  k_rowfft<R1, R2, INVERSE><<<grid, 4 * RM, smem, ctx->st>>>(a);
+  LAUNCHED(ctx);
+  KCHECK();
+  return NNPM_OK;
+}
+
+// x pass over planes [plane0, plane0 + nplanes) of the owned slab, in place
+static int rowfft_x(nnpm_ctx* ctx, bool inverse, i64 plane0 = 0, i64 nplanes = -1) {
+  const Geom& g = ctx->g;
+  CKR(rowfft_tables(ctx));
+  if (nplanes < 0) nplanes = g.nzl;
+  RowFftArgs a;
+  a.mesh = ctx->mesh + g.plane * (g.glo + plane0);
+  a.rowp = g.rowp;
+  a.nrows = g.N2 * nplanes;
+  a.twM = ctx->xtwM;
+  a.twN = ctx->xtwN;
+  if (a.nrows == 0) return NNPM_OK;
+#define RF(R1_, R2_) return inverse ? rowfft_go<R1_, R2_, true>(ctx, a) : rowfft_go<R1_, R2_, false>(ctx, a)
+  switch (g.N1 / 2) {
+    case 64: RF(8, 8);
+    case 128: RF(16, 8);
+    case 256: RF(16, 16);
+    case 512: RF(32, 16);
+    case 1024: RF(32, 32);
+  }
+#undef RF
+  return fail(ctx, NNPM_ERR_STATE, "row FFT does not support N1 = %lld", (long long)g.N1);
+}

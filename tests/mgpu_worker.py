@@ -23,9 +23,9 @@ def main():
     lr = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(lr)
     dist.init_process_group("gloo")
-    N = 32
+    N = 64                     # >= 64: the TMA column FFT, the fused z pass and the fused NVLink transposes all run
     dims = (N, N, N)
-    npart = 40000
+    npart = 60000
     x, v = make_particles(101, npart, 3, clustered=True)
     v *= 0.2
     m = float(N ** 3) / npart
@@ -38,11 +38,11 @@ def main():
             errs.append(f"rank {rank}: {name} FAILED {detail}")
 
     # (deposit mode, sort cadence): sort_every > 0 runs the tiled shared-memory deposit / push on slabs
-    # the last case runs the persistent push (3 CTAs, so that each walks many work items) on slabs with ghost planes
+    # the last case runs the un-fused slab transposes (copy engines) instead of the ones fused into the FFT kernels
     for mode, sort_every, opts in (("atomic", 0, {}), ("fixedpoint", 0, {}), ("atomic", 1, {}), ("fixedpoint", 2, {}),
-                                   ("atomic", 1, {"push_persist": 1, "push_grid": 3})):
+                                   ("atomic", 1, {"fuse_transpose": 0})):
         dev = DevicePM(dims, npart, rank=3, device=lr, nranks=P, rank_id=rank, deposit_mode=mode, timing=True,
-                       sort_every=sort_every)
+                       sort_every=sort_every, part_capacity=npart)   # clustered particles: a slab may hold far more than npart / P
         for k_, v_ in opts.items():
             dev.set_option(k_, v_)
         uid = [DevicePM.comm_unique_id() if rank == 0 else None]
@@ -106,17 +106,19 @@ def main():
             print(f"[mgpu P={P} {mode} sort_every={sort_every}] untiled={st.n_untiled} migrated(last step, all ranks)={int(cnt[1].item())} ms={st.as_dict()['ms']}")
         dev.close()
 
-    # pipelined solve (transposes overlapped with the chunked transforms; needs N2, N3 in 64..1024):
-    # equal to the oracle, and bit-identical to the un-pipelined and to the NCCL send/recv paths
+    # the four transpose paths -- fused into the FFT kernels' stores (default), copy engines pipelined with chunked
+    # transforms, copy engines un-pipelined, grouped NCCL send/recv -- equal the oracle and each other bit for bit
+    # (N1 = 128 so that the own row-FFT x passes run too)
     N2 = 64
     rng = np.random.default_rng(5)
-    rho = rng.random((N2, N2, N2))
+    rho = rng.random((N2, N2, 2 * N2))
     ref = np.empty_like(rho)
-    O.compute_potential(ref, rho - rho.mean(), np.zeros((N2, N2, N2 // 2 + 1), dtype=np.complex128))
+    O.compute_potential(ref, rho - rho.mean(), np.zeros((N2, N2, N2 + 1), dtype=np.complex128))
     nz2 = N2 // P
     got = {}
-    for name, opts in (("pipelined", {"pipeline": 2}), ("unpipelined", {"pipeline": 0}), ("kernel", {"peer_transpose": 2}), ("nccl", {"peer_transpose": 0})):
-        dev = DevicePM((N2, N2, N2), 8, rank=3, device=lr, nranks=P, rank_id=rank)
+    for name, opts in (("fused", {}), ("pipelined", {"fuse_transpose": 0, "pipeline": 2}), ("unpipelined", {"fuse_transpose": 0, "pipeline": 0}),
+                       ("nccl", {"fuse_transpose": 0, "peer_transpose": 0})):
+        dev = DevicePM((2 * N2, N2, N2), 8, rank=3, device=lr, nranks=P, rank_id=rank)
         uid = [DevicePM.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         dev.comm_init(uid[0])
@@ -128,8 +130,8 @@ def main():
             got[name] = dev.get_field("phi")
         check(f"solve {name}", nlinf(got[name], ref[rank * nz2:(rank + 1) * nz2]) < 1e-12 * np.max(np.abs(ref)) / np.max(np.abs(ref[rank * nz2:(rank + 1) * nz2])))
         dev.close()
-    for name in ("unpipelined", "kernel", "nccl"):
-        check(f"solve pipelined == {name}", np.array_equal(got["pipelined"], got[name]))
+    for name in ("pipelined", "unpipelined", "nccl"):
+        check(f"solve fused == {name}", np.array_equal(got["fused"], got[name]))
 
     # fine mesh along z (N3 = 2048, BASELINE config 5): slab transposes + the radix-2-wrapped fused z pass
     d5 = (16, 16, 2048)

@@ -131,7 +131,7 @@ def test_every_runtime_option_is_documented_in_the_header():
     assert accepted == documented, f"undocumented: {sorted(accepted - documented)}; stale: {sorted(documented - accepted)}"
 
 
-HOT_KERNELS = ("k_push_tile", "k_deposit_tile", "k_zfused_p", "k_colfft", "k_sort_count", "k_permute")
+HOT_KERNELS = ("k_push_tile", "k_deposit_tile", "k_zfused_s", "k_zfused_p", "k_colfft", "k_rowfft", "k_sort_count", "k_permute")
 
 
 def test_hot_kernels_do_not_spill(lib_built):
@@ -145,9 +145,7 @@ def test_hot_kernels_do_not_spill(lib_built):
     seen = set()
     for mangled, stack, st, ld in entries:
         hot = [k for k in HOT_KERNELS if k in mangled]
-        # launch-shape experiments may spill: 3 CTAs per SM (k_push_tile<.., MINB = 3, ..>, 85 registers) and the
-        # persistent push (k_push_tile_p, an option) at 320 / 384 threads
-        if not hot or re.search(r"k_push_tileILi\dELb\dELi3E", mangled) or "k_push_tile_p" in mangled:
+        if not hot:
             continue
         seen.add(hot[0])
         assert int(st) == 0 and int(ld) == 0, f"{mangled} spills ({st} B stores, {ld} B loads)"
@@ -169,7 +167,7 @@ def test_sass_carries_the_blackwell_data_movement_instructions(lib_built):
         if m:
             cur = m.group(1)
             continue
-        m = re.search(r"\b(UTMALDG|UTMASTG|UBLKRED|UBLKPF|SYNCS)\b", line)
+        m = re.search(r"\b(UTMALDG|UTMASTG|UBLKRED|UBLKPF|UBLKCP|SYNCS)\b", line)
         if m and cur:
             per_kernel.setdefault(cur, set()).add(m.group(1))
 
@@ -183,4 +181,6 @@ def test_sass_carries_the_blackwell_data_movement_instructions(lib_built):
     assert {"UTMALDG", "SYNCS", "UBLKPF"} <= ops("k_push_tile")
     assert {"UBLKRED", "UBLKPF"} <= ops("k_deposit_tile")
     assert {"UTMALDG", "SYNCS"} <= ops("k_zfused_p")
+    assert {"UTMALDG", "SYNCS"} <= ops("k_zfused_s")
     assert {"UTMALDG", "UTMASTG", "SYNCS"} <= ops("k_colfft")
+    assert {"UBLKCP", "SYNCS"} <= ops("k_rowfft")

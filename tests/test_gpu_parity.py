@@ -87,23 +87,22 @@ def test_potential_fused_z_pass(lib_built, O, dims):
     ref = np.empty(shape)
     O.compute_potential(ref, rho - rho.mean(), np.zeros((shape[0], shape[1], shape[2] // 2 + 1), dtype=np.complex128))
     out = {}
-    for zf in (2, 1, 0):          # 2 = persistent + TMA prefetch, 1 = one CTA per column group, 0 = cuFFT z + Green kernel
+    for zf in (3, 2, 0):          # 3 = split exchange (load overlaps the whole transform), 2 = single buffer, 0 = cuFFT z + Green kernel
         with DevicePM(dims, 1, rank=3) as dev:
             dev.set_option("zfused", zf)
             for rep in range(2):
                 dev.set_field("rho", rho)
                 dev.solve()
                 out[zf] = dev.get_field("phi")
+    assert nlinf(out[3], ref) < TOL
     assert nlinf(out[2], ref) < TOL
-    assert nlinf(out[1], ref) < TOL
     assert nlinf(out[0], ref) < TOL
-    assert nlinf(out[2], out[1]) < 1e-14    # same algorithm, different data movement (FMA contraction may differ)
+    assert nlinf(out[3], out[2]) < 1e-14    # same algorithm, different data movement (FMA contraction may differ)
 
 
 @pytest.mark.parametrize("dims,rank", [((48, 20, 1), 2), ((64, 64, 1), 2), ((40, 24, 20), 3), ((64, 32, 32), 3), ((16, 16, 16), 3)])
 @pytest.mark.parametrize("mode", ["atomic", "fixedpoint"])
-@pytest.mark.parametrize("unroll", [1, 2])
-def test_tiled_deposit_matches_oracle_and_global_path(lib_built, O, dims, rank, mode, unroll):
+def test_tiled_deposit_matches_oracle_and_global_path(lib_built, O, dims, rank, mode):
     """shared-memory tiled scatter on tile-sorted particles == oracle == global-atomic path, also after
     the particles strayed from their tiles (no re-sort); fixed-point sums are bit-identical."""
     from noname_b200 import DevicePM
@@ -112,7 +111,6 @@ def test_tiled_deposit_matches_oracle_and_global_path(lib_built, O, dims, rank, 
     m = 0.41
     shape = (dims[2], dims[1], dims[0])
     with DevicePM(dims, npart, rank=rank, deposit_mode=mode) as dev:
-        dev.set_option("deposit_unroll", unroll)
         dev.upload(x, v, m)
         dev.sort()
         for stray_dt in (0.0, 0.4, 3.0):           # 0.05-sigma velocities: up to ~cells of straying
@@ -140,11 +138,14 @@ def test_tiled_deposit_matches_oracle_and_global_path(lib_built, O, dims, rank, 
 
 
 @pytest.mark.parametrize("dims", [(24, 64, 8), (20, 128, 64), (10, 256, 12), (6, 512, 128), (8, 1024, 4), (64, 64, 64),
-                                  (128, 128, 1), (130, 64, 1)])
-def test_potential_tma_column_fft(lib_built, O, dims):
-    """the TMA-staged column-FFT engine (y pass of the 2-D transform, fused z pass) against the oracle and
-    against the all-cuFFT composition; icn = N1/2+1 is never a multiple of the 4-column group, so the
-    out-of-bounds clipping of the last group is always exercised."""
+                                  (128, 128, 1), (130, 64, 1), (256, 64, 16), (512, 64, 4), (1024, 64, 2), (2048, 64, 1),
+                                  (128, 20, 12), (1024, 12, 1)])
+def test_potential_own_x_and_y_passes(lib_built, O, dims):
+    """the hand-written 2-D transform passes against the oracle and against the cuFFT compositions:
+    x = bulk-copy staged row FFT (r2c / c2r through a half-length complex transform, N1 = 128 .. 2048),
+    y = TMA-staged column FFT (N2 = 64 .. 1024; icn = N1/2+1 is never a multiple of the 4-column group, so the
+    out-of-bounds clipping of the last group is always exercised).  Row counts that are not a multiple of the
+    4-row group exercise the ragged tail."""
     from noname_b200 import DevicePM
     rng = np.random.default_rng(35)
     shape = (dims[2], dims[1], dims[0])
@@ -152,19 +153,18 @@ def test_potential_tma_column_fft(lib_built, O, dims):
     ref = np.empty(shape)
     O.compute_potential(ref, rho - rho.mean(), np.zeros((shape[0], shape[1], shape[2] // 2 + 1), dtype=np.complex128))
     out = {}
-    for key, (cf, cz) in {1: (1, 1), 2: (1, 2), 0: (0, 0)}.items():   # cz: 1 = double-buffered, 2 = two CTAs per SM
+    for key, (rf, cf) in {"own": (1, 1), "cufft_x": (0, 1), "cufft": (0, 0)}.items():
         with DevicePM(dims, 1, rank=3 if dims[2] > 1 else 2) as dev:
+            dev.set_option("rowfft", rf)
             dev.set_option("colfft", cf)
-            dev.set_option("colfft_z", cz)
             dev.set_field("rho", rho)
             dev.solve()
             out[key] = dev.get_field("phi")
-            dev.set_field("rho", rho)          # a second solve through the same context (buffer ring reuse)
+            dev.set_field("rho", rho)          # a second solve through the same context (buffer reuse)
             dev.solve()
             assert np.array_equal(out[key], dev.get_field("phi"))
-    assert nlinf(out[2], ref) < TOL
-    assert nlinf(out[1], ref) < TOL
-    assert nlinf(out[0], ref) < TOL
+    for key in out:
+        assert nlinf(out[key], ref) < TOL, key
 
 
 @pytest.mark.parametrize("dims", [(12, 10, 128), (32, 16, 256), (8, 8, 512), (10, 4, 1024), (8, 4, 2048), (34, 6, 2048)])
@@ -302,15 +302,8 @@ def test_fused_step_matches_oracle(lib_built, O, dims, rank, comoving, sort):
     assert st.kernel_launches > 0 and st.n_halo_violations == 0
 
 
-# kernel variants of the tiled push: one CTA per work item (register loads / DMA warp), and the persistent
-# kernel at 256 / 320 / 384 threads, also on a 3-CTA grid so that every CTA walks many work items through
-# both box buffers (the default grid of 2 * SMs - 1 gives each CTA at most one item at test sizes)
-PUSH_VARIANTS = [{}, {"push_tma": 1}, {"push_persist": 1}, {"push_persist": 1, "push_grid": 3},
-                 {"push_persist": 2, "push_grid": 2}, {"push_persist": 3, "push_grid": 5},
-                 {"push_persist": 1, "push_flags": 4, "push_grid": 3}, {"push_persist": 2, "push_flags": 12, "push_grid": 2},
-                 {"push_persist": 1, "push_flags": 12},
-                 {"push_depth": 2, "l2pf_push": 0}, {"l2pf_push": 1, "l2pf_deposit": 1, "deposit_unroll": 2},
-                 {"l2pf_push": 7, "l2pf_deposit": 0, "deposit_unroll": 1}]
+# kernel options of the tiled paths: bulk L2 prefetch of the work item's particle runs on / off, per-cell flush
+PUSH_VARIANTS = [{}, {"l2pf_push": 0, "l2pf_deposit": 0}, {"bulk_flush": 0}]
 
 
 # (128, 32, 32) and (128, 64, 1) have tiles whose phi box lies inside the mesh (staged by one TMA tensor
@@ -390,7 +383,7 @@ def test_synthetic_ics_match_oracle(lib_built, O):
 
 
 @pytest.mark.parametrize("mode", ["atomic", "fixedpoint"])
-@pytest.mark.parametrize("variant", [{}, {"push_persist": 1, "push_grid": 7, "deposit_unroll": 2}], ids=["default", "persist"])
+@pytest.mark.parametrize("variant", [{}, {"l2pf_push": 0, "l2pf_deposit": 0}], ids=["default", "nol2pf"])
 def test_clustered_state_matches_oracle(lib_built, O, mode, variant):
     """BASELINE config 4 stand-in at test size: device-generated clustered particles equal the oracle's
     generator; a tile then holds many chunks of the work list (collapsed blobs), and the tiled deposit /
