@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define NNPM_VERSION 1
+#define NNPM_VERSION 2
 
 typedef struct nnpm_ctx nnpm_ctx;
 
@@ -55,7 +55,8 @@ enum { NNPM_INTERP_NONE = 0, NNPM_INTERP_CIC = 1 };
 enum { NNPM_DEPOSIT_ATOMIC = 0, NNPM_DEPOSIT_FIXED = 1 };
 /* fields for nnpm_get_field / nnpm_set_field */
 enum { NNPM_FIELD_RHO = 0, NNPM_FIELD_PHI = 1, NNPM_FIELD_ACC = 2, NNPM_FIELD_PA = 3 };
-/* synthetic initial conditions generated on the device (nnpm_init_synthetic) */
+/* synthetic initial conditions generated on the device (nnpm_init_synthetic; nnpm_init_grf and nnpm_init_pancake
+ * have entry points of their own) */
 enum { NNPM_IC_LATTICE = 0, NNPM_IC_ZELDOVICH_MODES = 1, NNPM_IC_CLUSTERED = 2 };
 
 typedef struct {
@@ -86,7 +87,9 @@ enum {
   NNPM_MS_COMM = 5,    /* of SOLVE: time inside the all-to-all transposes */
   NNPM_MS_FFT_Z = 6,   /* of SOLVE: the z pass (z-FFT, Green multiply, z-iFFT) */
   NNPM_MS_FFT_XY = 7,  /* of SOLVE: the two batched 2-D transforms */
-  NNPM_MS_COUNT = 8
+  NNPM_MS_FFT_X = 8,   /* of FFT_XY: the x passes (r2c + c2r); 0 when not separately timed */
+  NNPM_MS_FFT_Y = 9,   /* of FFT_XY: the y passes (forward + inverse; with nranks > 1 the forward one carries the fused NVLink transpose) */
+  NNPM_MS_COUNT = 10
 };
 
 /* per-step reductions the reference prints / uses for dt control
@@ -143,6 +146,23 @@ int nnpm_download_particles(nnpm_ctx *ctx, double *x_aos, double *v_aos, int64_t
  * velocity dispersion vfac; oracle/pm_ref.py:synthetic_clustered is the checker. */
 int nnpm_init_synthetic(nnpm_ctx *ctx, int kind, const int64_t pdims[3], uint64_t seed,
                         int32_t nmodes, int32_t kmax, double disp_rms, double vfac, double m);
+/* PowerSpectrumParticles (src/ParticleMesh.jl:209-254) with scaleFreePS (src/InputPowerSpectra.jl:26), on the
+ * device and SEEDED: lattice + Zel'dovich displacement psi = irfft(c_d) on the particle lattice pdims with
+ *   c_d(k) = sqrt(P(|k|)) (g1 - i g2) / 2 / k^2 * k_d,  P(k) = k^ps_index,  k in rad/cell via fftfreq (:202-206),
+ * k = 0 skipped, (g1, g2) standard normal from a counter-based generator keyed by (seed, mode index) -- any slab
+ * decomposition draws the same field.  Deviations from the (non-parsing, unseeded) reference function, as
+ * SURVEY.md section 8(d) prescribes: one complex amplitude per mode shared by the components instead of a fresh
+ * randn(2) per component; the planes i = 0 and i = N1/2 are made Hermitian so that the field is real whatever the
+ * c2r transform does with redundant bins; psi is rescaled to a per-component RMS of disp_rms (box units); and
+ * velocities v = vfac * psi are set (the reference leaves them "still to implement", :251; vfac = adot/a gives the
+ * growing mode as in ZeldovichPancakeParticles :193-194).  The inverse transform runs through the library's own
+ * FFT passes (and slab transposes when nranks > 1).  oracle/pm_ref.py:synthetic_grf is the checker. */
+int nnpm_init_grf(nnpm_ctx *ctx, const int64_t pdims[3], uint64_t seed, double ps_index, double disp_rms,
+                  double vfac, double m);
+/* ZeldovichPancakeParticles (src/ParticleMesh.jl:177-198) on the device: lattice, then
+ *   v1 = vamp * sin(2 pi x1),  x1 += xamp * sin(2 pi x1),  make_periodic;
+ * the host passes xamp = 2/5 A a and vamp = 2/5 A adot with A, a, adot evaluated as the reference does. */
+int nnpm_init_pancake(nnpm_ctx *ctx, const int64_t pdims[3], double xamp, double vamp, double m);
 /* Counting sort of the local particles by cell (new; K0 of the design). */
 int nnpm_sort(nnpm_ctx *ctx);
 
@@ -197,16 +217,23 @@ int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, in
  *   "l2pf_push"    1 = each CTA of the tiled push pulls its work item's x, v runs into L2 with one
  *                  cp.async.bulk.prefetch.L2 per array before it stages its phi box (default), 0 = off
  *   "l2pf_deposit" 1 = the same in the tiled deposit (default), 0 = off
- *   "fuse_transpose" nranks > 1: 1 = the slab transposes are fused into the transform kernels (default): the forward
- *                  y pass stores each column group straight into the owning ranks' transposed spectra through
- *                  per-peer TMA tensor maps, the z pass stores its rows straight into the owning ranks' slabs --
- *                  NVLink peer memory, no separate all-to-all pass; 0 = separate transposes ("peer_transpose")
+ *   "fuse_transpose" nranks > 1: 1 = the slab transposes are fused into the transform kernels: the forward y pass
+ *                  stores each column group straight into the owning ranks' transposed spectra through per-peer
+ *                  TMA tensor maps, the z pass stores its rows straight into the owning ranks' slabs (NVLink peer
+ *                  memory, no separate all-to-all pass).  Bit-identical to the other paths, but measured SLOWER:
+ *                  the 64 / 128-byte pieces such stores put on NVLink reach ~380 GB/s against ~600 GB/s for the
+ *                  copy engines' 1 MB runs; 0 = separate transposes (default)
  *   "peer_transpose" un-fused transposes: 1 = copy-engine peer copies over NVLink (default), 0 = grouped
  *                  ncclSend/ncclRecv (also the fallback when CUDA IPC mapping of the peers' meshes fails)
  *   "pipeline"     un-fused copy-engine transposes: 1 = overlap them with chunked transforms when the chunks are
  *                  large enough (default), 2 = always, 0 = never
+ *   "mig_in_push"  nranks > 1: 1 = the push kernels classify the particles they move and pack the leavers for
+ *                  migration themselves (default), 0 = separate classification pass over all particles
  *   "zsplit"       1 = run N3 in 128..1024 through the radix-2 wrapper of the persistent fused z pass (the path
  *                  N3 = 2048 always takes); test hook
+ *   "keep_rho"     1 = the fused steps copy the deposited density before the solve consumes it, so that
+ *                  nnpm_get_field(NNPM_FIELD_RHO) after the step returns what gd[1].d["ρD"] holds in the reference
+ *                  (the host sets it only for steps after which an output is due); 0 = off (default)
  *   "cfrun_y"      launch-shape experiment of the y pass */
 int nnpm_set_option(nnpm_ctx *ctx, const char *name, double value);
 

@@ -192,35 +192,69 @@ def UniformParticleWind(gp, gd, p, conf):
     p["v"][:, 0] = conf["UniformParticleWindVelocity"]
 
 
-def ZeldovichPancakeParticles(gp, gd, p, conf):
-    """:177-198"""
-    zc = conf["ZeldovichCausticRedshift"]
-    kZ = 1.0
-    zinit = conf["InitialRedshift"]
+def _pancake_amplitudes(conf):
+    """:178-191: A = 5 (1 + zc) / (2 kZ) / (1 + zinit); x += 2/5 A a sin, v = 2/5 A adot sin."""
+    zc, kZ, zinit = conf["ZeldovichCausticRedshift"], 1.0, conf["InitialRedshift"]
     cosmo = conf["_cosmo"]
     A = 5.0 * (1.0 + zc) / (2 * kZ) * 1.0 / (1.0 + zinit)
-    x, v = p["x"], p["v"]
-    initialize_particles_uniform(x, conf["ParticleDimensions"])
     adot = _cos.dadt_from_t_internal(cosmo, conf["StartTime"], zinit)
     a = _cos.a_from_t_internal(cosmo, conf["StartTime"], zinit, zwherea1=zinit)
-    v[:, 0] = 2.0 / 5 * A * adot * np.sin(2 * math.pi * kZ * x[:, 0])
-    x[:, 0] += 2.0 / 5 * A * a * np.sin(2 * math.pi * kZ * x[:, 0])
+    return 2.0 / 5 * A * a, 2.0 / 5 * A * adot
+
+
+def ZeldovichPancakeParticles(gp, gd, p, conf):
+    """:177-198 (host arrays, as the reference; DeviceInitialConditions = true generates the same on the device)"""
+    xamp, vamp = _pancake_amplitudes(conf)
+    x, v = p["x"], p["v"]
+    initialize_particles_uniform(x, conf["ParticleDimensions"])
+    sn = np.sin(2 * math.pi * 1.0 * x[:, 0])
+    v[:, 0] = vamp * sn
+    x[:, 0] += xamp * sn
     np.add(x, 1.0, out=x, where=x < 0.0)     # make_periodic, host side (initialisation only)
     np.subtract(x, 1.0, out=x, where=x > 1.0)
 
 
 def SyntheticZeldovichParticles(gp, gd, p, conf):
-    """Seeded plane-wave Zel'dovich ICs generated on the device (new: the reference's
-    PowerSpectrumParticles is unseeded and does not parse).  conf keys:
+    """Seeded plane-wave Zel'dovich ICs generated on the device (test workload; not in the reference).  conf keys:
     SyntheticSeed, SyntheticModes, SyntheticKmax, SyntheticDispRms (box units), SyntheticVfac."""
-    p["_synthetic"] = dict(seed=int(conf.get("SyntheticSeed", 12345)), nmodes=int(conf.get("SyntheticModes", 32)),
-                           kmax=int(conf.get("SyntheticKmax", 8)),
-                           disp_rms=float(conf.get("SyntheticDispRms", 0.3 / max(conf["TopgridDimensions"]))),
-                           vfac=float(conf.get("SyntheticVfac", 0.0)))
+    p["_ic"] = ("synthetic", dict(seed=int(conf.get("SyntheticSeed", 12345)), nmodes=int(conf.get("SyntheticModes", 32)),
+                                  kmax=int(conf.get("SyntheticKmax", 8)),
+                                  disp_rms=float(conf.get("SyntheticDispRms", 0.3 / max(conf["TopgridDimensions"]))),
+                                  vfac=float(conf.get("SyntheticVfac", 0.0))))
+
+
+def _parse_scale_free_ps(expr):
+    """InputPowerSpectrum = scaleFreePS(n, norm)  (src/InputPowerSpectra.jl:1-4, :26) -> (n, norm).  multiplePeaksPS is
+    not provided (the shipped run/PM conf names it, but its ProblemDefinition does not parse in the reference)."""
+    import re
+    m = re.match(r"^\s*scaleFreePS\(\s*([-+0-9.eE]+)\s*,\s*([-+0-9.eE]+)\s*\)\s*$", str(expr))
+    if not m:
+        raise NotImplementedError(f"InputPowerSpectrum = {expr!r}: only scaleFreePS(n, norm) is provided")
+    return float(m.group(1)), float(m.group(2))
+
+
+def PowerSpectrumParticles(gp, gd, p, conf):
+    """:209-254 with InputPowerSpectrum = scaleFreePS(n, norm), generated on the device by nnpm_init_grf -- seeded
+    (conf RandomSeed, default 12345), rescaled to a per-component RMS displacement of DisplacementRMS (box units,
+    default 0.3 cell) and with growing-mode velocities v = (adot/a) psi when a cosmology is set: the reference's own
+    function does not parse (:246), draws unseeded randn and leaves the velocities unimplemented (:251)."""
+    if "InputPowerSpectrum" not in conf:
+        raise KeyError("Requested to use PowerSpectrumParticles but did not specify InputPowerSpectrum")   # :212-216
+    n, _norm = _parse_scale_free_ps(conf["InputPowerSpectrum"])
+    vfac = 0.0
+    if "_cosmo" in conf and "InitialRedshift" in conf:
+        zi = conf["InitialRedshift"]
+        a = _cos.a_from_t_internal(conf["_cosmo"], conf["StartTime"], zi, zwherea1=zi)
+        vfac = _cos.dadt_from_t_internal(conf["_cosmo"], conf["StartTime"], zi) / a
+    p["_ic"] = ("grf", dict(seed=int(conf.get("RandomSeed", 12345)), ps_index=n,
+                            disp_rms=float(conf.get("DisplacementRMS", 0.3 / max(conf["TopgridDimensions"]))), vfac=vfac))
 
 
 PROBLEMS = {f.__name__: f for f in (UniformParticles, UniformParticleWind, ZeldovichPancakeParticles,
-                                    SyntheticZeldovichParticles)}
+                                    SyntheticZeldovichParticles, PowerSpectrumParticles)}
+#: ProblemDefinitions whose particles can be generated on the device (conf DeviceInitialConditions = true): nothing
+#: is allocated on the host until the first output -- at 1024^3 the host arrays alone are 51.5 GB
+_DEVICE_IC = {"UniformParticles", "ZeldovichPancakeParticles", "SyntheticZeldovichParticles", "PowerSpectrumParticles"}
 
 
 def InitializeParticleSimulation(gp, gd, p, conf):
@@ -235,7 +269,9 @@ def InitializeParticleSimulation(gp, gd, p, conf):
     shape = (dim[2], dim[1], dim[0])
     gd[1].d["ρD"] = np.ones(shape)
     gd[1].d["Φ"] = np.ones(shape)
-    lazy = conf.get("ProblemDefinition") == "SyntheticZeldovichParticles"
+    name = conf.get("ProblemDefinition")
+    always_device = name in ("SyntheticZeldovichParticles", "PowerSpectrumParticles")
+    lazy = always_device or (bool(conf.get("DeviceInitialConditions", False)) and name in _DEVICE_IC)
     p["x"] = None if lazy else np.zeros((npart, rank))
     p["v"] = None if lazy else np.zeros((npart, rank))
     p["m"] = 1.0 * float(np.prod(dim)) / npart
@@ -253,14 +289,16 @@ def InitializeParticleSimulation(gp, gd, p, conf):
             conf["StopTime"] = tend
             conf["OmegaCDM"] = cosmo.Om - conf.get("OmegaBaryon", 0.0)
             p["m"] *= conf["OmegaCDM"]
-    name = conf["ProblemDefinition"]
-    if name == "PowerSpectrumParticles":
-        raise NotImplementedError(
-            "PowerSpectrumParticles does not parse in the reference (ParticleMesh.jl:246) and draws unseeded "
-            "randn; use ProblemDefinition = SyntheticZeldovichParticles (seeded, device-generated)")
     if name not in PROBLEMS:
         raise KeyError(f"unknown ProblemDefinition {name!r}")
-    PROBLEMS[name](gp, gd, p, conf)
+    if lazy and not always_device:
+        if name == "UniformParticles":
+            p["_ic"] = ("lattice", {})
+        else:
+            xamp, vamp = _pancake_amplitudes(conf)
+            p["_ic"] = ("pancake", dict(xamp=xamp, vamp=vamp))
+    else:
+        PROBLEMS[name](gp, gd, p, conf)
     return None
 
 
@@ -281,17 +319,47 @@ def readyForOutput(c):
 
 
 def _sync_host(dev, gd, p, fields=True):
-    """Device -> host copy of the state the reference keeps in gd / p (only at outputs)."""
+    """Device -> host copy of the state the reference keeps in gd / p (only at outputs and at the end).
+    gd[1].d["ρD"] receives the density of the last step's deposit, as in the reference, where `deposit` writes gd's array
+    in place (:767, :857) and the solve works on a temporary: the evolve loops set the `keep_rho` option for the steps
+    after which an output is due.  If no kept density exists (state uploaded but never stepped) the particles are
+    deposited where they are.  With NGPUs > 1 every rank receives the complete arrays."""
     n = dev.local_count
-    if p.get("x") is None or p["x"].shape[0] != n:
-        p["x"] = np.empty((n, dev.rank))
-        p["v"] = np.empty((n, dev.rank))
-    dev.download(p["x"], p["v"])
+    if dev.nranks == 1:
+        if p.get("x") is None or p["x"].shape[0] != n:
+            p["x"] = np.empty((n, dev.rank))
+            p["v"] = np.empty((n, dev.rank))
+        dev.download(p["x"], p["v"])
+    else:
+        from . import slab
+        xl, vl, ids = dev.download(ids=True)
+        ids = slab.allgather_rows(ids)
+        xs, vs = slab.allgather_rows(xl), slab.allgather_rows(vl)
+        if p.get("x") is None or p["x"].shape != xs.shape:
+            p["x"], p["v"] = np.empty_like(xs), np.empty_like(vs)
+        p["x"][ids] = xs            # the reference's particle order
+        p["v"][ids] = vs
     if fields:
-        try:
-            dev.get_field("phi", gd[1].d["Φ"])
-        except _lib.NNPMError:
-            pass
+        def fetch(which, key):
+            try:
+                a = dev.get_field(which)
+            except _lib.NNPMError:
+                return False
+            gd[1].d[key][...] = a if dev.nranks == 1 else __import__("noname_b200.slab", fromlist=["x"]).allgather_slabs(a)
+            return True
+        fetch("phi", "Φ")
+        if not fetch("rho", "ρD") and n >= 0:
+            dev.deposit()           # overwrites the mesh: phi was fetched first
+            fetch("rho", "ρD")
+
+
+def _output_due(c, t, cycle):
+    """readyForOutput (src/IOtools.jl:40-59) evaluated WITHOUT its side effects at a future (time, cycle)."""
+    if c.get("OutputDisabled"):
+        return False
+    if c["OutputEveryNCycle"] > 0 and cycle % c["OutputEveryNCycle"] == 0:
+        return True
+    return c["OutputDtDataDump"] != 0 and abs(t - c["LastOutputTime"]) >= c["OutputDtDataDump"]
 
 
 def analyzePM(gp, gd, p, conf, dev=None, force=False):
@@ -304,6 +372,9 @@ def analyzePM(gp, gd, p, conf, dev=None, force=False):
     c = conf
     if dev is not None:
         _sync_host(dev, gd, p)
+    if dev is not None and dev.nranks > 1 and dev.rank_id != 0:
+        c["CurrentOutputNumber"] += 1     # every rank keeps the same counters; rank 0 writes the files
+        return None
     os.makedirs(c["OutputDirectory"], exist_ok=True)
     on = c["CurrentOutputNumber"]
     s = "%05d" % on
@@ -328,20 +399,52 @@ def analyzePM(gp, gd, p, conf, dev=None, force=False):
 # evolve loops (conf["Evolve"] plugins)
 # ---------------------------------------------------------------------------------------------
 def _device_for(gp, p, conf):
+    """Device context(s) for an evolve loop.  New conf keys (no reference counterpart): NGPUs (slab decomposition
+    over that many processes / GPUs; the process must have been launched once per GPU), SortEvery, DepositMode =
+    atomic | fixedpoint, BackInterpBugCompat, Device, PartCapacityFactor."""
     dims = tuple(gp[1].dim)
     rank = conf.get("_rank", sum(1 for d in dims if d > 1))
     npart = int(np.prod([int(q) for q in conf["ParticleDimensions"]]))
+    ngpus = int(conf.get("NGPUs", 1))
+    rid, local = 0, int(conf.get("Device", options["device"]))
+    if ngpus > 1:
+        from . import slab
+        rid, _, local = slab.require_world(ngpus)
+    cap = 0
+    if ngpus > 1 and "PartCapacityFactor" in conf:
+        cap = int(float(conf["PartCapacityFactor"]) * npart / ngpus) + 4096
     dev = DevicePM(dims, npart, rank=rank, deposit=conf["ParticleDepositInterpolation"],
                    backinterp=conf["ParticleBackInterpolation"],
                    deposit_mode=conf.get("DepositMode", options["deposit_mode"]),
                    sort_every=int(conf.get("SortEvery", options["sort_every"])),
                    bugcompat_interp_z=bool(conf.get("BackInterpBugCompat", options["bugcompat_interp_z"])),
-                   device=int(conf.get("Device", options["device"])))
-    if p.get("_synthetic") is not None:
-        dev.init_synthetic(conf["ParticleDimensions"], m=p["m"], **p["_synthetic"])
+                   device=local, nranks=ngpus, rank_id=rid, part_capacity=cap)
+    if ngpus > 1:
+        dev.comm_init(slab.broadcast_bytes(DevicePM.comm_unique_id() if rid == 0 else None))
+    if p.get("_ic") is not None and p.get("x") is None:
+        kind, kw = p["_ic"]
+        pd = conf["ParticleDimensions"]
+        if kind == "grf":
+            dev.init_grf(pd, m=p["m"], **kw)
+        elif kind == "pancake":
+            dev.init_pancake(pd, m=p["m"], **kw)
+        elif kind == "lattice":
+            dev.init_synthetic(pd, kind="lattice", m=p["m"])
+        else:
+            dev.init_synthetic(pd, m=p["m"], **kw)
+    elif ngpus > 1:
+        # every rank holds the full host arrays (the initialisers ran on each): upload one contiguous share, then
+        # route the particles to their slabs
+        lo, hi = rid * npart // ngpus, (rid + 1) * npart // ngpus
+        dev.upload(np.ascontiguousarray(p["x"][lo:hi]), np.ascontiguousarray(p["v"][lo:hi]), p["m"], first_id=lo)
+        dev.redistribute()
     else:
         dev.upload(p["x"], p["v"], p["m"])
     return dev
+
+
+def _step_stats(dev, st):
+    return dev.reduce_stats(st) if dev.nranks > 1 else st
 
 
 def evolvePM(gp, gd, p, conf, log=None):
@@ -354,7 +457,10 @@ def evolvePM(gp, gd, p, conf, log=None):
         c["CurrentTime"] = c["StartTime"]
         c["CurrentCycle"] = c["StartCycle"]
         while c["CurrentTime"] < c["StopTime"] and c["CurrentCycle"] < c["StopCycle"]:
-            st = dev.step_static(dt)
+            # keep the deposited density only for steps after which analyzePM will write (or the loop ends)
+            t1, cyc1 = c["CurrentTime"] + dt, c["CurrentCycle"] + 1
+            dev.set_option("keep_rho", _output_due(c, t1, cyc1) or not (t1 < c["StopTime"] and cyc1 < c["StopCycle"]))
+            st = _step_stats(dev, dev.step_static(dt))
             c["CurrentTime"] += dt
             if log is not None:
                 log.append((c["CurrentTime"], dt, st.max_pa, st.max_v))
@@ -390,7 +496,10 @@ def evolvePMCosmology(gp, gd, p, conf, log=None):
             ak = _cos.a_from_t_internal(cosmo, t + dt / 2, zinit, zwherea1=zinit)
             adk = _cos.dadt(cosmo, ak, zwherea1=zinit)
             a2 = _cos.a_from_t_internal(cosmo, t + 3.0 * dt / 2 / 2, zinit, zwherea1=zinit)
-            st = dev.step_comoving(dt, a1, ak, adk, a2)
+            t1, cyc1 = t + dt, c["CurrentCycle"] + 1
+            dev.set_option("keep_rho", _output_due(c, t, c["CurrentCycle"]) or _output_due(c, t1, cyc1)
+                           or not (t1 < c["StopTime"] and cyc1 < c["StopCycle"]))
+            st = _step_stats(dev, dev.step_comoving(dt, a1, ak, adk, a2))
             analyzePM(gp, gd, p, c, dev)
             c["CurrentTime"] += dt
             c["CurrentRedshift"] = _cos.z_from_t_internal(cosmo, c["CurrentTime"], zinit)

@@ -13,8 +13,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnnpm.so")
 
-NNPM_MS_COUNT = 8
-MS_NAMES = ("deposit", "solve", "push", "sort", "exchange", "comm", "fft_z", "fft_xy")
+NNPM_MS_COUNT = 10
+MS_NAMES = ("deposit", "solve", "push", "sort", "exchange", "comm", "fft_z", "fft_xy", "fft_x", "fft_y")
 INTERP = {"none": 0, "cic": 1}
 DEPOSIT_MODE = {"atomic": 0, "fixedpoint": 1, "fixed": 1}
 FIELD_RHO, FIELD_PHI, FIELD_ACC, FIELD_PA = 0, 1, 2, 3
@@ -25,7 +25,8 @@ IC_LATTICE, IC_ZELDOVICH_MODES, IC_CLUSTERED = 0, 1, 2
 SYMBOLS = (
     "nnpm_version", "nnpm_create", "nnpm_destroy", "nnpm_last_error", "nnpm_comm_unique_id",
     "nnpm_comm_init", "nnpm_host_alloc", "nnpm_host_free", "nnpm_upload_particles",
-    "nnpm_redistribute", "nnpm_local_count", "nnpm_download_particles", "nnpm_init_synthetic",
+    "nnpm_redistribute", "nnpm_local_count", "nnpm_download_particles", "nnpm_init_synthetic", "nnpm_init_grf",
+    "nnpm_init_pancake",
     "nnpm_sort", "nnpm_make_periodic", "nnpm_deposit", "nnpm_solve", "nnpm_accel", "nnpm_interp",
     "nnpm_drift", "nnpm_kick", "nnpm_kick_comoving", "nnpm_get_field", "nnpm_set_field",
     "nnpm_step_static", "nnpm_step_comoving", "nnpm_reduce_stats", "nnpm_device_bytes",
@@ -93,6 +94,8 @@ def load():
         "nnpm_download_particles": ([vp, vp, vp, vp], C.c_int),
         "nnpm_init_synthetic": ([vp, C.c_int, C.POINTER(i64), C.c_uint64, C.c_int32, C.c_int32,
                                  C.c_double, C.c_double, C.c_double], C.c_int),
+        "nnpm_init_grf": ([vp, C.POINTER(i64), C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double], C.c_int),
+        "nnpm_init_pancake": ([vp, C.POINTER(i64), C.c_double, C.c_double, C.c_double], C.c_int),
         "nnpm_sort": ([vp], C.c_int),
         "nnpm_make_periodic": ([vp], C.c_int),
         "nnpm_deposit": ([vp], C.c_int),

@@ -42,6 +42,9 @@ struct nnpm_ctx {
   double* meshS;  // nranks>1: send/recv staging   [d][kl][jl][ic]
   double *s1, *s2, *s3;  // sin^2(k/2) tables
   int field_state;       // what mesh currently holds: 0 nothing, 1 rho, 2 phi
+  double* rho_keep;      // "keep_rho": copy of the owned planes' density taken by the fused step before the solve
+  bool rho_keep_valid;
+  int opt_keep_rho;
 
   // particles (SoA)
   PartPtrs pp;
@@ -88,12 +91,14 @@ struct nnpm_ctx {
 
   // timing
   cudaEvent_t ev[16];
+  cudaEvent_t ev_fft[8];  // x fwd [0,1], y fwd [1,2], y inv [4,5], x inv [5,6]  (timing = 1)
   int step_count;
   int launches;
 
   // comm
   NcclApi* nccl;
   void* comm;
+  bool comm_borrowed;   // temporary lattice context of nnpm_init_grf: the communicator belongs to its parent
   // migration scratch (nranks > 1)
   double* mig_send;
   double* mig_recv;
@@ -106,6 +111,7 @@ struct nnpm_ctx {
   i64* h_cnt;      // pinned
   i64 last_migrated;
   double* pk_buf;
+  double* ic_partial;   // per-block partial sums of nnpm_init_grf's displacement norm
   double2* ztw;  // z-FFT twiddles W_N3^m
   // NVLink peer-memory transposes (nranks > 1): every rank's mesh / meshT mapped through CUDA IPC
   double* peer_mesh[64];
@@ -121,7 +127,7 @@ struct nnpm_ctx {
   cufftHandle plan1f, plan1b;  // batched 1-D x transforms (r2c / c2r) over the owned rows
   int opt_pipeline;
   cudaEvent_t ev_chunk[4];
-  int opt_l2pf_push, opt_l2pf_deposit, opt_colfft, opt_cfrun_y, opt_rowfft, opt_fuse_transpose, nsm;
+  int opt_l2pf_push, opt_l2pf_deposit, opt_colfft, opt_cfrun_y, opt_rowfft, opt_fuse_transpose, opt_mig_in_push, nsm;
   double2 *xtwM, *xtwN;         // x-pass twiddles W_M^m, W_N^k (nnpm_rowfft.cuh)
   struct PeerMaps* peer_maps;   // tensor maps over every rank's transposed spectrum (fused forward transpose)
   cudaStream_t st2[4];    // side streams: the blocks of a transpose go out on several copy engines at once
@@ -362,6 +368,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   g.fN1 = (double)N1; g.fN2 = (double)N2; g.fN3 = (double)N3;
   c->dev_bytes = 0;
   c->mesh = c->meshT = c->meshS = nullptr;
+  c->rho_keep = nullptr; c->rho_keep_valid = false; c->opt_keep_rho = 0;
   c->spare = nullptr; c->ids = c->ids_spare = nullptr;
   c->acc = nullptr; c->pa[0] = c->pa[1] = c->pa[2] = nullptr;
   c->acc_valid = c->pa_valid = false;
@@ -373,10 +380,10 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->opt_fft3d = 0; c->opt_zfused = 3; c->opt_tile_deposit = 1; c->opt_tile_push = 1; c->opt_bulk_flush = 1;
   c->fftwork = nullptr; c->fftwork_bytes = 0;
   c->step_count = 0; c->launches = 0;
-  c->nccl = nullptr; c->comm = nullptr;
+  c->nccl = nullptr; c->comm = nullptr; c->comm_borrowed = false;
   c->mig_send = c->mig_recv = nullptr; c->mig_cap = 0; c->mig_holes = nullptr; c->mig_cnt = nullptr; c->h_cnt = nullptr;
   c->last_migrated = 0;
-  c->pk_buf = nullptr;
+  c->pk_buf = nullptr; c->ic_partial = nullptr;
   c->ztw = nullptr;
   for (int i = 0; i < 64; i++) { c->peer_mesh[i] = nullptr; c->peer_meshT[i] = nullptr; }
   c->peer_ok = false; c->opt_peer = 1; c->bar_buf = nullptr;
@@ -385,13 +392,14 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->opt_pipeline = 1;
   for (int i = 0; i < 4; i++) c->ev_chunk[i] = nullptr;
   c->have_tm_y = c->have_tm_z8 = c->have_tm_z4 = c->have1 = false; c->opt_zsplit = 0; c->ytw = nullptr;
-  c->opt_l2pf_push = 1; c->opt_l2pf_deposit = 1; c->opt_colfft = 1; c->opt_cfrun_y = 1; c->opt_rowfft = 1; c->opt_fuse_transpose = 1;
+  c->opt_l2pf_push = 1; c->opt_l2pf_deposit = 1; c->opt_colfft = 1; c->opt_cfrun_y = 1; c->opt_rowfft = 1; c->opt_fuse_transpose = 0; c->opt_mig_in_push = 1;
   c->xtwM = c->xtwN = nullptr; c->peer_maps = nullptr; c->nsm = 148;
   c->mig_lo = nullptr; c->ghost_rx = nullptr; c->red_buf = nullptr;
   c->np = 0; c->m = 0.0; c->ids_dirty = false; c->field_state = 0; c->first_id = 0;
   c->own_stream = false;
   c->h_red = nullptr;
   for (int i = 0; i < 16; i++) c->ev[i] = nullptr;
+  for (int i = 0; i < 8; i++) c->ev_fft[i] = nullptr;
 
   auto bail = [&](int rc) {
     g_create_err = c->err;
@@ -437,6 +445,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   CKB(CKR(make_tensor_map(c)));
   CKB(CKR(make_plans(c)));
   for (int i = 0; i < 16; i++) CKB(CK(cudaEventCreate(&c->ev[i])));
+  for (int i = 0; i < 8; i++) CKB(CK(cudaEventCreate(&c->ev_fft[i])));
   c->tg.tx = (int)(N1 < NNPM_TX ? N1 : NNPM_TX);
   c->tg.ty = (int)(N2 < NNPM_TY ? N2 : NNPM_TY);
   c->tg.tz = c->R == 3 ? (int)(g.nzl < NNPM_TZ ? g.nzl : NNPM_TZ) : 1;
@@ -469,6 +478,7 @@ extern "C" int nnpm_destroy(nnpm_ctx* ctx) {
   if (ctx->h_red) cudaFreeHost(ctx->h_red);
   if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
   for (int i = 0; i < 16; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 8; i++) if (ctx->ev_fft[i]) cudaEventDestroy(ctx->ev_fft[i]);
   if (ctx->own_stream && ctx->st) cudaStreamDestroy(ctx->st);
   delete ctx;
   return NNPM_OK;
@@ -876,9 +886,13 @@ static int fft_forward(nnpm_ctx* ctx, double2** Tout, bool z_too, cudaEvent_t* c
     *Tout = (double2*)own;
     return NNPM_OK;
   }
+  const bool tim = comm_t != nullptr;  // the fused step passes its event array when timing = 1
   if (ctx->opt_colfft && colfft_supported_n(g.N2)) {
+    if (tim) CK(cudaEventRecord(ctx->ev_fft[0], ctx->st));
     CKR(fft_x(ctx, false));
+    if (tim) CK(cudaEventRecord(ctx->ev_fft[1], ctx->st));
     CKR(colfft_y(ctx, false, 0, -1, fuse));
+    if (tim) CK(cudaEventRecord(ctx->ev_fft[2], ctx->st));
   } else {
     CKF(cufftExecD2Z(ctx->plan2f, own, (cufftDoubleComplex*)own));
     LAUNCHED(ctx);
@@ -914,8 +928,12 @@ static int fft_inverse(nnpm_ctx* ctx, bool z_too, cudaEvent_t* comm_t, bool fuse
     if (comm_t) CK(cudaEventRecord(comm_t[3], ctx->st));
   }
   if (ctx->opt_colfft && colfft_supported_n(g.N2)) {
+    const bool tim = comm_t != nullptr;
+    if (tim) CK(cudaEventRecord(ctx->ev_fft[4], ctx->st));
     CKR(colfft_y(ctx, true));
+    if (tim) CK(cudaEventRecord(ctx->ev_fft[5], ctx->st));
     CKR(fft_x(ctx, true));
+    if (tim) CK(cudaEventRecord(ctx->ev_fft[6], ctx->st));
   } else {
     CKF(cufftExecZ2D(ctx->plan2b, (cufftDoubleComplex*)own, own));
     LAUNCHED(ctx);
@@ -1066,9 +1084,12 @@ extern "C" int nnpm_get_field(nnpm_ctx* ctx, int which, double* host_out) {
   CK(cudaSetDevice(ctx->cfg.device));
   const Geom& g = ctx->g;
   if (which == NNPM_FIELD_RHO || which == NNPM_FIELD_PHI) {
-    if (ctx->field_state != (which == NNPM_FIELD_RHO ? 1 : 2))
-      return fail(ctx, NNPM_ERR_STATE, "mesh does not currently hold %s", which == NNPM_FIELD_RHO ? "rho" : "phi");
-    CK(cudaMemcpy2DAsync(host_out, (size_t)g.N1 * 8, ctx->mesh + g.plane * g.glo, (size_t)g.rowp * 8, (size_t)g.N1 * 8,
+    const double* src = ctx->mesh + g.plane * g.glo;
+    if (which == NNPM_FIELD_RHO && ctx->field_state != 1 && ctx->rho_keep_valid) src = ctx->rho_keep;  // kept by the last fused step
+    else if (ctx->field_state != (which == NNPM_FIELD_RHO ? 1 : 2))
+      return fail(ctx, NNPM_ERR_STATE, "mesh does not currently hold %s%s", which == NNPM_FIELD_RHO ? "rho" : "phi",
+                  which == NNPM_FIELD_RHO ? " (the solve consumed it; set option keep_rho before the step)" : "");
+    CK(cudaMemcpy2DAsync(host_out, (size_t)g.N1 * 8, src, (size_t)g.rowp * 8, (size_t)g.N1 * 8,
                          (size_t)g.N2 * g.nzl, cudaMemcpyDeviceToHost, ctx->st));
   } else if (which == NNPM_FIELD_ACC) {
     if (!ctx->acc_valid) return fail(ctx, NNPM_ERR_STATE, "acc not computed (call nnpm_accel)");
@@ -1197,7 +1218,18 @@ static int do_step(nnpm_ctx* ctx, bool comoving, double dt, double a_d1, double 
     pp.a = 1.0;
     pp.hub = 0.0;
   }
+  // nranks > 1: the push packs this step's leavers itself (mig_emit); the counters must be clean before it runs
+  const bool mig_in_push = ctx->P > 1 && ctx->comm && ctx->R == 3 && ctx->opt_mig_in_push;
+  memset(&pp.mg, 0, sizeof pp.mg);
+  if (mig_in_push) { CKR(migrate_reset(ctx)); pp.mg = migrate_args(ctx); }
   CKR(do_deposit(ctx, comoving, pp.c0));
+  ctx->rho_keep_valid = false;
+  if (ctx->opt_keep_rho) {  // gd[1].d["ρD"] of the reference holds this deposit until the next one (ParticleMesh.jl:767, :857)
+    const size_t n = (size_t)ctx->g.plane * ctx->g.nzl;
+    if (!ctx->rho_keep) CKR(dalloc(ctx, &ctx->rho_keep, n));
+    CK(cudaMemcpyAsync(ctx->rho_keep, ctx->mesh + ctx->g.plane * ctx->g.glo, n * 8, cudaMemcpyDeviceToDevice, ctx->st));
+    ctx->rho_keep_valid = true;
+  }
   if (tim) CK(cudaEventRecord(ev[2], ctx->st));
   CKR(do_solve(ctx, tim ? ev + 8 : nullptr));
   if (tim) CK(cudaEventRecord(ev[3], ctx->st));
@@ -1209,7 +1241,7 @@ static int do_step(nnpm_ctx* ctx, bool comoving, double dt, double a_d1, double 
   }
   if (tim) CK(cudaEventRecord(ev[4], ctx->st));
   ctx->last_migrated = 0;
-  if (ctx->P > 1) CKR(comm_migrate(ctx));
+  if (ctx->P > 1) CKR(comm_migrate(ctx, mig_in_push));
   if (tim) CK(cudaEventRecord(ev[5], ctx->st));
   CK(cudaMemcpyAsync(ctx->h_red, ctx->d_red, 5 * sizeof(i64), cudaMemcpyDeviceToHost, ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
@@ -1243,6 +1275,13 @@ static int do_step(nnpm_ctx* ctx, bool comoving, double dt, double a_d1, double 
       cudaEventElapsedTime(&ms, ev[12], ev[13]);
       stats->ms[NNPM_MS_FFT_Z] = ms;  // un-fused path: includes the inverse 2-D transforms' z part only
       stats->ms[NNPM_MS_FFT_XY] = stats->ms[NNPM_MS_SOLVE] - ms - stats->ms[NNPM_MS_COMM];
+      // x / y split of the 2-D transforms (only recorded on the un-pipelined path with the own y pass)
+      float a1, a2;
+      if (cudaEventElapsedTime(&a1, ctx->ev_fft[0], ctx->ev_fft[1]) == cudaSuccess && cudaEventElapsedTime(&a2, ctx->ev_fft[5], ctx->ev_fft[6]) == cudaSuccess)
+        stats->ms[NNPM_MS_FFT_X] = a1 + a2;
+      if (cudaEventElapsedTime(&a1, ctx->ev_fft[1], ctx->ev_fft[2]) == cudaSuccess && cudaEventElapsedTime(&a2, ctx->ev_fft[4], ctx->ev_fft[5]) == cudaSuccess)
+        stats->ms[NNPM_MS_FFT_Y] = a1 + a2;
+      cudaGetLastError();  // events never recorded (cuFFT 2-D path): not an error
     }
   }
   if (ctx->h_red[3] != 0)
@@ -1261,6 +1300,7 @@ extern "C" int nnpm_step_comoving(nnpm_ctx* ctx, double dt, double a_d1, double 
 }
 
 #include "nnpm_pk.cuh"
+#include "nnpm_ic.cuh"
 
 extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   if (!ctx || !name) return NNPM_ERR_ARG;
@@ -1276,11 +1316,13 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   else if (!strcmp(name, "rowfft")) ctx->opt_rowfft = v;
   else if (!strcmp(name, "pipeline")) ctx->opt_pipeline = v;
   else if (!strcmp(name, "fuse_transpose")) ctx->opt_fuse_transpose = v;
+  else if (!strcmp(name, "mig_in_push")) ctx->opt_mig_in_push = v;
   else if (!strcmp(name, "peer_transpose")) ctx->opt_peer = v;
   else if (!strcmp(name, "zsplit")) ctx->opt_zsplit = v;
   else if (!strcmp(name, "l2pf_push")) ctx->opt_l2pf_push = v;
   else if (!strcmp(name, "l2pf_deposit")) ctx->opt_l2pf_deposit = v;
   else if (!strcmp(name, "cfrun_y")) ctx->opt_cfrun_y = v < 1 ? 1 : v;
+  else if (!strcmp(name, "keep_rho")) ctx->opt_keep_rho = v;
   else return fail(ctx, NNPM_ERR_ARG, "unknown option '%s'", name);
   return NNPM_OK;
 }

@@ -86,7 +86,6 @@ extern "C" int nnpm_comm_unique_id(uint8_t id_out[128]) {
   return NNPM_OK;
 }
 
-static const int MIG_REC = 7;  // doubles per migrating particle record: x[3], v[3], id bits
 
 static int comm_allreduce(nnpm_ctx* ctx, double* host, int n, ncclRedOp_t op);
 
@@ -165,6 +164,7 @@ extern "C" int nnpm_comm_init(nnpm_ctx* ctx, const uint8_t id[128]) {
 }
 
 static void comm_destroy(nnpm_ctx* ctx) {
+  if (ctx->comm_borrowed) { ctx->comm = nullptr; return; }
   for (int d = 0; d < ctx->P && d < 64; d++) {
     if (d == ctx->r) continue;
     if (ctx->peer_mesh[d]) cudaIpcCloseMemHandle(ctx->peer_mesh[d]);
@@ -394,10 +394,6 @@ extern "C" int nnpm_reduce_stats(nnpm_ctx* ctx, nnpm_stats* s) {
 // ------------------------------------------------------------------------------------------
 // particle migration
 // ------------------------------------------------------------------------------------------
-#define MIG_HOLE 0xFFFFFFFFu
-// counter record of one rank: [0, 64) particles packed per destination, then the slots below; MC_REC entries of it
-// are all-gathered (one row per rank) behind the local record
-enum { MC_HOLES = 64, MC_OVER = 65, MC_NLO = 66, MC_NFILL = 67, MC_NP = 68, MC_CAP = 69, MC_REC = 72, MC_ALL = 80 };
 __global__ void k_mig_set(unsigned long long* cnt, unsigned long long np, unsigned long long cap) {
   cnt[MC_NP] = np;
   cnt[MC_CAP] = cap;
@@ -446,17 +442,37 @@ __global__ void k_mig_unpack(PartPtrs p, uint32_t* __restrict__ ids, i64 base, c
   ids[d] = (uint32_t)__double_as_longlong(rec[6]);
 }
 
-// one migration round; *leftover = particles (all ranks) that did not fit the send segments
-static int migrate_round(nnpm_ctx* ctx, i64* leftover) {
+// zero the counter record and note np / capacity in it (before a classification, by the push or by k_mig_classify)
+static int migrate_reset(nnpm_ctx* ctx) {
+  unsigned long long* cnt = (unsigned long long*)ctx->mig_cnt;
+  CK(cudaMemsetAsync(cnt, 0, MC_ALL * 8, ctx->st));
+  k_mig_set<<<1, 1, 0, ctx->st>>>(cnt, (unsigned long long)ctx->np, (unsigned long long)ctx->cap);
+  LAUNCHED(ctx);
+  return NNPM_OK;
+}
+static MigArgs migrate_args(nnpm_ctx* ctx) {
+  MigArgs mg;
+  memset(&mg, 0, sizeof mg);
+  if (ctx->P > 1 && ctx->comm && ctx->R == 3) {
+    mg.on = 1; mg.P = ctx->P; mg.r = ctx->r; mg.kz0 = (int)ctx->g.kz0; mg.nzl = (int)ctx->g.nzl; mg.N3 = (int)ctx->g.N3;
+    mg.fN3 = ctx->g.fN3;
+    mg.seg_cap = ctx->mig_cap / ctx->P;
+    mg.send = ctx->mig_send; mg.holes = ctx->mig_holes; mg.cnt = (unsigned long long*)ctx->mig_cnt; mg.ids = ctx->ids;
+  }
+  return mg;
+}
+
+// one migration round; *leftover = particles (all ranks) that did not fit the send segments.
+// classified: the push already packed this step's leavers (mig_emit) -- skip the classification pass.
+static int migrate_round(nnpm_ctx* ctx, i64* leftover, bool classified) {
   NEED_COMM();
   const Geom& g = ctx->g;
   const int P = ctx->P, r = ctx->r;
   const i64 seg_cap = ctx->mig_cap / P;
   unsigned long long* cnt = (unsigned long long*)ctx->mig_cnt;
-  CK(cudaMemsetAsync(cnt, 0, MC_ALL * 8, ctx->st));
   const i64 np = ctx->np;
-  k_mig_set<<<1, 1, 0, ctx->st>>>(cnt, (unsigned long long)np, (unsigned long long)ctx->cap);
-  if (np) {
+  if (!classified) CKR(migrate_reset(ctx));
+  if (np && !classified) {
     k_mig_classify<<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->pp, ctx->ids, np, g, P, r, seg_cap, ctx->mig_send, ctx->mig_holes, cnt);
     LAUNCHED(ctx);
     KCHECK();
@@ -514,10 +530,10 @@ static int migrate_round(nnpm_ctx* ctx, i64* leftover) {
   return NNPM_OK;
 }
 
-static int comm_migrate(nnpm_ctx* ctx) {
+static int comm_migrate(nnpm_ctx* ctx, bool classified = false) {
   i64 left = 0;
-  CKR(migrate_round(ctx, &left));
-  for (int it = 0; left > 0 && it < 64; it++) CKR(migrate_round(ctx, &left));
+  CKR(migrate_round(ctx, &left, classified));
+  for (int it = 0; left > 0 && it < 64; it++) CKR(migrate_round(ctx, &left, false));
   if (left > 0) return fail(ctx, NNPM_ERR_CAPACITY, "particle migration did not converge (%lld left)", (long long)left);
   return NNPM_OK;
 }

@@ -34,66 +34,80 @@ struct RowFftArgs {
   const double2* twN;  // W_N^k, k < M
 };
 
-// complex FFT of length M = R1 * R2 on the C rows held in the slots, natural order in and out, in place.
-//   pass A  thread j (< R2): elements j + r*R2 -> radix-R1 DIF -> exchange E[q*(R2+1) + j]   (padded: both sides of
-//           the exchange are bank-conflict free for 16-byte elements)
-//   pass B  thread j (< R1): E[j*(R2+1) + r] * W_M^(r j) -> radix-R2 DIF -> element j + q*R1
-template <int R1, int R2, int SIGN>
-__device__ __forceinline__ void rowfft_core(double2* slot, const double2* stwM, int j) {
-  constexpr int RM = R1 > R2 ? R1 : R2, B1 = zf_log2(R1), B2 = zf_log2(R2), EST = R2 + 1;
-  double2 v[RM];
-  if (j < R2) {
+// Complex FFT of length M = R1 * R2 (R1 >= R2) on the C rows held in the slots, natural order in and out, in place.
+// T = C * R2 threads, every lane busy in both passes (FP64 issue slots are the co-limit of this kernel: a half-idle
+// warp costs as many as a full one):
+//   pass A  C * R2 sub-transforms of radix R1, one per thread: row c = tid / R2, j = tid % R2: elements j + r*R2 ->
+//           DIF -> exchange E[q*(R2+1) + j]   (padded: both sides of the exchange are bank-conflict free)
+//   pass B  C * R1 sub-transforms of radix R2, KB = R1 / R2 per thread (held together in the same R1 registers):
+//           E[j*(R2+1) + r] * W_M^(r j) -> DIF -> element j + q*R1
+template <int R1, int R2, int C, int SLOT, int SIGN>
+__device__ __forceinline__ void rowfft_core(double2* slots, const double2* stwM, int tid) {
+  static_assert(R1 >= R2 && R1 % R2 == 0, "factor order");
+  constexpr int T = C * R2, KB = R1 / R2, B1 = zf_log2(R1), B2 = zf_log2(R2), EST = R2 + 1;
+  double2 v[R1];
+  {
+    double2* slot = slots + (tid / R2) * SLOT;
+    const int j = tid % R2;
 #pragma unroll
     for (int r = 0; r < R1; r++) v[r] = slot[j + r * R2];
     ZDif<R1, 0, SIGN>::run(v);
-  }
-  __syncthreads();  // the row is in registers: the slot becomes the exchange buffer
-  if (j < R2) {
+    __syncthreads();  // every row is in registers: the slots become the exchange buffers
 #pragma unroll
     for (int q = 0; q < R1; q++) slot[q * EST + j] = v[zf_brev(q, B1)];
   }
   __syncthreads();
-  if (j < R1) {
 #pragma unroll
-    for (int r = 0; r < R2; r++) v[r] = slot[j * EST + r];
+  for (int it = 0; it < KB; it++) {
+    const int t = tid + it * T;
+    const double2* slot = slots + (t / R1) * SLOT;
+    const int j = t % R1;
+#pragma unroll
+    for (int r = 0; r < R2; r++) v[it * R2 + r] = slot[j * EST + r];
 #pragma unroll
     for (int r = 1; r < R2; r++) {
       const double2 w = stwM[r * j];
-      v[r] = zmul(v[r], w.x, SIGN < 0 ? w.y : -w.y);
+      v[it * R2 + r] = zmul(v[it * R2 + r], w.x, SIGN < 0 ? w.y : -w.y);
     }
-    ZDif<R2, 0, SIGN>::run(v);
   }
-  __syncthreads();  // the exchange is consumed: the slot takes the result in natural order
-  if (j < R1) {
+  ZDif<R2, 0, SIGN>::run(v);
+  if (KB == 2) ZDif<R2, R2, SIGN>::run(v);
+  __syncthreads();  // the exchange is consumed: the slots take the result in natural order
 #pragma unroll
-    for (int q = 0; q < R2; q++) slot[j + q * R1] = v[zf_brev(q, B2)];
+  for (int it = 0; it < KB; it++) {
+    const int t = tid + it * T;
+    double2* slot = slots + (t / R1) * SLOT;
+    const int j = t % R1;
+#pragma unroll
+    for (int q = 0; q < R2; q++) slot[j + q * R1] = v[it * R2 + zf_brev(q, B2)];
   }
   __syncthreads();
 }
 
 // INVERSE = false: real rows -> half spectrum (r2c, forward sign);  true: half spectrum -> real rows (c2r, unnormalised)
 template <int R1, int R2, bool INVERSE>
-__global__ void __launch_bounds__(4 * (R1 > R2 ? R1 : R2), (R1 * R2 > 512 ? 2 : R1 * R2 == 512 ? 3 : 4))
+__global__ void __launch_bounds__(4 * R2, (R1 * R2 > 512 ? 2 : 4))
 k_rowfft(RowFftArgs a) {
-  constexpr int C = 4, M = R1 * R2, RM = R1 > R2 ? R1 : R2;
+  constexpr int C = 4, M = R1 * R2, T = C * R2;
   constexpr int SLOT = R1 * (R2 + 1) > M + 1 ? R1 * (R2 + 1) : M + 1;   // complex elements per row slot
   extern __shared__ __align__(128) unsigned char rf_smem[];
   double2* slots = (double2*)rf_smem;       // [C][SLOT]
-  double2* stwM = slots + C * SLOT;         // [M]
-  double2* stwN = stwM + M;                 // [M]
+  double2* stwM = slots + C * SLOT;         // [M]      W_M^m
+  double2* stwH = stwM + M;                 // [M/2+1]  forward: -i/2 W_N^k;  inverse: i conj(W_N^k)
   __shared__ __align__(8) unsigned long long full;
-  const int tid = threadIdx.x, c = tid / RM, j = tid % RM;
-  for (int t = tid; t < M; t += blockDim.x) {
-    stwM[t] = __ldg(a.twM + t);
-    stwN[t] = __ldg(a.twN + t);
+  const int tid = threadIdx.x;
+  for (int t = tid; t < M; t += T) stwM[t] = __ldg(a.twM + t);
+  for (int t = tid; t <= M / 2; t += T) {
+    const double2 w = __ldg(a.twN + t);
+    stwH[t] = INVERSE ? make_double2(w.y, w.x) : make_double2(0.5 * w.y, -0.5 * w.x);
   }
   if (tid == 0) mbar_init(&full, 1);
   __syncthreads();
   constexpr unsigned IN_BYTES = INVERSE ? (M + 1) * 16u : M * 16u;
   constexpr unsigned OUT_BYTES = INVERSE ? M * 16u : (M + 1) * 16u;
+  constexpr int NPAIR = M / 2 + 1;          // bins k = 0 .. M/2, each paired with M - k
   const i64 ngroups = (a.nrows + C - 1) / C;
   unsigned phase = 0u;
-  double2* slot = slots + c * SLOT;
   for (i64 g = blockIdx.x; g < ngroups; g += gridDim.x) {
     const i64 row0 = g * C;
     const int nr = (int)((a.nrows - row0) < C ? (a.nrows - row0) : C);
@@ -107,35 +121,34 @@ k_rowfft(RowFftArgs a) {
     phase ^= 1u;
     if (INVERSE) {
       // Z'[k] = (X[k] + conj X[M-k]) + i conj(W_N^k) (X[k] - conj X[M-k]), pairs (k, M-k) in place; k = 0 also consumes X[M]
-      for (int k = j; k <= M / 2; k += RM) {
+      for (int t = tid; t < C * NPAIR; t += T) {
+        double2* slot = slots + (t / NPAIR) * SLOT;
+        const int k = t % NPAIR;
         double2 xa = slot[k], xb = slot[M - k];
         if (k == 0) { xa.y = 0.0; xb.y = 0.0; }                      // the DC and Nyquist bins of a real signal are real
-        const double2 w = stwN[k];                                   // W_N^k = (wr, wi)
+        const double2 h = stwH[k];                                   // i conj(W_N^k)
         const double2 e = make_double2(xa.x + xb.x, xa.y - xb.y);    // X[k] + conj X[M-k]
         const double2 d = make_double2(xa.x - xb.x, xa.y + xb.y);    // X[k] - conj X[M-k]
-        // i * conj(w) * d = i (wr - i wi)(dx + i dy) = i [(wr dx + wi dy) + i (wr dy - wi dx)]
-        const double tr = w.x * d.x + w.y * d.y, ti = w.x * d.y - w.y * d.x;
-        const double2 za = make_double2(e.x - ti, e.y + tr);
-        // bin M-k: X[M-k] + conj X[k] = conj(e);  X[M-k] - conj X[k] = -conj(d);  W_N^(M-k) = -conj(W_N^k)
-        //   i conj(-conj w) (-conj d) = i w conj(d) = i [(wr dx + wi dy) + i (wi dx - wr dy)] = i (tr - i ti)
-        const double2 zb = make_double2(e.x + ti, -e.y + tr);
-        slot[k] = za;
-        if (k != 0 && k != M - k) slot[M - k] = zb;
+        const double2 u = make_double2(h.x * d.x - h.y * d.y, h.x * d.y + h.y * d.x);   // i conj(W_N^k) d
+        slot[k] = make_double2(e.x + u.x, e.y + u.y);
+        // bin M-k:  conj(e) + i conj(W_N^(M-k)) (-conj d) = conj(e) - conj(u)
+        if (k != 0 && k != M - k) slot[M - k] = make_double2(e.x - u.x, -e.y + u.y);
       }
       __syncthreads();
-      rowfft_core<R1, R2, +1>(slot, stwM, j);
+      rowfft_core<R1, R2, C, SLOT, +1>(slots, stwM, tid);
     } else {
-      rowfft_core<R1, R2, -1>(slot, stwM, j);
-      // X[k] = E + W_N^k O,  X[M-k] = conj(E) - conj(W_N^k) conj(O) ... evaluated from Z[k], Z[M-k] in place
-      for (int k = j; k <= M / 2; k += RM) {
+      rowfft_core<R1, R2, C, SLOT, -1>(slots, stwM, tid);
+      // X[k] = s/2 + h d,  X[M-k] = conj(s/2) - conj(h d),  s = Z[k] + conj Z[M-k], d = Z[k] - conj Z[M-k], h = -i/2 W_N^k
+      for (int t = tid; t < C * NPAIR; t += T) {
+        double2* slot = slots + (t / NPAIR) * SLOT;
+        const int k = t % NPAIR;
         const double2 za = slot[k], zb = slot[k == 0 ? 0 : M - k];
-        const double2 w = stwN[k];
-        const double2 e = make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y));   // E[k]
-        const double2 o = make_double2(0.5 * (za.y + zb.y), -0.5 * (za.x - zb.x));  // O[k] = -i (Z[k] - conj Z[M-k]) / 2
-        const double tr = w.x * o.x - w.y * o.y, ti = w.x * o.y + w.y * o.x;        // W_N^k O[k]
-        slot[k] = make_double2(e.x + tr, e.y + ti);
-        // X[M-k] = conj(E[k]) - conj(W_N^k O[k])   (E[M-k] = conj E[k], O[M-k] = conj O[k], W_N^(M-k) = -conj W_N^k)
-        slot[M - k] = make_double2(e.x - tr, -e.y + ti);
+        const double2 h = stwH[k];
+        const double2 sh = make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y));
+        const double2 d = make_double2(za.x - zb.x, za.y + zb.y);
+        const double2 u = make_double2(h.x * d.x - h.y * d.y, h.x * d.y + h.y * d.x);
+        slot[k] = make_double2(sh.x + u.x, sh.y + u.y);
+        slot[M - k] = make_double2(sh.x - u.x, -sh.y + u.y);
       }
       __syncthreads();
     }
@@ -175,14 +188,14 @@ static int rowfft_tables(nnpm_ctx* ctx) {
 
 template <int R1, int R2, bool INVERSE>
 static int rowfft_go(nnpm_ctx* ctx, const RowFftArgs& a) {
-  constexpr int M = R1 * R2, RM = R1 > R2 ? R1 : R2;
+  constexpr int M = R1 * R2;
   constexpr int SLOT = R1 * (R2 + 1) > M + 1 ? R1 * (R2 + 1) : M + 1;
-  const size_t smem = (size_t)4 * SLOT * 16 + (size_t)2 * M * 16;
+  const size_t smem = (size_t)4 * SLOT * 16 + (size_t)M * 16 + (size_t)(M / 2 + 1) * 16;
   CK(cudaFuncSetAttribute(k_rowfft<R1, R2, INVERSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const i64 ngroups = (a.nrows + 3) / 4;
-  const i64 maxg = (i64)ctx->nsm * (M > 512 ? 2 : M == 512 ? 3 : 4);
+  const i64 maxg = (i64)ctx->nsm * (M > 512 ? 2 : 4);
   const unsigned grid = (unsigned)(ngroups < maxg ? ngroups : maxg);
-  k_rowfft<R1, R2, INVERSE><<<grid, 4 * RM, smem, ctx->st>>>(a);
+  k_rowfft<R1, R2, INVERSE><<<grid, 4 * R2, smem, ctx->st>>>(a);
   LAUNCHED(ctx);
   KCHECK();
   return NNPM_OK;

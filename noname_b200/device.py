@@ -150,6 +150,18 @@ class DevicePM:
         self._ck(self._L.nnpm_init_synthetic(self._h, k, pd, int(seed), int(nmodes), int(kmax),
                                              float(disp_rms), float(vfac), self.m))
 
+    def init_grf(self, pdims, seed=12345, ps_index=-1.0, disp_rms=0.0, vfac=0.0, m=1.0):
+        """PowerSpectrumParticles + scaleFreePS(ps_index, .) on the device, seeded (ParticleMesh.jl:209-254)."""
+        pd = (C.c_int64 * 3)(*[int(p) for p in pdims])
+        self.m = float(m)
+        self._ck(self._L.nnpm_init_grf(self._h, pd, int(seed), float(ps_index), float(disp_rms), float(vfac), self.m))
+
+    def init_pancake(self, pdims, xamp, vamp, m=1.0):
+        """ZeldovichPancakeParticles on the device (ParticleMesh.jl:177-198): xamp = 2/5 A a, vamp = 2/5 A adot."""
+        pd = (C.c_int64 * 3)(*[int(p) for p in pdims])
+        self.m = float(m)
+        self._ck(self._L.nnpm_init_pancake(self._h, pd, float(xamp), float(vamp), self.m))
+
     def sort(self):
         self._ck(self._L.nnpm_sort(self._h))
 

@@ -480,6 +480,65 @@ def synthetic_clustered(pdims, rank, seed, nblobs, sigma, vdisp):
     return x, v
 
 
+def grf_spectrum(pdims, comp, seed, ps_index):
+    """Half spectrum c_d[k, j, i] (i <= P1/2) of displacement component `comp`, PowerSpectrumParticles :224-240 with
+    scaleFreePS P(k) = k^n (InputPowerSpectra.jl:26; the norm drops out of the rescaled field): amplitude
+    sqrt(P(|k|)) (g1 - i g2)/2 / k^2 * k_d, k in rad/cell via fftfreq (:202-206), k = 0 skipped.  Deviations SURVEY.md
+    8(d) prescribes and nnpm_init_grf implements: SEEDED draws (mix64 keyed by the mode's linear index), one complex
+    amplitude per mode shared by the components, Hermitian i = 0 and i = P1/2 planes."""
+    P1, P2, P3 = (int(q) for q in pdims)
+    icn = P1 // 2 + 1
+    K, J, I = np.meshgrid(np.arange(P3), np.arange(P2), np.arange(icn), indexing="ij")
+
+    def kf(idx, n):
+        w = np.where(idx > n // 2, idx - n, idx).astype(np.float64)
+        return (2.0 * math.pi * w) / float(n)
+
+    edge = (I == 0) | (2 * I == P1)
+    Jm, Km = (P2 - J) % P2, (P3 - K) % P3
+    a, b = J + P2 * K, Jm + P2 * Km
+    conj = edge & (b < a)
+    real_only = edge & (b == a)
+    Jc, Kc = np.where(conj, Jm, J), np.where(conj, Km, K)
+    kk = [kf(I, P1), kf(Jc, P2), kf(Kc, P3) if P3 > 1 else np.zeros(I.shape)]
+    k2 = kk[0] * kk[0] + kk[1] * kk[1] + kk[2] * kk[2]
+    nz = k2 > 0.0
+    k2s = np.where(nz, k2, 1.0)
+    psv = np.sqrt(np.power(np.sqrt(k2s), ps_index))
+    with np.errstate(over="ignore"):
+        lin = I.astype(np.uint64) + np.uint64(icn) * (Jc.astype(np.uint64) + np.uint64(P2) * Kc.astype(np.uint64))
+        h = _mix64(np.uint64(seed) ^ _mix64(lin))
+        u1, u2 = _u01(_mix64(h + np.uint64(1))), _u01(_mix64(h + np.uint64(2)))
+    r = np.sqrt(-2.0 * np.log(u1))
+    g1, g2 = r * np.cos(2.0 * math.pi * u2), r * np.sin(2.0 * math.pi * u2)
+    re = np.where(nz, psv * g1 / k2s / 2.0, 0.0) * kk[comp]
+    im = np.where(nz, -(psv * g2 / k2s) / 2.0, 0.0) * kk[comp]
+    im = np.where(conj, -im, im)
+    im = np.where(real_only, 0.0, im)
+    return re + 1j * im
+
+
+def synthetic_grf(pdims, rank, seed, ps_index, disp_rms, vfac):
+    """Seeded Gaussian-random-field Zel'dovich ICs (checker of nnpm_init_grf): x = wrap(q + s psi), v = vfac s psi with
+    psi_d = irfft(c_d) on the particle lattice (:241) and s rescaling psi to a per-component RMS of disp_rms."""
+    P1, P2, P3 = (int(q) for q in pdims)
+    if rank == 2:
+        P3 = 1
+    q = initialize_particles_uniform(pdims, rank)
+    psi = np.empty_like(q)
+    for d in range(rank):
+        c = grf_spectrum((P1, P2, P3), d, seed, ps_index)
+        f = sfft.irfftn(c, s=(P3, P2, P1), axes=(0, 1, 2)) * float(P1 * P2 * P3)   # unnormalised, like the device
+        psi[:, d] = f.reshape(-1)
+    rms = math.sqrt(float(np.sum(psi * psi)) / (psi.shape[0] * rank))
+    s = disp_rms / rms if rms > 0 else 0.0
+    psi *= s
+    x = q + psi
+    v = vfac * psi
+    make_periodic(x)
+    return x, v
+
+
 # --------------------------------------------------------------------------------------
 # P(k)                                                            ParticleMesh.jl:65-100, 202-206
 # --------------------------------------------------------------------------------------

@@ -104,7 +104,7 @@ def test_abi_mismatch_and_bad_arguments_are_rejected(lib_built):
     cfg.struct_size = C.sizeof(_lib.Config)
     cfg.rank = 4
     assert lib_built.nnpm_create(C.byref(h), C.byref(cfg)) == -1
-    assert lib_built.nnpm_version() == 1
+    assert lib_built.nnpm_version() == 2
     assert lib_built.nnpm_destroy(None) == 0
 
 

@@ -155,6 +155,9 @@ def test_lattice_matches_oracle():
 
 def test_unknown_or_broken_problem_definitions_raise(tmp_path):
     c = cf.load_conf(_write(tmp_path, "TopgridDimensions=[8,8,1]\nParticleDimensions=[8,8,1]\nProblemDefinition = PowerSpectrumParticles\n"), user_default=False)
+    with pytest.raises(KeyError):                 # :212-216: InputPowerSpectrum is required
+        PM.InitializeParticleSimulation({}, {}, {}, c)
+    c["InputPowerSpectrum"] = "multiplePeaksPS(-1, 1, [0.1, 1, 10], 1.)"     # as shipped in run/PM: not provided
     with pytest.raises(NotImplementedError):
         PM.InitializeParticleSimulation({}, {}, {}, c)
     c["ProblemDefinition"] = "Nope"
@@ -166,6 +169,34 @@ def test_unknown_or_broken_problem_definitions_raise(tmp_path):
         PM.deposit(np.zeros((1, 4, 4)), np.zeros((1, 2)), 1.0, interpolation="tsc")
 
 
+def test_power_spectrum_particles_are_generated_on_the_device(tmp_path):
+    """PowerSpectrumParticles + scaleFreePS (ParticleMesh.jl:209-254, InputPowerSpectra.jl:26): the host only records
+    the request (seed, spectral index, RMS displacement, growing-mode velocity factor); nothing is allocated"""
+    c = cf.load_conf(_write(tmp_path, SHIPPED_COSMO_CONF.replace("ProblemDefinition = ZeldovichPancakeParticles",
+                                                                  "ProblemDefinition = PowerSpectrumParticles\nInputPowerSpectrum = scaleFreePS(-1, .3)")),
+                     user_default=False)
+    gp, gd, p = {}, {}, {}
+    PM.InitializeParticleSimulation(gp, gd, p, c)
+    assert p["x"] is None and p["v"] is None
+    kind, kw = p["_ic"]
+    oc = O.Cosmo(h=1.0, OmegaM=1.0, OmegaR=0.0)
+    a = O.a_from_t_internal(oc, c["StartTime"], 400, zwherea1=400)
+    ad = O.dadt_from_t_internal(oc, c["StartTime"], 400)
+    assert kind == "grf" and kw["ps_index"] == -1.0 and kw["seed"] == 12345
+    assert kw["disp_rms"] == pytest.approx(0.3 / 64) and kw["vfac"] == pytest.approx(ad / a, rel=1e-9)
+
+
+def test_device_initial_conditions_key_defers_pancake_and_lattice(tmp_path):
+    c = cf.load_conf(_write(tmp_path, SHIPPED_COSMO_CONF + "DeviceInitialConditions = true\n"), user_default=False)
+    gp, gd, p = {}, {}, {}
+    PM.InitializeParticleSimulation(gp, gd, p, c)
+    assert p["x"] is None and p["_ic"][0] == "pancake"
+    oc = O.Cosmo(h=1.0, OmegaM=1.0, OmegaR=0.0)
+    A = 5.0 * 11.0 / 2.0 / 401.0
+    assert p["_ic"][1]["xamp"] == pytest.approx(0.4 * A * O.a_from_t_internal(oc, c["StartTime"], 400, zwherea1=400), rel=1e-9)
+    assert p["_ic"][1]["vamp"] == pytest.approx(0.4 * A * O.dadt_from_t_internal(oc, c["StartTime"], 400), rel=1e-9)
+
+
 # ------------------------------------------------------------------------------ evolve loops: dt control
 class _FakeStats:
     def __init__(self, mv):
@@ -175,9 +206,15 @@ class _FakeStats:
 class _FakeDev:
     """records the scalars the loops hand to the device; returns scripted max|v| values"""
     rank = 2
+    nranks = 1
+    rank_id = 0
 
     def __init__(self, maxv):
-        self.maxv, self.calls = maxv, []
+        self.maxv, self.calls, self.keep = maxv, [], []
+
+    def set_option(self, name, value):
+        assert name == "keep_rho"
+        self.keep.append(bool(value))
 
     def step_static(self, dt):
         self.calls.append((dt,))
@@ -214,6 +251,26 @@ def test_evolvepm_dt_control_matches_oracle_rules(monkeypatch):
     assert sum(dts) == pytest.approx(0.1, rel=1e-12) and c["CurrentTime"] >= 0.1
     assert dts[-1] <= courant * (1 + 1e-12)
     assert c["CurrentCycle"] == len(dts)
+    # outputs disabled: the density is kept (copied on the device) for the last step only
+    assert fake.keep == [False] * (len(dts) - 1) + [True]
+
+
+def test_keep_rho_is_requested_exactly_for_steps_followed_by_an_output(monkeypatch, tmp_path):
+    """gd[1].d["ρD"] of the reference holds the last deposit whenever analyzePM writes (ParticleMesh.jl:767 / :857,
+    IOtools.jl:94-116): the loop asks the device to keep the density for those steps and no others"""
+    fake = _FakeDev(2.0)
+    monkeypatch.setattr(PM, "_device_for", lambda gp, p, c: fake)
+    synced = []
+    monkeypatch.setattr(PM, "_sync_host", lambda *a, **k: synced.append(len(fake.calls)))
+    c = dict(cf.DEFAULTS, StartTime=0.0, StopTime=1.0, StopCycle=7, InitialDt=1e-3, CourantFactor=0.5, MaximumDt=0.03,
+             OutputEveryNCycle=3, OutputDirectory=str(tmp_path / "out"), ParticleDimensions=[8, 8, 1])
+    gp = {1: PM.GridPatch([0, 0, 0], [1, 1, 1], 1, 1, (16, 16, 1))}
+    gd = {1: PM.GridData({"ρD": np.ones((1, 16, 16)), "Φ": np.ones((1, 16, 16))})}
+    p = {"x": np.zeros((4, 2)), "v": np.zeros((4, 2)), "m": 1.0}
+    PM.evolvePM(gp, gd, p, c)
+    assert len(fake.calls) == 7
+    assert fake.keep == [False, False, True, False, False, True, True]     # cycles 3 and 6 write; 7 ends the loop
+    assert synced == [3, 6, 7]
 
 
 def test_evolvepmcosmology_scalars_and_dt(monkeypatch, tmp_path):

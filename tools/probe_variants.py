@@ -1,5 +1,5 @@
 # perf probe over kernel variants on ONE device context (scratch; not part of the product):
-#   python tools/probe_variants.py 1024 "push_persist=1" "push_persist=2" "deposit_unroll=2,push_persist=1"
+#   python tools/probe_variants.py 1024 base "zfused=2" "rowfft=0" "rowfft=0,zfused=2"
 # Each argument after the size is one variant (comma-separated option=value pairs applied on top of
 # the defaults; "base" = defaults).  Prints mean deposit / solve / push / wall ms over the last 4 of 5 steps.
 import os
@@ -19,13 +19,15 @@ else:
     dev.init_synthetic((n, n, n), seed=1, nmodes=32, kmax=8, disp_rms=0.3 / n, vfac=0.05, m=0.3)
 dev.sort()
 print("device GB", dev.device_bytes / 1e9, "ic", ic, flush=True)
+DEFAULTS = {"rowfft": 1, "colfft": 1, "zfused": 3, "fft3d": 0, "tile_deposit": 1, "tile_push": 1, "bulk_flush": 1,
+            "l2pf_push": 1, "l2pf_deposit": 1, "cfrun_y": 1, "zsplit": 0}
 known = {}
 for var in variants:
     opts = {} if var == "base" else dict(kv.split("=") for kv in var.split(","))
     for k in known:                       # back to the defaults recorded so far
         dev.set_option(k, known[k])
     for k, v in opts.items():
-        known.setdefault(k, 0.0 if k != "deposit_unroll" else 1.0)
+        known.setdefault(k, float(DEFAULTS[k]))
         dev.set_option(k, float(v))
     acc = {}
     walls = []
@@ -38,5 +40,6 @@ for var in variants:
             for k, v in st.as_dict()["ms"].items():
                 acc[k] = acc.get(k, 0.0) + v / (nsteps - 1)
     d = st.as_dict()
-    print("%-40s dep %.2f solve %.2f (z %.2f) push %.2f wall %.2f | untiled %d maxv %.6g maxpa %.6g" % (
-        var, acc["deposit"], acc["solve"], acc["fft_z"], acc["push"], sum(walls[1:]) / (nsteps - 1), d["n_untiled"], d["max_abs_v"], d["max_pa"]), flush=True)
+    print("%-32s dep %.2f solve %.2f (x %.2f y %.2f z %.2f) push %.2f wall %.2f | untiled %d maxv %.9g maxpa %.9g" % (
+        var, acc["deposit"], acc["solve"], acc["fft_x"], acc["fft_y"], acc["fft_z"], acc["push"], sum(walls[1:]) / (nsteps - 1),
+        d["n_untiled"], d["max_abs_v"], d["max_pa"]), flush=True)
