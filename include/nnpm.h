@@ -205,6 +205,9 @@ int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, in
  * fastest measured paths; the other values are the library / un-fused compositions the tests cross-check against.
  *   "rowfft"       1 = own row-FFT kernels for the x passes (r2c / c2r, bulk-copy staged; default when N1/2 is
  *                  64..1024), 0 = cuFFT batched 1-D plans
+ *   "fft2d"        1 = x and y passes of a plane in ONE persistent kernel with the intermediate held in L2 (work queue
+ *                  of row / column items, per-plane completion counters; N1 = N2 in 128..1024); 0 = separate kernels
+ *   "fft2d_block"  planes per block of that kernel (default 4: ~34 MB of intermediate in flight at 1024^2)
  *   "colfft"       1 = TMA-staged column FFT for the y passes (default when N2 is 64..1024), 0 = cuFFT 2-D plans
  *   "zfused"       3 = fused z-FFT * Green * z-iFFT kernel, persistent, next column group loaded by TMA during the
  *                  whole transform (separate landing zone + half-size split exchange; default; N3 = 64..1024),
@@ -213,6 +216,8 @@ int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, in
  *   "fft3d"        1 = single cuFFT 3-D plan instead of the passes above (nranks == 1 only)
  *   "tile_deposit" 1 = shared-memory tiled deposit on tile-sorted particles (default), 0 = global atomics
  *   "tile_push"    1 = push gathers phi from a shared-memory tile on sorted particles, 0 = L2 gather
+ *   "sort_cells"   1 = the counting sort orders the particles of a tile by cell (bins = mesh cells of the slab; default
+ *                  while the slab has <= 2^30 cells), 0 = by tile only (arrival order within a tile)
  *   "bulk_flush"   1 = tiled deposit flushes its box with cp.reduce.async.bulk (default), 0 = per-cell atomics
  *   "l2pf_push"    1 = each CTA of the tiled push pulls its work item's x, v runs into L2 with one
  *                  cp.async.bulk.prefetch.L2 per array before it stages its phi box (default), 0 = off

@@ -67,7 +67,9 @@ struct nnpm_ctx {
   i64 stage_elems;
 
   // sort scratch
-  uint32_t *hist, *bsum, *bsum2, *skey, *srnk;
+  uint32_t *hist, *hist_fine, *bsum, *bsum2, *skey, *srnk;   // hist: tile offsets; hist_fine: (tile, cell) bin offsets of the cell-order sort
+  i64 bsum_cap;
+  int opt_sort_cells;
   uint32_t *wcnt, *wtile, *wbeg;  // work list of the tiled kernels (k_work_count / k_work_fill)
   i64 wcap;
   TileGeom tg;
@@ -129,6 +131,8 @@ struct nnpm_ctx {
   cudaEvent_t ev_chunk[4];
   int opt_l2pf_push, opt_l2pf_deposit, opt_colfft, opt_cfrun_y, opt_rowfft, opt_fuse_transpose, opt_mig_in_push, nsm;
   double2 *xtwM, *xtwN;         // x-pass twiddles W_M^m, W_N^k (nnpm_rowfft.cuh)
+  unsigned* f2_sync;            // work queue, fault flag and per-plane counters of the fused 2-D transform (k_fft2d)
+  int opt_fft2d, opt_fft2d_block;
   struct PeerMaps* peer_maps;   // tensor maps over every rank's transposed spectrum (fused forward transpose)
   cudaStream_t st2[4];    // side streams: the blocks of a transpose go out on several copy engines at once
   cudaEvent_t ev_fork, ev_join[4];
@@ -373,7 +377,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->acc = nullptr; c->pa[0] = c->pa[1] = c->pa[2] = nullptr;
   c->acc_valid = c->pa_valid = false;
   c->stage = nullptr; c->stage_elems = 0;
-  c->hist = c->bsum = c->bsum2 = c->skey = c->srnk = nullptr;
+  c->hist = c->hist_fine = c->bsum = c->bsum2 = c->skey = c->srnk = nullptr; c->bsum_cap = 0; c->opt_sort_cells = 1;
   c->wcnt = c->wtile = c->wbeg = nullptr; c->wcap = 0;
   c->have2 = c->havez = c->have3 = false;
   c->have_tmap = false;
@@ -394,6 +398,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->have_tm_y = c->have_tm_z8 = c->have_tm_z4 = c->have1 = false; c->opt_zsplit = 0; c->ytw = nullptr;
   c->opt_l2pf_push = 1; c->opt_l2pf_deposit = 1; c->opt_colfft = 1; c->opt_cfrun_y = 1; c->opt_rowfft = 1; c->opt_fuse_transpose = 0; c->opt_mig_in_push = 1;
   c->xtwM = c->xtwN = nullptr; c->peer_maps = nullptr; c->nsm = 148;
+  c->f2_sync = nullptr; c->opt_fft2d = 0; c->opt_fft2d_block = 4;
   c->mig_lo = nullptr; c->ghost_rx = nullptr; c->red_buf = nullptr;
   c->np = 0; c->m = 0.0; c->ids_dirty = false; c->field_state = 0; c->first_id = 0;
   c->own_stream = false;
@@ -690,17 +695,33 @@ extern "C" int nnpm_init_synthetic(nnpm_ctx* ctx, int kind, const int64_t pdims[
 // ------------------------------------------------------------------------------------------
 // K0 sort
 // ------------------------------------------------------------------------------------------
+// exclusive scan of n uint32 in place (up to SCAN_ITEMS^3 entries); bsum / bsum2 hold the block sums of the two levels
 static int scan_u32(nnpm_ctx* ctx, uint32_t* data, i64 n) {
-  // exclusive scan, up to SCAN_BLOCK^3 entries (three levels)
-  i64 nb1 = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-  i64 nb2 = (nb1 + SCAN_BLOCK - 1) / SCAN_BLOCK;
-  if (nb2 > SCAN_BLOCK) return fail(ctx, NNPM_ERR_ARG, "scan too large");
-  k_scan_block<<<(unsigned)nb1, SCAN_BLOCK, 0, ctx->st>>>(data, ctx->bsum, n);
-  k_scan_block<<<(unsigned)nb2, SCAN_BLOCK, 0, ctx->st>>>(ctx->bsum, ctx->bsum2, nb1);
-  k_scan_block<<<1, SCAN_BLOCK, 0, ctx->st>>>(ctx->bsum2, ctx->bsum2 + SCAN_BLOCK, nb2);
-  k_scan_add<<<(unsigned)nb2, SCAN_BLOCK, 0, ctx->st>>>(ctx->bsum, ctx->bsum2, nb1);
-  k_scan_add<<<(unsigned)nb1, SCAN_BLOCK, 0, ctx->st>>>(data, ctx->bsum, n);
-  ctx->launches += 5;
+  const i64 nb1 = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
+  const i64 nb2 = (nb1 + SCAN_ITEMS - 1) / SCAN_ITEMS;
+  if (nb2 > SCAN_ITEMS) return fail(ctx, NNPM_ERR_ARG, "scan too large");
+  if (nb1 > ctx->bsum_cap) {
+    CKR(dalloc(ctx, &ctx->bsum, (size_t)nb1 + 16));   // (the previous, smaller buffer stays in ctx->allocs until destroy)
+    ctx->bsum_cap = nb1;
+  }
+  if (!ctx->bsum2) CKR(dalloc(ctx, &ctx->bsum2, (size_t)SCAN_ITEMS + 16));
+  if (nb1 == 1) {
+    k_scan_apply<<<1, 256, 0, ctx->st>>>(data, nullptr, n);
+    LAUNCHED(ctx);
+  } else {
+    k_scan_reduce<<<(unsigned)nb1, 256, 0, ctx->st>>>(data, ctx->bsum, n);
+    if (nb2 == 1) {
+      k_scan_apply<<<1, 256, 0, ctx->st>>>(ctx->bsum, nullptr, nb1);
+      ctx->launches += 2;
+    } else {
+      k_scan_reduce<<<(unsigned)nb2, 256, 0, ctx->st>>>(ctx->bsum, ctx->bsum2, nb1);
+      k_scan_apply<<<1, 256, 0, ctx->st>>>(ctx->bsum2, nullptr, nb2);
+      k_scan_apply<<<(unsigned)nb2, 256, 0, ctx->st>>>(ctx->bsum, ctx->bsum2, nb1);
+      ctx->launches += 4;
+    }
+    k_scan_apply<<<(unsigned)nb1, 256, 0, ctx->st>>>(data, ctx->bsum, n);
+    LAUNCHED(ctx);
+  }
   KCHECK();
   return NNPM_OK;
 }
@@ -710,20 +731,29 @@ extern "C" int nnpm_sort(nnpm_ctx* ctx) {
   CK(cudaSetDevice(ctx->cfg.device));
   const i64 np = ctx->np;
   if (np == 0) return NNPM_OK;
-  if (!ctx->hist) {
-    CKR(dalloc(ctx, &ctx->hist, (size_t)ctx->ntiles + 1));
-    i64 nb1 = (ctx->ntiles + SCAN_BLOCK) / SCAN_BLOCK + 1;
-    CKR(dalloc(ctx, &ctx->bsum, (size_t)nb1 + SCAN_BLOCK));
-    CKR(dalloc(ctx, &ctx->bsum2, (size_t)2 * SCAN_BLOCK + 2));
-  }
+  if (!ctx->hist) CKR(dalloc(ctx, &ctx->hist, (size_t)ctx->ntiles + 1));
   if (!ctx->skey) CKR(dalloc(ctx, &ctx->skey, (size_t)ctx->cap));
   if (!ctx->srnk) CKR(dalloc(ctx, &ctx->srnk, (size_t)ctx->cap));
-  CK(cudaMemsetAsync(ctx->hist, 0, (size_t)(ctx->ntiles + 1) * 4, ctx->st));
-  if (ctx->R == 3) k_sort_count<3><<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->pp, np, ctx->g, ctx->tg, ctx->hist, ctx->skey, ctx->srnk);
-  else k_sort_count<2><<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->pp, np, ctx->g, ctx->tg, ctx->hist, ctx->skey, ctx->srnk);
+  // cell-order sort ("sort_cells", default): bins = (tile, cell in tile); needs a counter per mesh cell of the slab
+  const int cpt = ctx->tg.tx * ctx->tg.ty * ctx->tg.tz;
+  const i64 nbins = ctx->ntiles * (i64)cpt;
+  const bool fine = ctx->opt_sort_cells && nbins <= (1ll << 30) && np < (1ll << 32);
+  uint32_t* bins = ctx->hist;
+  i64 nb = ctx->ntiles;
+  if (fine) {
+    if (!ctx->hist_fine) CKR(dalloc(ctx, &ctx->hist_fine, (size_t)nbins + 16));
+    bins = ctx->hist_fine;
+    nb = nbins;
+  }
+  CK(cudaMemsetAsync(bins, 0, (size_t)(nb + 1) * 4, ctx->st));
+  if (ctx->R == 3) k_sort_count<3><<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->pp, np, ctx->g, ctx->tg, fine ? cpt : 0, bins, ctx->skey, ctx->srnk);
+  else k_sort_count<2><<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->pp, np, ctx->g, ctx->tg, fine ? cpt : 0, bins, ctx->skey, ctx->srnk);
   LAUNCHED(ctx);
-  CKR(scan_u32(ctx, ctx->hist, ctx->ntiles + 1));
-  k_sort_dest<<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->skey, ctx->srnk, ctx->hist, np);
+  CKR(scan_u32(ctx, bins, nb));   // bins[nb] is not needed by k_sort_dest
+  k_sort_dest<<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->skey, ctx->srnk, bins, np);
+  LAUNCHED(ctx);
+  if (fine) k_tile_offsets<<<nblk(ctx->ntiles + 1, 256), 256, 0, ctx->st>>>(ctx->hist, bins, ctx->ntiles, cpt, (uint32_t)np);
+  else k_tile_offsets<<<nblk(ctx->ntiles + 1, 256), 256, 0, ctx->st>>>(ctx->hist, bins, ctx->ntiles, 1, (uint32_t)np);   // sets hist[ntiles] = np
   LAUNCHED(ctx);
   KCHECK();
   CKR(permute_all(ctx, ctx->skey));
@@ -887,7 +917,9 @@ static int fft_forward(nnpm_ctx* ctx, double2** Tout, bool z_too, cudaEvent_t* c
     return NNPM_OK;
   }
   const bool tim = comm_t != nullptr;  // the fused step passes its event array when timing = 1
-  if (ctx->opt_colfft && colfft_supported_n(g.N2)) {
+  if (ctx->opt_fft2d && !fuse && ctx->opt_colfft && ctx->opt_rowfft && fft2d_supported(ctx)) {
+    CKR(fft2d_xy(ctx, false));   // x and y passes in one kernel, intermediate in L2
+  } else if (ctx->opt_colfft && colfft_supported_n(g.N2)) {
     if (tim) CK(cudaEventRecord(ctx->ev_fft[0], ctx->st));
     CKR(fft_x(ctx, false));
     if (tim) CK(cudaEventRecord(ctx->ev_fft[1], ctx->st));
@@ -927,7 +959,9 @@ static int fft_inverse(nnpm_ctx* ctx, bool z_too, cudaEvent_t* comm_t, bool fuse
     else CKR(comm_transpose_bwd(ctx));
     if (comm_t) CK(cudaEventRecord(comm_t[3], ctx->st));
   }
-  if (ctx->opt_colfft && colfft_supported_n(g.N2)) {
+  if (ctx->opt_fft2d && ctx->opt_colfft && ctx->opt_rowfft && fft2d_supported(ctx)) {
+    CKR(fft2d_xy(ctx, true));
+  } else if (ctx->opt_colfft && colfft_supported_n(g.N2)) {
     const bool tim = comm_t != nullptr;
     if (tim) CK(cudaEventRecord(ctx->ev_fft[4], ctx->st));
     CKR(colfft_y(ctx, true));
@@ -1166,8 +1200,9 @@ static int launch_push(nnpm_ctx* ctx, bool comoving, const PushParams& pp) {
     return NNPM_OK;
   }
   // one CTA per work item, phi box staged by TMA, x / v by register loads behind a bulk L2 prefetch.  The variants
-  // measured slower in round 1 (DMA-warp particle streams, persistent double-buffered boxes, deeper register
-  // prefetch; profiles/r01_probe_logs) are no longer compiled.
+  // measured slower (round 1: DMA-warp particle streams, persistent double-buffered boxes, deeper register prefetch,
+  // profiles/r01_probe_logs; round 2: a streamed separable gather at 3 / 4 CTAs per SM, 26.3 / 32.6 ms against 25.9:
+  // the kernel is bound by shared-memory wavefronts, not by occupancy, profiles/r02_probe_logs) are no longer compiled.
   const size_t smem = (size_t)NNPM_BX * NNPM_BY * (RANK == 3 ? NNPM_BZ : 1) * sizeof(double);
   const i64 covered = ctx->sorted_np < np ? ctx->sorted_np : np;
   const WorkList wl = {ctx->wtile, ctx->wbeg, ctx->wcnt + ctx->ntiles};
@@ -1275,12 +1310,14 @@ static int do_step(nnpm_ctx* ctx, bool comoving, double dt, double a_d1, double 
       cudaEventElapsedTime(&ms, ev[12], ev[13]);
       stats->ms[NNPM_MS_FFT_Z] = ms;  // un-fused path: includes the inverse 2-D transforms' z part only
       stats->ms[NNPM_MS_FFT_XY] = stats->ms[NNPM_MS_SOLVE] - ms - stats->ms[NNPM_MS_COMM];
-      // x / y split of the 2-D transforms (only recorded on the un-pipelined path with the own y pass)
+      // x / y split of the 2-D transforms (only recorded on the un-pipelined path with separate x and y kernels)
       float a1, a2;
-      if (cudaEventElapsedTime(&a1, ctx->ev_fft[0], ctx->ev_fft[1]) == cudaSuccess && cudaEventElapsedTime(&a2, ctx->ev_fft[5], ctx->ev_fft[6]) == cudaSuccess)
-        stats->ms[NNPM_MS_FFT_X] = a1 + a2;
-      if (cudaEventElapsedTime(&a1, ctx->ev_fft[1], ctx->ev_fft[2]) == cudaSuccess && cudaEventElapsedTime(&a2, ctx->ev_fft[4], ctx->ev_fft[5]) == cudaSuccess)
-        stats->ms[NNPM_MS_FFT_Y] = a1 + a2;
+      if (!(ctx->opt_fft2d && fft2d_supported(ctx))) {
+        if (cudaEventElapsedTime(&a1, ctx->ev_fft[0], ctx->ev_fft[1]) == cudaSuccess && cudaEventElapsedTime(&a2, ctx->ev_fft[5], ctx->ev_fft[6]) == cudaSuccess)
+          stats->ms[NNPM_MS_FFT_X] = a1 + a2;
+        if (cudaEventElapsedTime(&a1, ctx->ev_fft[1], ctx->ev_fft[2]) == cudaSuccess && cudaEventElapsedTime(&a2, ctx->ev_fft[4], ctx->ev_fft[5]) == cudaSuccess)
+          stats->ms[NNPM_MS_FFT_Y] = a1 + a2;
+      }
       cudaGetLastError();  // events never recorded (cuFFT 2-D path): not an error
     }
   }
@@ -1312,8 +1349,11 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   else if (!strcmp(name, "tile_deposit")) ctx->opt_tile_deposit = v;
   else if (!strcmp(name, "tile_push")) ctx->opt_tile_push = v;
   else if (!strcmp(name, "bulk_flush")) ctx->opt_bulk_flush = v;
+  else if (!strcmp(name, "sort_cells")) ctx->opt_sort_cells = v;
   else if (!strcmp(name, "colfft")) ctx->opt_colfft = v;
   else if (!strcmp(name, "rowfft")) ctx->opt_rowfft = v;
+  else if (!strcmp(name, "fft2d")) ctx->opt_fft2d = v;
+  else if (!strcmp(name, "fft2d_block")) ctx->opt_fft2d_block = v;
   else if (!strcmp(name, "pipeline")) ctx->opt_pipeline = v;
   else if (!strcmp(name, "fuse_transpose")) ctx->opt_fuse_transpose = v;
   else if (!strcmp(name, "mig_in_push")) ctx->opt_mig_in_push = v;

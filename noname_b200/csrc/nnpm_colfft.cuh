@@ -171,7 +171,7 @@ struct ZDst {
 // of one); the Green factor uses the true bin kz = 2q + parity; after the inverse passes the two parities of a
 // column sit in lanes l and l ^ 4 of one warp and are combined by one shuffle exchange:
 // x[n] = E[n] + W_NT^-n O[n],  x[n + N] = E[n] - W_NT^-n O[n].
-template <int R1, int R2, bool TWO>
+template <int R1, int R2, bool TWO, bool PEER>
 __global__ void __launch_bounds__(8 * (R1 > R2 ? R1 : R2), 1)
 k_zfused_p(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ZDst dst, ColFftArgs a) {
   constexpr int C = 8, N = R1 * R2, RM = R1 > R2 ? R1 : R2, B1 = zf_log2(R1), B2 = zf_log2(R2);
@@ -296,7 +296,9 @@ k_zfused_p(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ZDs
           e = par ? zsub(o, e) : zadd(e, o);
         }
         const int nn = n + N * par;
-        if (colok) dst.base[nn >> dst.shift][(i64)(nn & dst.mask) * dst.plane_c + col] = e;
+        if (!colok) continue;
+        if (PEER) dst.base[nn >> dst.shift][(i64)(nn & dst.mask) * dst.plane_c + col] = e;
+        else dst.base[0][(i64)nn * dst.plane_c + col] = e;
       }
     }
   }
@@ -309,7 +311,7 @@ k_zfused_p(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ZDs
 // imaginary parts in two half-steps through a [N][8] buffer of DOUBLES (64 KB): 128 KB landing zone + 64 KB
 // exchange + 24 KB tables = 216 KB.  The exchange rows are skewed by 8 doubles per 32 rows so that the four rows a
 // warp touches in the scatter half-step fall on two bank groups (2 wavefronts per 256 bytes: the minimum).
-template <int R1, int R2>
+template <int R1, int R2, bool PEER>
 __global__ void __launch_bounds__(8 * (R1 > R2 ? R1 : R2), 1)
 k_zfused_s(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ZDst dst, ColFftArgs a) {
   constexpr int C = 8, N = R1 * R2, RM = R1 > R2 ? R1 : R2, B1 = zf_log2(R1), B2 = zf_log2(R2);
@@ -421,10 +423,13 @@ k_zfused_s(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ZDs
       }
       ZDif<R1, 0, +1>::run(v);
       const i64 col = (dst.row0 + jl) * (i64)a.icn + ic;
+      double2* const base0 = dst.base[0] + col;   // in place: one base for every row (no per-row constant-bank lookup)
 #pragma unroll
       for (int q = 0; q < R1; q++) {
         const int n = j + q * R2;
-        if (colok) dst.base[n >> dst.shift][(i64)(n & dst.mask) * dst.plane_c + col] = v[zf_brev(q, B1)];
+        if (!colok) continue;
+        if (PEER) dst.base[n >> dst.shift][(i64)(n & dst.mask) * dst.plane_c + col] = v[zf_brev(q, B1)];
+        else base0[(i64)n * dst.plane_c] = v[zf_brev(q, B1)];
       }
     }
     // the next iteration's first barrier (after its landing-zone reads) separates these exchange reads from the
@@ -592,9 +597,14 @@ static int zfused_p_launch(nnpm_ctx* ctx, double2* T, double scale, i64 jlbeg, i
 #define ZP(R1_, R2_, TWO_)                                                                                             \
   do {                                                                                                                 \
     const size_t smem = (size_t)R1_ * R2_ * (8 * 16 + (TWO_ ? 2 : 1) * (16 + 8));                                        \
-    CK(cudaFuncSetAttribute(k_zfused_p<R1_, R2_, TWO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
     const int grid = a.ngroups < ctx->nsm ? a.ngroups : ctx->nsm;                                                       \
-    k_zfused_p<R1_, R2_, TWO_><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(TWO_ ? ctx->tm_z4 : ctx->tm_z8, d, a); \
+    if (dst) {                                                                                                         \
+      CK(cudaFuncSetAttribute(k_zfused_p<R1_, R2_, TWO_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      k_zfused_p<R1_, R2_, TWO_, true><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(TWO_ ? ctx->tm_z4 : ctx->tm_z8, d, a); \
+    } else {                                                                                                           \
+      CK(cudaFuncSetAttribute(k_zfused_p<R1_, R2_, TWO_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      k_zfused_p<R1_, R2_, TWO_, false><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(TWO_ ? ctx->tm_z4 : ctx->tm_z8, d, a); \
+    }                                                                                                                  \
     LAUNCHED(ctx);                                                                                                     \
     KCHECK();                                                                                                          \
     return NNPM_OK;                                                                                                    \
@@ -645,9 +655,14 @@ static int zfused_s_launch(nnpm_ctx* ctx, double2* T, double scale, i64 jlbeg, i
   do {                                                                                                                 \
     constexpr int N_ = R1_ * R2_;                                                                                      \
     const size_t smem = (size_t)N_ * 8 * 16 + ((size_t)N_ * 8 + 8 * (N_ / 32)) * 8 + (size_t)N_ * 24;                    \
-    CK(cudaFuncSetAttribute(k_zfused_s<R1_, R2_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
     const int grid = a.ngroups < ctx->nsm ? a.ngroups : ctx->nsm;                                                       \
-    k_zfused_s<R1_, R2_><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(ctx->tm_z8, d, a);                         \
+    if (dst) {                                                                                                         \
+      CK(cudaFuncSetAttribute(k_zfused_s<R1_, R2_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+      k_zfused_s<R1_, R2_, true><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(ctx->tm_z8, d, a);                 \
+    } else {                                                                                                           \
+      CK(cudaFuncSetAttribute(k_zfused_s<R1_, R2_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+      k_zfused_s<R1_, R2_, false><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(ctx->tm_z8, d, a);                \
+    }                                                                                                                  \
     LAUNCHED(ctx);                                                                                                     \
     KCHECK();                                                                                                          \
     return NNPM_OK;                                                                                                    \

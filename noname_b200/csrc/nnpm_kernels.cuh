@@ -1212,9 +1212,12 @@ k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, WorkList wl, 
 // K0 counting sort by tile of NNPM_TX x NNPM_TY x NNPM_TZ cells (histogram -> scan -> scatter).
 // After the scan `hist` holds the tile offsets the tiled deposit / push kernels index by.
 // ------------------------------------------------------------------------------------------
+// cpt > 0 (cell-order sort): the bin is (tile, cell within the tile), x fastest -- after the sort the particles of a
+// tile are ordered by cell, so the 32 lanes of a warp work on ~32 consecutive cells of one mesh row: shared-memory
+// gathers and atomics of the tiled kernels become conflict-free runs instead of scattered accesses.  cpt == 0: tile bins.
 template <int RANK>
 __global__ void __launch_bounds__(256)
-k_sort_count(PartPtrs p, i64 np, Geom g, TileGeom tg, uint32_t* __restrict__ hist,
+k_sort_count(PartPtrs p, i64 np, Geom g, TileGeom tg, int cpt, uint32_t* __restrict__ hist,
              uint32_t* __restrict__ key, uint32_t* __restrict__ rnk) {
   const i64 n = blockIdx.x * (i64)blockDim.x + threadIdx.x;
   uint32_t t = 0xFFFFFFFFu;  // lanes past the end form their own group and do nothing
@@ -1230,11 +1233,12 @@ k_sort_count(PartPtrs p, i64 np, Geom g, TileGeom tg, uint32_t* __restrict__ his
       if (kl < 0) kl = 0;              // strays (not yet migrated) sort into the boundary tiles
       if (kl >= (int)g.nzl) kl = (int)g.nzl - 1;
     }
-    t = (uint32_t)((i / tg.tx) + tg.ntx * ((j / tg.ty) + tg.nty * (kl / tg.tz)));
+    const int ti = i / tg.tx, tj = j / tg.ty, tk = kl / tg.tz;
+    t = (uint32_t)(ti + tg.ntx * (tj + tg.nty * tk));
+    if (cpt) t = t * (uint32_t)cpt + (uint32_t)((i - ti * tg.tx) + tg.tx * ((j - tj * tg.ty) + tg.ty * (kl - tk * tg.tz)));
   }
-  // warp-aggregated histogram: particles arrive nearly sorted (lattice ICs, previous sorts), so a
-  // warp usually holds one or two distinct tiles -- one atomic per distinct tile instead of 32
-  // same-address atomics.
+  // warp-aggregated histogram: particles arrive nearly sorted (lattice ICs, previous sorts, collapsed halos), so a
+  // warp often holds few distinct bins -- one atomic per distinct bin instead of one per lane.
   const unsigned peers = __match_any_sync(0xffffffffu, t);
   const int lane = threadIdx.x & 31;
   const int leader = __ffs(peers) - 1;
@@ -1246,27 +1250,79 @@ k_sort_count(PartPtrs p, i64 np, Geom g, TileGeom tg, uint32_t* __restrict__ his
     rnk[n] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
   }
 }
-
-// exclusive scan of uint32 in three launches (block sums -> scan of sums -> add back)
-#define SCAN_BLOCK 1024
-__global__ void k_scan_block(uint32_t* data, uint32_t* bsum, i64 n) {
-  __shared__ uint32_t s[SCAN_BLOCK];
-  i64 t = blockIdx.x * (i64)SCAN_BLOCK + threadIdx.x;
-  uint32_t v = t < n ? data[t] : 0u;
-  s[threadIdx.x] = v;
-  __syncthreads();
-  for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
-    uint32_t a = threadIdx.x >= o ? s[threadIdx.x - o] : 0u;
-    __syncthreads();
-    s[threadIdx.x] += a;
-    __syncthreads();
-  }
-  if (t < n) data[t] = s[threadIdx.x] - v;  // exclusive
-  if (threadIdx.x == SCAN_BLOCK - 1) bsum[blockIdx.x] = s[threadIdx.x];
+// tile offsets out of the (scanned) bin offsets of a cell-order sort: toff[t] = boff[t * cpt], toff[ntiles] = np
+__global__ void k_tile_offsets(uint32_t* __restrict__ toff, const uint32_t* __restrict__ boff, i64 ntiles, int cpt, uint32_t np) {
+  const i64 t = blockIdx.x * (i64)blockDim.x + threadIdx.x;
+  if (t < ntiles) toff[t] = boff[t * (i64)cpt];
+  else if (t == ntiles) toff[t] = np;
 }
-__global__ void k_scan_add(uint32_t* data, const uint32_t* bsum, i64 n) {
-  i64 t = blockIdx.x * (i64)SCAN_BLOCK + threadIdx.x;
-  if (t < n) data[t] += bsum[blockIdx.x];
+
+// exclusive scan of uint32, reduce-then-scan: blocks of SCAN_ITEMS = 256 threads x 16 items.
+//   k_scan_reduce: bsum[b] = sum of block b;   (the block sums are scanned recursively)
+//   k_scan_apply : data[i] = bprefix[b] + exclusive prefix within block b  (thread-sequential 16 items, warp shuffles,
+//                  one shared-memory hop across the 8 warps)
+#define SCAN_ITEMS 4096
+__device__ __forceinline__ uint32_t scan_block_excl(uint32_t mine, uint32_t* total) {   // exclusive prefix of `mine` over 256 threads
+  __shared__ uint32_t wsum[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    if (w < warp) base += wsum[w];
+    tot += wsum[w];
+  }
+  __syncthreads();
+  if (total) *total = tot;
+  return base + inc - mine;
+}
+__global__ void __launch_bounds__(256) k_scan_reduce(const uint32_t* __restrict__ data, uint32_t* __restrict__ bsum, i64 n) {
+  const i64 b0 = blockIdx.x * (i64)SCAN_ITEMS + threadIdx.x * 16;
+  uint32_t acc = 0;
+  if (b0 + 16 <= n && ((size_t)(data + b0) & 15) == 0) {
+    const uint4* q = (const uint4*)(data + b0);
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const uint4 v = q[u]; acc += v.x + v.y + v.z + v.w; }
+  } else {
+    for (int u = 0; u < 16; u++) if (b0 + u < n) acc += data[b0 + u];
+  }
+  uint32_t tot;
+  scan_block_excl(acc, &tot);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(256) k_scan_apply(uint32_t* __restrict__ data, const uint32_t* __restrict__ bprefix, i64 n) {
+  const i64 b0 = blockIdx.x * (i64)SCAN_ITEMS + threadIdx.x * 16;
+  uint32_t v[16];
+  const bool fast = b0 + 16 <= n && ((size_t)(data + b0) & 15) == 0;
+  if (fast) {
+    const uint4* q = (const uint4*)(data + b0);
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const uint4 t = q[u]; v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w; }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 16; u++) v[u] = (b0 + u < n) ? data[b0 + u] : 0u;
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int u = 0; u < 16; u++) acc += v[u];
+  uint32_t run = scan_block_excl(acc, nullptr) + (bprefix ? bprefix[blockIdx.x] : 0u);
+#pragma unroll
+  for (int u = 0; u < 16; u++) { const uint32_t t = v[u]; v[u] = run; run += t; }
+  if (fast) {
+    uint4* q = (uint4*)(data + b0);
+#pragma unroll
+    for (int u = 0; u < 4; u++) q[u] = make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+  } else {
+#pragma unroll
+    for (int u = 0; u < 16; u++) if (b0 + u < n) data[b0 + u] = v[u];
+  }
 }
 __global__ void k_sort_dest(uint32_t* __restrict__ key, const uint32_t* __restrict__ rnk,
                             const uint32_t* __restrict__ off, i64 np) {

@@ -224,3 +224,266 @@ static int rowfft_x(nnpm_ctx* ctx, bool inverse, i64 plane0 = 0, i64 nplanes = -
 #undef RF
   return fail(ctx, NNPM_ERR_STATE, "row FFT does not support N1 = %lld", (long long)g.N1);
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused 2-D transform of the owned planes with the intermediate held in L2 (k_fft2d).
+//
+// Run as separate kernels, the x pass and the y pass each read and write the whole mesh from / to HBM: 4 x 8.6 GB per
+// direction at 1024^3.  A plane is only 8.4 MB, though, and the 126 MB L2 holds a dozen of them.  Here ONE persistent
+// kernel does both passes, plane block by plane block: its CTAs draw work items from a global queue ordered
+//     X(block 0) | X(block 1) Y(block 0) | X(block 2) Y(block 1) | ... | Y(last block)          (forward; B planes per block)
+// where X(p, g) transforms 8 rows of plane p (bulk-copy staged, as k_rowfft) and Y(p, c) one group of 4 columns of plane
+// p (TMA tensor copies, as k_colfft).  A Y item needs every row of its plane: each finished X item bumps a per-plane
+// counter (release), a Y item waits until the counter is complete (acquire).  Because items are started in queue order
+// and X items never wait, the oldest unfinished item can always run: no deadlock, and since a plane's Y items sit a
+// whole block behind its X items the wait is almost never taken.  The x output of a block (B x 8.4 MB) is still in L2
+// when the y pass reads it, and is overwritten there before it is ever evicted: HBM sees one read and one write of the
+// mesh per direction instead of two each.  Inverse direction: Y items first, X items (c2r) one block behind.
+// ------------------------------------------------------------------------------------------------------------------
+struct Fft2dArgs {
+  double* mesh;          // first owned plane
+  i64 rowp, plane;       // row / plane pitch in doubles
+  int nplanes, bplanes;  // planes to transform, planes per block (nplanes % bplanes == 0)
+  int icn, nicg;         // complex columns, column groups of 4
+  const double2* twM;    // x pass: W_M^m
+  const double2* twN;    // x pass: W_N^k
+  const double2* twY;    // y pass: W_N2^m
+  unsigned* queue;       // [0] next item; zeroed before the launch
+  unsigned* done;        // [nplanes] finished first-pass items per plane; zeroed before the launch
+  unsigned* fault;       // set when a dependency wait gave up (never in a correct run)
+};
+
+template <int R1, int R2, int R1Y, int R2Y, bool INVERSE>
+__global__ void __launch_bounds__(128, 2)
+k_fft2d(const __grid_constant__ CUtensorMap tmap, Fft2dArgs a) {
+  constexpr int CX = 128 / R2;                       // rows per X item: every lane busy in pass A of the row FFT
+  constexpr int M = R1 * R2, NY = R1Y * R2Y;
+  constexpr int SLOT = R1 * (R2 + 1) > M + 1 ? R1 * (R2 + 1) : M + 1;
+  constexpr int CY = 4, ESTY = R2Y + 1, B1Y = zf_log2(R1Y), B2Y = zf_log2(R2Y), RMY = R1Y > R2Y ? R1Y : R2Y;
+  constexpr int YBUF = R1Y * ESTY * CY > NY * CY ? R1Y * ESTY * CY : NY * CY;   // landing zone / exchange / output, aliased
+  constexpr int BUF = CX * SLOT > YBUF ? CX * SLOT : YBUF;
+  constexpr int RB = NY < 256 ? NY : 256, NOPS = NY / RB;
+  static_assert(4 * RMY <= 128 && CX * R2 == 128, "thread mapping");
+  extern __shared__ __align__(128) unsigned char f2_smem[];
+  double2* buf = (double2*)f2_smem;                  // [BUF]
+  double2* stwM = buf + BUF;                         // [M]
+  double2* stwH = stwM + M;                          // [M/2+1]
+  double2* stwY = stwH + (M / 2 + 1);                // [NY]
+  __shared__ __align__(8) unsigned long long full;
+  __shared__ unsigned s_item;
+  const int tid = threadIdx.x;
+  for (int t = tid; t < M; t += 128) stwM[t] = __ldg(a.twM + t);
+  for (int t = tid; t <= M / 2; t += 128) {
+    const double2 w = __ldg(a.twN + t);
+    stwH[t] = INVERSE ? make_double2(w.y, w.x) : make_double2(0.5 * w.y, -0.5 * w.x);
+  }
+  for (int t = tid; t < NY; t += 128) stwY[t] = __ldg(a.twY + t);
+  if (tid == 0) mbar_init(&full, 1);
+  __syncthreads();
+  const int N2 = NY;
+  const unsigned xpp = (unsigned)(N2 / CX), ypp = (unsigned)a.nicg;          // items per plane
+  const unsigned B = (unsigned)a.bplanes, nb = (unsigned)a.nplanes / B;
+  // first pass = X (forward) or Y (inverse); second pass one block behind
+  const unsigned f_pp = INVERSE ? ypp : xpp, s_pp = INVERSE ? xpp : ypp;
+  const unsigned S = B * (f_pp + s_pp);
+  const unsigned total = (unsigned)a.nplanes * (xpp + ypp);
+  constexpr unsigned IN_BYTES = INVERSE ? (M + 1) * 16u : M * 16u;
+  constexpr unsigned OUT_BYTES = INVERSE ? M * 16u : (M + 1) * 16u;
+  constexpr int NPAIR = M / 2 + 1;
+  constexpr int SIGNY = INVERSE ? +1 : -1;
+  unsigned phase = 0u;
+  for (;;) {
+    if (tid == 0) s_item = atomicAdd(a.queue, 1u);
+    __syncthreads();
+    const unsigned item = s_item;
+    __syncthreads();
+    if (item >= total) break;
+    // decode: (first | second pass, plane, sub-item)
+    bool second;
+    unsigned pl, sub;
+    if (item < B * f_pp) { second = false; pl = item / f_pp; sub = item % f_pp; }
+    else {
+      const unsigned i2 = item - B * f_pp, s = 1u + i2 / S, r = i2 % S;
+      if (s < nb && r < B * f_pp) { second = false; pl = s * B + r / f_pp; sub = r % f_pp; }
+      else {
+        const unsigned r2 = s < nb ? r - B * f_pp : r;
+        second = true; pl = (s - 1u) * B + r2 / s_pp; sub = r2 % s_pp;
+      }
+    }
+    const bool is_x = (second == INVERSE);
+    if (second) {
+      // dependency: every first-pass item of this plane has finished (and its stores are visible)
+      if (tid == 0) {
+        unsigned spins = 0;
+        while (atomicAdd(a.done + pl, 0u) < f_pp) {
+          __nanosleep(200);
+          if (++spins > (1u << 24)) { atomicExch(a.fault, 1u); break; }
+        }
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");   // the data was written, and is about to be read, through the async proxy
+      }
+    }
+    double* pbase = a.mesh + a.plane * (i64)pl;
+    if (is_x) {
+      const i64 row0 = (i64)sub * CX;
+      if (tid == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_expect_tx(&full, (unsigned)CX * IN_BYTES);
+        for (int r = 0; r < CX; r++) bulk_load_1d(buf + r * SLOT, pbase + (row0 + r) * a.rowp, IN_BYTES, &full);
+      }
+      mbar_wait(&full, phase);
+      phase ^= 1u;
+      if (INVERSE) {
+        for (int t = tid; t < CX * NPAIR; t += 128) {
+          double2* slot = buf + (t / NPAIR) * SLOT;
+          const int k = t % NPAIR;
+          double2 xa = slot[k], xb = slot[M - k];
+          if (k == 0) { xa.y = 0.0; xb.y = 0.0; }
+          const double2 h = stwH[k];
+          const double2 e = make_double2(xa.x + xb.x, xa.y - xb.y);
+          const double2 d = make_double2(xa.x - xb.x, xa.y + xb.y);
+          const double2 u = make_double2(h.x * d.x - h.y * d.y, h.x * d.y + h.y * d.x);
+          slot[k] = make_double2(e.x + u.x, e.y + u.y);
+          if (k != 0 && k != M - k) slot[M - k] = make_double2(e.x - u.x, -e.y + u.y);
+        }
+        __syncthreads();
+        rowfft_core<R1, R2, CX, SLOT, +1>(buf, stwM, tid);
+      } else {
+        rowfft_core<R1, R2, CX, SLOT, -1>(buf, stwM, tid);
+        for (int t = tid; t < CX * NPAIR; t += 128) {
+          double2* slot = buf + (t / NPAIR) * SLOT;
+          const int k = t % NPAIR;
+          const double2 za = slot[k], zb = slot[k == 0 ? 0 : M - k];
+          const double2 h = stwH[k];
+          const double2 sh = make_double2(0.5 * (za.x + zb.x), 0.5 * (za.y - zb.y));
+          const double2 d = make_double2(za.x - zb.x, za.y + zb.y);
+          const double2 u = make_double2(h.x * d.x - h.y * d.y, h.x * d.y + h.y * d.x);
+          slot[k] = make_double2(sh.x + u.x, sh.y + u.y);
+          slot[M - k] = make_double2(sh.x - u.x, -sh.y + u.y);
+        }
+        __syncthreads();
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        for (int r = 0; r < CX; r++) bulk_store_1d(pbase + (row0 + r) * a.rowp, buf + r * SLOT, OUT_BYTES);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else {
+      // ---- Y item: column group `sub` (4 complex columns) of plane pl, all N2 rows, single buffer
+      const int c = tid % CY, j = tid / CY;
+      if (tid == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_expect_tx(&full, (unsigned)(NY * CY * sizeof(double2)));
+#pragma unroll
+        for (int o = 0; o < NOPS; o++) tma_load_3d(buf + o * RB * CY, &tmap, (int)sub * 8, o * RB, (int)pl, &full);
+      }
+      mbar_wait(&full, phase);
+      phase ^= 1u;
+      double2 v[RMY];
+      if (j < R2Y) {
+#pragma unroll
+        for (int r = 0; r < R1Y; r++) v[r] = buf[(j + r * R2Y) * CY + c];
+        ZDif<R1Y, 0, SIGNY>::run(v);
+      }
+      __syncthreads();   // the group is in registers: the buffer becomes the padded exchange
+      if (j < R2Y) {
+#pragma unroll
+        for (int q = 0; q < R1Y; q++) buf[(q * ESTY + j) * CY + c] = v[zf_brev(q, B1Y)];
+      }
+      __syncthreads();
+      if (j < R1Y) {
+#pragma unroll
+        for (int r = 0; r < R2Y; r++) v[r] = buf[(j * ESTY + r) * CY + c];
+#pragma unroll
+        for (int r = 1; r < R2Y; r++) {
+          const double2 w = stwY[r * j];
+          v[r] = zmul(v[r], w.x, SIGNY < 0 ? w.y : -w.y);
+        }
+        ZDif<R2Y, 0, SIGNY>::run(v);
+      }
+      __syncthreads();   // the exchange is consumed: natural order for the tensor store
+      if (j < R1Y) {
+#pragma unroll
+        for (int q = 0; q < R2Y; q++) buf[(j + q * R1Y) * CY + c] = v[zf_brev(q, B2Y)];
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+#pragma unroll
+        for (int o = 0; o < NOPS; o++) tma_store_3d(&tmap, buf + o * RB * CY, (int)sub * 8, o * RB, (int)pl);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (!second && tid == 0) {
+      // publish: the stores must be COMPLETE (not merely read out of shared memory) before the counter moves
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __threadfence();
+      atomicAdd(a.done + pl, 1u);
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <int R1, int R2, int R1Y, int R2Y, bool INVERSE>
+static int fft2d_go(nnpm_ctx* ctx, const Fft2dArgs& a) {
+  constexpr int CX = 128 / R2, M = R1 * R2, NY = R1Y * R2Y;
+  constexpr int SLOT = R1 * (R2 + 1) > M + 1 ? R1 * (R2 + 1) : M + 1;
+  constexpr int YBUF = R1Y * (R2Y + 1) * 4 > NY * 4 ? R1Y * (R2Y + 1) * 4 : NY * 4;
+  constexpr int BUF = CX * SLOT > YBUF ? CX * SLOT : YBUF;
+  const size_t smem = ((size_t)BUF + M + (M / 2 + 1) + NY) * 16;
+  CK(cudaFuncSetAttribute(k_fft2d<R1, R2, R1Y, R2Y, INVERSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const i64 total = (i64)a.nplanes * (NY / CX + a.nicg);
+  const i64 maxg = (i64)ctx->nsm * 2;
+  const unsigned grid = (unsigned)(total < maxg ? total : maxg);
+  k_fft2d<R1, R2, R1Y, R2Y, INVERSE><<<grid, 128, smem, ctx->st>>>(ctx->tm_y, a);
+  LAUNCHED(ctx);
+  KCHECK();
+  return NNPM_OK;
+}
+
+static bool fft2d_supported(const nnpm_ctx* ctx) {
+  const Geom& g = ctx->g;
+  return g.N1 == g.N2 && (g.N1 == 128 || g.N1 == 256 || g.N1 == 512 || g.N1 == 1024);
+}
+
+// fused x + y passes over planes [plane0, plane0 + nplanes) of the owned slab, in place
+static int fft2d_xy(nnpm_ctx* ctx, bool inverse, i64 plane0 = 0, i64 nplanes = -1) {
+  const Geom& g = ctx->g;
+  CKR(rowfft_tables(ctx));
+  CKR(colfft_twiddles(ctx, &ctx->ytw, g.N2));
+  if (!ctx->have_tm_y) {
+    CKR(colfft_tensor_map(ctx, &ctx->tm_y, ctx->mesh + g.plane * g.glo, g.N2, g.nzl, ctx->icn * 16, g.plane * 8, true, g.N2));
+    ctx->have_tm_y = true;
+  }
+  if (nplanes < 0) nplanes = g.nzl;
+  if (nplanes == 0) return NNPM_OK;
+  if (!ctx->f2_sync) CKR(dalloc(ctx, &ctx->f2_sync, (size_t)g.nzl + 8));
+  CK(cudaMemsetAsync(ctx->f2_sync, 0, (size_t)(g.nzl + 8) * 4, ctx->st));
+  Fft2dArgs a;
+  a.mesh = ctx->mesh + g.plane * g.glo;   // plane indices are relative to the tensor map's origin: the first owned plane
+  a.rowp = g.rowp;
+  a.plane = g.plane;
+  a.nplanes = (int)nplanes;
+  const int want = ctx->opt_fft2d_block > 0 ? ctx->opt_fft2d_block : 4;
+  int b = want;
+  while (b > 1 && nplanes % b) b--;
+  a.bplanes = b;
+  a.icn = (int)ctx->icn;
+  a.nicg = (int)((ctx->icn + 3) / 4);
+  a.twM = ctx->xtwM; a.twN = ctx->xtwN; a.twY = ctx->ytw;
+  a.queue = ctx->f2_sync;
+  a.fault = ctx->f2_sync + 1;
+  a.done = ctx->f2_sync + 8;
+  if (plane0 != 0) return fail(ctx, NNPM_ERR_STATE, "fused 2-D transform: plane sub-ranges are not supported");
+#define F2(R1_, R2_, RY1_, RY2_) return inverse ? fft2d_go<R1_, R2_, RY1_, RY2_, true>(ctx, a) : fft2d_go<R1_, R2_, RY1_, RY2_, false>(ctx, a)
+  switch (g.N1) {
+    case 128: F2(8, 8, 16, 8);
+    case 256: F2(16, 8, 16, 16);
+    case 512: F2(16, 16, 32, 16);
+    case 1024: F2(32, 16, 32, 32);
+  }
+#undef F2
+  return fail(ctx, NNPM_ERR_STATE, "fused 2-D transform does not support N1 = N2 = %lld", (long long)g.N1);
+}

@@ -11,16 +11,19 @@ from noname_b200 import DevicePM
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 variants = sys.argv[2:] or ["base"]
-ic = os.environ.get("PROBE_IC", "zeldovich")
+ic = os.environ.get("PROBE_IC", "grf")
 dev = DevicePM((n, n, n), n ** 3, rank=3, timing=True, part_capacity=n ** 3, sort_every=0)
 if ic == "clustered":
     dev.init_synthetic((n, n, n), kind="clustered", seed=777, nmodes=100, kmax=1000, disp_rms=1.5 / n, vfac=2e-5, m=0.3)
-else:
+elif ic == "modes":
     dev.init_synthetic((n, n, n), seed=1, nmodes=32, kmax=8, disp_rms=0.3 / n, vfac=0.05, m=0.3)
+else:
+    dev.init_grf((n, n, n), seed=12345, ps_index=-1.0, disp_rms=0.3 / n, vfac=0.05, m=0.3)
 dev.sort()
 print("device GB", dev.device_bytes / 1e9, "ic", ic, flush=True)
 DEFAULTS = {"rowfft": 1, "colfft": 1, "zfused": 3, "fft3d": 0, "tile_deposit": 1, "tile_push": 1, "bulk_flush": 1,
-            "l2pf_push": 1, "l2pf_deposit": 1, "cfrun_y": 1, "zsplit": 0}
+            "l2pf_push": 1, "l2pf_deposit": 1, "cfrun_y": 1, "zsplit": 0, "sort_cells": 1, "fft2d": 0, "fft2d_block": 4,
+            "keep_rho": 0}
 known = {}
 for var in variants:
     opts = {} if var == "base" else dict(kv.split("=") for kv in var.split(","))
