@@ -423,7 +423,8 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   CKB(CKR(dalloc(c, &c->mesh, (size_t)g.plane * g.nplanes)));
   if (P > 1) {
     CKB(CKR(dalloc(c, &c->meshT, (size_t)g.plane * g.nzl)));
-    CKB(CKR(dalloc(c, &c->meshS, (size_t)g.plane * g.nzl)));
+    // meshS (staging of the grouped ncclSend / ncclRecv transposes) is allocated on first use: the peer-memory paths
+    // never need it, and at 2048^3 on 2 GPUs it would be another 34 GB
   }
   for (int d = 0; d < 3; d++) { c->pp.x[d] = nullptr; c->pp.v[d] = nullptr; }
   for (int d = 0; d < c->R; d++) {

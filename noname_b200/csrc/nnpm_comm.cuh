@@ -338,6 +338,7 @@ static int comm_transpose_fwd(nnpm_ctx* ctx) {
   NEED_COMM();
   const Geom& g = ctx->g;
   if (ctx->peer_ok && ctx->opt_peer) return comm_transpose_ce(ctx, true);
+  if (!ctx->meshS) CKR(dalloc(ctx, &ctx->meshS, (size_t)g.plane * g.nzl));
   const double2* A = (const double2*)(ctx->mesh + g.plane * g.glo);
   dim3 grid(nblk(ctx->icn, 128), (unsigned)g.N2, (unsigned)g.nzl);
   k_pack_fwd<<<grid, 128, 0, ctx->st>>>(A, (double2*)ctx->meshS, ctx->icn, g.N2, ctx->njl, g.nzl, g.plane / 2);
@@ -350,6 +351,7 @@ static int comm_transpose_bwd(nnpm_ctx* ctx) {
   NEED_COMM();
   const Geom& g = ctx->g;
   if (ctx->peer_ok && ctx->opt_peer) return comm_transpose_ce(ctx, false);
+  if (!ctx->meshS) CKR(dalloc(ctx, &ctx->meshS, (size_t)g.plane * g.nzl));
   CKR(comm_all_to_all(ctx, ctx->meshT, ctx->meshS));
   double2* A = (double2*)(ctx->mesh + g.plane * g.glo);
   dim3 grid(nblk(ctx->icn, 128), (unsigned)g.N2, (unsigned)g.nzl);

@@ -840,7 +840,15 @@ __device__ __forceinline__ void push_finish_fast(const PartPtrs& p, i64 n, const
   if (RANK == 3 && pp.mg.on) mig_emit(pp.mg, n, xo, vo);
 }
 
-#define NNPM_BX (NNPM_TX + 2 * NNPM_TH + 4)  // 37 used + 1: the TMA inner box extent must be a multiple of 16 B
+#define NNPM_BXU (NNPM_TX + 2 * NNPM_TH + 3)  // 37 box columns a tile's particles can touch
+// Row pitch of the box in shared memory, a multiple of 16 doubles (one 128-byte bank period): cell-sorted particles walk
+// a mesh row, then the next one; with pitch = 0 (mod 16) the bank of a lane's cell keeps advancing cyclically across
+// the row (and plane: BX * BY = 0 mod 16 too) break, so 32 lanes on ~32 consecutive cells stay at two lanes per 8-byte
+// bank -- the minimum for LDS.64 -- instead of piling the two row segments onto the same banks (pitch 38: 3.2 wavefronts
+// per gather, ncu r2f).  The 11 padding columns are filled by the same tensor copy and never read.
+#ifndef NNPM_BX
+#define NNPM_BX 48
+#endif
 #define NNPM_BY (NNPM_TY + 2 * NNPM_TH + 3)
 #define NNPM_BZ (NNPM_TZ + 2 * NNPM_TH + 3)
 
@@ -923,7 +931,7 @@ k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g
   // issued by one thread, completion on an mbarrier.  Tiles whose box wraps: cp.async row by row.
   const int bx0 = ti0 - NNPM_TH - 1, by0 = tj0 - NNPM_TH - 1;
   const int bz0 = (RANK == 3) ? tk0 - NNPM_TH - 1 + g.glo : g.glo;  // local plane of the box origin
-  const bool interior = bx0 >= 0 && bx0 + BX - 1 <= N1 && by0 >= 0 && by0 + BY <= N2 &&
+  const bool interior = bx0 >= 0 && bx0 + NNPM_BXU <= N1 && by0 >= 0 && by0 + BY <= N2 &&   // columns past N1 (padding only) are zero-filled by TMA
                         (RANK == 2 || g.glo != 0 || (bz0 >= 0 && bz0 + BZ <= N3));
   if (interior) {
     if (threadIdx.x == 0) {
@@ -949,10 +957,10 @@ k_push_tile(const __grid_constant__ CUtensorMap tmap, PartPtrs p, i64 np, Geom g
       double* dst = box + row * BX;
       if (valid) {
         __pipeline_memcpy_async(dst + lane, src + gi0, 8);
-        if (lane + 32 < BX - 1) __pipeline_memcpy_async(dst + lane + 32, src + gi1, 8);
+        if (lane + 32 < NNPM_BXU) __pipeline_memcpy_async(dst + lane + 32, src + gi1, 8);
       } else {
         dst[lane] = 0.0;
-        if (lane + 32 < BX - 1) dst[lane + 32] = 0.0;
+        if (lane + 32 < NNPM_BXU) dst[lane + 32] = 0.0;
       }
     }
     __pipeline_commit();

@@ -26,6 +26,40 @@ __device__ __forceinline__ void bulk_store_1d(void* gdst, const void* ssrc, unsi
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
 }
 
+// L2 eviction-priority hints for the fused 2-D transform: data read or written for the last time goes in as
+// evict_first, the intermediate between its two passes as evict_last
+__device__ __forceinline__ u64 l2_policy_evict_first() {
+  u64 p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ u64 l2_policy_evict_last() {
+  u64 p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_load_1d_hint(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar, u64 pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d_hint(void* gdst, const void* ssrc, unsigned bytes, u64 pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, unsigned long long* bar, u64 pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, u64 pol) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(tm), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+               : "memory");
+}
+
 struct RowFftArgs {
   double* mesh;        // first row
   i64 rowp;            // row pitch in doubles (2 * (N1/2 + 1))
@@ -280,6 +314,9 @@ k_fft2d(const __grid_constant__ CUtensorMap tmap, Fft2dArgs a) {
   for (int t = tid; t < NY; t += 128) stwY[t] = __ldg(a.twY + t);
   if (tid == 0) mbar_init(&full, 1);
   __syncthreads();
+  // first-pass items read their input for the last time and write the intermediate; second-pass items read the
+  // intermediate for the last time and write the final result
+  const u64 pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
   const int N2 = NY;
   const unsigned xpp = (unsigned)(N2 / CX), ypp = (unsigned)a.nicg;          // items per plane
   const unsigned B = (unsigned)a.bplanes, nb = (unsigned)a.nplanes / B;
@@ -329,7 +366,7 @@ k_fft2d(const __grid_constant__ CUtensorMap tmap, Fft2dArgs a) {
       if (tid == 0) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         mbar_expect_tx(&full, (unsigned)CX * IN_BYTES);
-        for (int r = 0; r < CX; r++) bulk_load_1d(buf + r * SLOT, pbase + (row0 + r) * a.rowp, IN_BYTES, &full);
+        for (int r = 0; r < CX; r++) bulk_load_1d_hint(buf + r * SLOT, pbase + (row0 + r) * a.rowp, IN_BYTES, &full, pol_first);
       }
       mbar_wait(&full, phase);
       phase ^= 1u;
@@ -366,7 +403,7 @@ k_fft2d(const __grid_constant__ CUtensorMap tmap, Fft2dArgs a) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
       if (tid == 0) {
-        for (int r = 0; r < CX; r++) bulk_store_1d(pbase + (row0 + r) * a.rowp, buf + r * SLOT, OUT_BYTES);
+        for (int r = 0; r < CX; r++) bulk_store_1d_hint(pbase + (row0 + r) * a.rowp, buf + r * SLOT, OUT_BYTES, second ? pol_first : pol_last);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     } else {
@@ -376,7 +413,7 @@ k_fft2d(const __grid_constant__ CUtensorMap tmap, Fft2dArgs a) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         mbar_expect_tx(&full, (unsigned)(NY * CY * sizeof(double2)));
 #pragma unroll
-        for (int o = 0; o < NOPS; o++) tma_load_3d(buf + o * RB * CY, &tmap, (int)sub * 8, o * RB, (int)pl, &full);
+        for (int o = 0; o < NOPS; o++) tma_load_3d_hint(buf + o * RB * CY, &tmap, (int)sub * 8, o * RB, (int)pl, &full, pol_first);
       }
       mbar_wait(&full, phase);
       phase ^= 1u;
@@ -411,7 +448,7 @@ k_fft2d(const __grid_constant__ CUtensorMap tmap, Fft2dArgs a) {
       __syncthreads();
       if (tid == 0) {
 #pragma unroll
-        for (int o = 0; o < NOPS; o++) tma_store_3d(&tmap, buf + o * RB * CY, (int)sub * 8, o * RB, (int)pl);
+        for (int o = 0; o < NOPS; o++) tma_store_3d_hint(&tmap, buf + o * RB * CY, (int)sub * 8, o * RB, (int)pl, second ? pol_first : pol_last);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
