@@ -221,7 +221,8 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--n", type=int, default=1024, help="particles per dimension")
+    ap.add_argument("--n", "--particles-per-dim", dest="n", type=int, default=1024,
+                    help="particles per dimension (under torchrun use the long spelling: --n is an ambiguous prefix of its own options)")
     ap.add_argument("--mesh", type=int, default=1024, help="mesh cells per dimension")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=192, help="n of the n^3/n^3 CPU-baseline sample (0 = skip)")

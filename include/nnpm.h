@@ -230,8 +230,11 @@ int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, in
  *                  copy engines' 1 MB runs; 0 = separate transposes (default)
  *   "peer_transpose" un-fused transposes: 1 = copy-engine peer copies over NVLink (default), 0 = grouped
  *                  ncclSend/ncclRecv (also the fallback when CUDA IPC mapping of the peers' meshes fails)
- *   "pipeline"     un-fused copy-engine transposes: 1 = overlap them with chunked transforms when the chunks are
- *                  large enough (default), 2 = always, 0 = never
+ *   "pipeline"     un-fused copy-engine transposes: 1 / 2 = overlap them with chunked transforms whenever the slab
+ *                  divides into the chunks (default), 0 = never
+ *   "pipeline_chunks" chunks of that pipeline, 1..4; 0 = automatic (default: 4 at nranks = 2, else 2)
+ *   "ce_streams"   side streams the peer copies of a transpose are spread over, 1..8; 0 = automatic (default: 8 when
+ *                  pipelined over more than 4 ranks, else 4)
  *   "mig_in_push"  nranks > 1: 1 = the push kernels classify the particles they move and pack the leavers for
  *                  migration themselves (default), 0 = separate classification pass over all particles
  *   "zsplit"       1 = run N3 in 128..1024 through the radix-2 wrapper of the persistent fused z pass (the path

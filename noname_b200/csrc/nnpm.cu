@@ -134,8 +134,10 @@ struct nnpm_ctx {
   unsigned* f2_sync;            // work queue, fault flag and per-plane counters of the fused 2-D transform (k_fft2d)
   int opt_fft2d, opt_fft2d_block;
   struct PeerMaps* peer_maps;   // tensor maps over every rank's transposed spectrum (fused forward transpose)
-  cudaStream_t st2[4];    // side streams: the blocks of a transpose go out on several copy engines at once
-  cudaEvent_t ev_fork, ev_join[4];
+  cudaStream_t st2[8];    // side streams: the blocks of a transpose go out on several copy engines at once
+  cudaEvent_t ev_fork, ev_join[8];
+  int opt_ce_streams, opt_pipe_chunks;
+  int pipe_nch, ce_ns;    // chunks / side streams in effect for the current solve
 };
 
 static thread_local std::string g_create_err;
@@ -392,7 +394,9 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   for (int i = 0; i < 64; i++) { c->peer_mesh[i] = nullptr; c->peer_meshT[i] = nullptr; }
   c->peer_ok = false; c->opt_peer = 1; c->bar_buf = nullptr;
   c->ev_fork = nullptr;
-  for (int i = 0; i < 4; i++) { c->st2[i] = nullptr; c->ev_join[i] = nullptr; }
+  for (int i = 0; i < 8; i++) { c->st2[i] = nullptr; c->ev_join[i] = nullptr; }
+  c->opt_ce_streams = 0; c->opt_pipe_chunks = 0;   // 0 = automatic (see do_solve)
+  c->pipe_nch = 4; c->ce_ns = 4;
   c->opt_pipeline = 1;
   for (int i = 0; i < 4; i++) c->ev_chunk[i] = nullptr;
   c->have_tm_y = c->have_tm_z8 = c->have_tm_z4 = c->have1 = false; c->opt_zsplit = 0; c->ytw = nullptr;
@@ -747,8 +751,8 @@ extern "C" int nnpm_sort(nnpm_ctx* ctx) {
     nb = nbins;
   }
   CK(cudaMemsetAsync(bins, 0, (size_t)(nb + 1) * 4, ctx->st));
-  if (ctx->R == 3) k_sort_count<3><<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->pp, np, ctx->g, ctx->tg, fine ? cpt : 0, bins, ctx->skey, ctx->srnk);
-  else k_sort_count<2><<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->pp, np, ctx->g, ctx->tg, fine ? cpt : 0, bins, ctx->skey, ctx->srnk);
+  if (ctx->R == 3) k_sort_count<3><<<nblk(np, 1024), 256, 0, ctx->st>>>(ctx->pp, np, ctx->g, ctx->tg, fine ? cpt : 0, bins, ctx->skey, ctx->srnk);
+  else k_sort_count<2><<<nblk(np, 1024), 256, 0, ctx->st>>>(ctx->pp, np, ctx->g, ctx->tg, fine ? cpt : 0, bins, ctx->skey, ctx->srnk);
   LAUNCHED(ctx);
   CKR(scan_u32(ctx, bins, nb));   // bins[nb] is not needed by k_sort_dest
   k_sort_dest<<<nblk(np, 256), 256, 0, ctx->st>>>(ctx->skey, ctx->srnk, bins, np);
@@ -982,7 +986,7 @@ static int fft_inverse(nnpm_ctx* ctx, bool z_too, cudaEvent_t* comm_t, bool fuse
 // fused z pass is chunked over jl the same way for the backward transpose.
 static int do_solve_pipelined(nnpm_ctx* ctx, cudaEvent_t* ev, double scale) {
   const Geom& g = ctx->g;
-  const int NCH = 4;
+  const int NCH = ctx->pipe_nch;
   const i64 pc = g.nzl / NCH, jc = ctx->njl / NCH;
   if (!ctx->ev_chunk[0])
     for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
@@ -1025,12 +1029,16 @@ static int do_solve(nnpm_ctx* ctx, cudaEvent_t* ev) {
   const bool fuse_fwd = fuse && ycol;
   const bool fuse_bwd = fuse && fusedz && zdst_peers(ctx, &zd);
   if (fuse_fwd) CKR(colfft_peer_maps(ctx));
-  // chunked copy-engine pipeline (un-fused path only): pays while a chunk's copy to one peer stays large (measured at
-  // 1024^3 in round 1: P = 2, 537 MB per copy: solve 17.5 -> 15.5 ms; P = 8, 34 MB per copy: 6.3 -> 7.0 ms)
-  const double chunk_copy_mb = (double)g.nzl * ctx->njl * ctx->icn * 16.0 / 4.0 / 1048576.0;
-  const bool pipe = ctx->opt_pipeline == 2 || (ctx->opt_pipeline == 1 && chunk_copy_mb >= 256.0);
-  if (ctx->P > 1 && !fuse && pipe && ctx->peer_ok && ctx->opt_peer == 1 && fusedz && ycol && rowfft_supported_n(g.N1) &&
-      g.nzl % 4 == 0 && ctx->njl % 4 == 0) {
+  // chunked copy-engine pipeline (un-fused path only).  Measured at 1024^3: P = 2, four chunks: solve 17.5 -> 15.5 ms
+  // (round 1); P = 8: two chunks on eight side streams 11.63 -> 11.25 ms per step, four chunks 11.51, eight streams
+  // without chunking 12.40 (profiles/bench_r02_variants_n8.txt).  Automatic: four chunks at P = 2, two beyond.
+  ctx->ce_ns = ctx->opt_ce_streams > 0 ? ctx->opt_ce_streams : 4;
+  const int nch = ctx->opt_pipe_chunks > 0 ? ctx->opt_pipe_chunks : (ctx->P == 2 ? 4 : 2);
+  const bool pipe = ctx->opt_pipeline >= 1;
+  if (ctx->P > 1 && !fuse && pipe && ctx->peer_ok && ctx->opt_peer == 1 && fusedz && ycol && rowfft_supported_n(g.N1) && ctx->opt_rowfft &&
+      g.nzl % nch == 0 && ctx->njl % nch == 0 && g.nzl / nch >= 1) {
+    ctx->pipe_nch = nch;
+    ctx->ce_ns = ctx->opt_ce_streams > 0 ? ctx->opt_ce_streams : (ctx->P > 4 ? 8 : 4);
     CKR(do_solve_pipelined(ctx, ev, scale));
     CKR(comm_fill_phi_ghosts(ctx));
     ctx->field_state = 2;
@@ -1202,8 +1210,9 @@ static int launch_push(nnpm_ctx* ctx, bool comoving, const PushParams& pp) {
   }
   // one CTA per work item, phi box staged by TMA, x / v by register loads behind a bulk L2 prefetch.  The variants
   // measured slower (round 1: DMA-warp particle streams, persistent double-buffered boxes, deeper register prefetch,
-  // profiles/r01_probe_logs; round 2: a streamed separable gather at 3 / 4 CTAs per SM, 26.3 / 32.6 ms against 25.9:
-  // the kernel is bound by shared-memory wavefronts, not by occupancy, profiles/r02_probe_logs) are no longer compiled.
+  // profiles/r01_probe_logs; round 2: a streamed separable gather at 3 / 4 CTAs per SM, 26.3 / 32.6 ms against 25.9 on
+  // tile-sorted particles and 24.1 against 23.5 - 24.0 on cell-sorted ones: occupancy is not the lever,
+  // profiles/r02_probe_logs) are no longer compiled.
   const size_t smem = (size_t)NNPM_BX * NNPM_BY * (RANK == 3 ? NNPM_BZ : 1) * sizeof(double);
   const i64 covered = ctx->sorted_np < np ? ctx->sorted_np : np;
   const WorkList wl = {ctx->wtile, ctx->wbeg, ctx->wcnt + ctx->ntiles};
@@ -1356,6 +1365,8 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   else if (!strcmp(name, "fft2d")) ctx->opt_fft2d = v;
   else if (!strcmp(name, "fft2d_block")) ctx->opt_fft2d_block = v;
   else if (!strcmp(name, "pipeline")) ctx->opt_pipeline = v;
+  else if (!strcmp(name, "pipeline_chunks")) ctx->opt_pipe_chunks = v < 0 ? 0 : (v > 4 ? 4 : v);
+  else if (!strcmp(name, "ce_streams")) ctx->opt_ce_streams = v < 0 ? 0 : (v > 8 ? 8 : v);
   else if (!strcmp(name, "fuse_transpose")) ctx->opt_fuse_transpose = v;
   else if (!strcmp(name, "mig_in_push")) ctx->opt_mig_in_push = v;
   else if (!strcmp(name, "peer_transpose")) ctx->opt_peer = v;

@@ -156,7 +156,7 @@ extern "C" int nnpm_comm_init(nnpm_ctx* ctx, const uint8_t id[128]) {
   CK(cudaMemsetAsync(ctx->bar_buf, 0, 16, ctx->st));
   CKR(peer_setup(ctx));
   CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < 8; i++) {
     CK(cudaStreamCreateWithFlags(&ctx->st2[i], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
   }
@@ -171,7 +171,7 @@ static void comm_destroy(nnpm_ctx* ctx) {
     if (ctx->peer_meshT[d]) cudaIpcCloseMemHandle(ctx->peer_meshT[d]);
     ctx->peer_mesh[d] = ctx->peer_meshT[d] = nullptr;
   }
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < 8; i++) {
     if (ctx->st2[i]) { cudaStreamSynchronize(ctx->st2[i]); cudaStreamDestroy(ctx->st2[i]); ctx->st2[i] = nullptr; }
     if (ctx->ev_join[i]) { cudaEventDestroy(ctx->ev_join[i]); ctx->ev_join[i] = nullptr; }
   }
@@ -272,7 +272,7 @@ static int comm_transpose_ce(nnpm_ctx* ctx, bool fwd) {
   const size_t chunk = (size_t)ctx->njl * ctx->icn * 16;      // bytes of one (plane, j-block) chunk
   const size_t plane_b = (size_t)g.plane * 8;
   const size_t glo_b = (size_t)g.plane * g.glo * 8;
-  const int ns = ctx->P < 4 ? ctx->P : 4;
+  const int ns = ctx->P < ctx->ce_ns ? ctx->P : ctx->ce_ns;
   CK(cudaEventRecord(ctx->ev_fork, ctx->st));
   for (int i = 0; i < ns; i++) CK(cudaStreamWaitEvent(ctx->st2[i], ctx->ev_fork, 0));
   for (int o = 0; o < ctx->P; o++) {
@@ -305,7 +305,7 @@ static int comm_chunk_ce(nnpm_ctx* ctx, bool fwd, int c, int nch, cudaEvent_t af
   const size_t chunk = (size_t)ctx->njl * ctx->icn * 16;
   const size_t plane_b = (size_t)g.plane * 8;
   const size_t glo_b = (size_t)g.plane * g.glo * 8;
-  const int ns = ctx->P < 4 ? ctx->P : 4;
+  const int ns = ctx->P < ctx->ce_ns ? ctx->P : ctx->ce_ns;
   for (int i = 0; i < ns; i++) CK(cudaStreamWaitEvent(ctx->st2[i], after, 0));
   for (int o = 0; o < ctx->P; o++) {
     const int d = (ctx->r + o) % ctx->P;
@@ -326,7 +326,7 @@ static int comm_chunk_ce(nnpm_ctx* ctx, bool fwd, int c, int nch, cudaEvent_t af
   return NNPM_OK;
 }
 static int comm_join_barrier(nnpm_ctx* ctx) {
-  const int ns = ctx->P < 4 ? ctx->P : 4;
+  const int ns = ctx->P < ctx->ce_ns ? ctx->P : ctx->ce_ns;
   for (int i = 0; i < ns; i++) {
     CK(cudaEventRecord(ctx->ev_join[i], ctx->st2[i]));
     CK(cudaStreamWaitEvent(ctx->st, ctx->ev_join[i], 0));

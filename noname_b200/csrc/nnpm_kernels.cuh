@@ -1227,35 +1227,52 @@ template <int RANK>
 __global__ void __launch_bounds__(256)
 k_sort_count(PartPtrs p, i64 np, Geom g, TileGeom tg, int cpt, uint32_t* __restrict__ hist,
              uint32_t* __restrict__ key, uint32_t* __restrict__ rnk) {
-  const i64 n = blockIdx.x * (i64)blockDim.x + threadIdx.x;
-  uint32_t t = 0xFFFFFFFFu;  // lanes past the end form their own group and do nothing
-  if (n < np) {
-    int i, j, k, dummy;
-    double d;
-    cell_of32(wrap01(p.x[0][n]), g.fN1, (int)g.N1, i, dummy, d);
-    cell_of32(wrap01(p.x[1][n]), g.fN2, (int)g.N2, j, dummy, d);
-    int kl = 0;
-    if (RANK == 3) {
-      cell_of32(wrap01(p.x[2][n]), g.fN3, (int)g.N3, k, dummy, d);
-      kl = k - (int)g.kz0;
-      if (kl < 0) kl = 0;              // strays (not yet migrated) sort into the boundary tiles
-      if (kl >= (int)g.nzl) kl = (int)g.nzl - 1;
+  // four particles per thread, their returning atomics all in flight before the first result is used: the kernel is
+  // bound by the round trip of that atomic (ncu: long_scoreboard), not by its 34 GB of traffic
+  constexpr int U = 4;
+  const i64 base = blockIdx.x * (i64)(256 * U) + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  uint32_t t[U], r[U];
+  unsigned peers[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const i64 n = base + u * 256;
+    t[u] = 0xFFFFFFFFu;  // lanes past the end form their own group and do nothing
+    if (n < np) {
+      int i, j, k, dummy;
+      double d;
+      cell_of32(wrap01(p.x[0][n]), g.fN1, (int)g.N1, i, dummy, d);
+      cell_of32(wrap01(p.x[1][n]), g.fN2, (int)g.N2, j, dummy, d);
+      int kl = 0;
+      if (RANK == 3) {
+        cell_of32(wrap01(p.x[2][n]), g.fN3, (int)g.N3, k, dummy, d);
+        kl = k - (int)g.kz0;
+        if (kl < 0) kl = 0;              // strays (not yet migrated) sort into the boundary tiles
+        if (kl >= (int)g.nzl) kl = (int)g.nzl - 1;
+      }
+      const int ti = i / tg.tx, tj = j / tg.ty, tk = kl / tg.tz;
+      t[u] = (uint32_t)(ti + tg.ntx * (tj + tg.nty * tk));
+      if (cpt) t[u] = t[u] * (uint32_t)cpt + (uint32_t)((i - ti * tg.tx) + tg.tx * ((j - tj * tg.ty) + tg.ty * (kl - tk * tg.tz)));
     }
-    const int ti = i / tg.tx, tj = j / tg.ty, tk = kl / tg.tz;
-    t = (uint32_t)(ti + tg.ntx * (tj + tg.nty * tk));
-    if (cpt) t = t * (uint32_t)cpt + (uint32_t)((i - ti * tg.tx) + tg.tx * ((j - tj * tg.ty) + tg.ty * (kl - tk * tg.tz)));
   }
   // warp-aggregated histogram: particles arrive nearly sorted (lattice ICs, previous sorts, collapsed halos), so a
   // warp often holds few distinct bins -- one atomic per distinct bin instead of one per lane.
-  const unsigned peers = __match_any_sync(0xffffffffu, t);
-  const int lane = threadIdx.x & 31;
-  const int leader = __ffs(peers) - 1;
-  uint32_t base = 0;
-  if (lane == leader && n < np) base = atomicAdd(&hist[t], (uint32_t)__popc(peers));
-  base = __shfl_sync(peers, base, leader);
-  if (n < np) {
-    key[n] = t;
-    rnk[n] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    peers[u] = __match_any_sync(0xffffffffu, t[u]);
+    const int leader = __ffs(peers[u]) - 1;
+    r[u] = 0;
+    if (lane == leader && t[u] != 0xFFFFFFFFu) r[u] = atomicAdd(&hist[t[u]], (uint32_t)__popc(peers[u]));
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const i64 n = base + u * 256;
+    const int leader = __ffs(peers[u]) - 1;
+    const uint32_t b = __shfl_sync(peers[u], r[u], leader);
+    if (n < np) {
+      key[n] = t[u];
+      rnk[n] = b + (uint32_t)__popc(peers[u] & ((1u << lane) - 1u));
+    }
   }
 }
 // tile offsets out of the (scanned) bin offsets of a cell-order sort: toff[t] = boff[t * cpt], toff[ntiles] = np

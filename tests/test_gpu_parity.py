@@ -505,6 +505,31 @@ def test_sort_keeps_particles_and_restores_order(lib_built):
         assert np.array_equal(xo, x) and np.array_equal(vo, v)
 
 
+@pytest.mark.parametrize("cells", [1, 0])
+def test_sort_orders_by_cell_and_survives_a_nonzero_first_id(lib_built, cells):
+    """cell-order sort: inside every tile the particles come out ordered by (k, j, i) cell, tiles in tile order; a single-GPU
+    upload whose ids start at first_id != 0 is still restored to its original order (out-of-bounds permute)"""
+    from noname_b200 import DevicePM
+    dims = (64, 32, 32)
+    x, v = make_particles(23, 30000, 3, clustered=True)
+    with DevicePM(dims, 30000, rank=3) as dev:
+        dev.set_option("sort_cells", cells)
+        dev.upload(x, v, 1.0, first_id=5000)
+        dev.sort()
+        xs, vs, ids = dev.download(ids=True)
+        assert sorted(ids.tolist()) == list(range(5000, 35000))
+        assert np.array_equal(xs, x[ids - 5000]) and np.array_equal(vs, v[ids - 5000])
+        xw = np.where(xs > 1.0, xs - 1.0, np.where(xs < 0.0, xs + 1.0, xs))
+        cell = [np.minimum(np.floor(xw[:, d] * dims[d]).astype(np.int64) % dims[d], dims[d] - 1) for d in range(3)]
+        tile = (cell[0] // 32) + 2 * ((cell[1] // 8) + 4 * (cell[2] // 8))
+        assert np.all(np.diff(tile) >= 0)                               # tile-sorted either way
+        if cells:
+            key = tile * 2048 + (cell[0] % 32) + 32 * ((cell[1] % 8) + 8 * (cell[2] % 8))
+            assert np.all(np.diff(key) >= 0)                            # and cell-ordered inside the tiles
+        xo, vo = dev.download()
+        assert np.array_equal(xo, x) and np.array_equal(vo, v)
+
+
 @pytest.mark.parametrize("dims,rank", [((16, 16, 1), 2), ((16, 16, 16), 3), ((8, 12, 20), 3)])
 def test_power_spectrum(lib_built, O, dims, rank):
     from noname_b200 import DevicePM
