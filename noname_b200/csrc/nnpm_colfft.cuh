@@ -433,7 +433,8 @@ k_zfused_s(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ZDs
       }
     }
     // the next iteration's first barrier (after its landing-zone reads) separates these exchange reads from the
-    // next exchange writes
+    // next exchange writes.  (Tried: handing the result to the TMA engine through the exchange buffer, two half-group
+    // tensor stores -- 5.25-5.55 ms against 5.0-5.3 for these register stores, profiles/r02_probe_logs/r2n_probe.log.)
   }
 }
 

@@ -12,6 +12,7 @@
 #include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 typedef long long i64;
 typedef unsigned long long u64;
@@ -1071,13 +1072,19 @@ __device__ __forceinline__ void bulk_reduce_add(void* gdst, const void* ssrc, un
 // UNR: particles whose loads are issued together before any of them is scattered (1 or 2): the loop has no
 // software prefetch, so UNR = 2 doubles the bytes each thread keeps in flight (at ~12 more registers).
 template <int RANK, bool FIXED, bool PRE, int UNR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, WorkList wl, const uint32_t* __restrict__ tile_off,
                double* __restrict__ mesh, double m, double fscale, uint32_t* __restrict__ slow_list,
                u64* __restrict__ slow_count, int bulk, int pf) {
   constexpr int DX = NNPM_DX, DY = NNPM_DY, DZ = (RANK == 3) ? NNPM_DZ : 1, DXY = DX * DY, NBOX = DXY * DZ;
-  // accumulators: little-endian (lo, hi) uint32 pairs == one u64 per cell; converted in place to f64
-  __shared__ __align__(16) uint32_t acc[2 * NBOX];
+  // accumulators: the low and the high 32-bit words of the cells' 64-bit sums in TWO arrays (lo[NBOX], then hi[NBOX]), so that
+  // the lanes of a warp -- on consecutive cells once the particles are cell-sorted -- hit consecutive 4-byte banks: as
+  // interleaved (lo, hi) pairs every atomic touched only the even (or only the odd) banks, a built-in 2-way conflict on
+  // top of the same-cell pairs (ncu r2e: 4.1 wavefronts per shared atomic).  Converted to one f64 / u64 per cell before the flush.
+  constexpr int NBOXP = (NBOX + 3) & ~3;
+  __shared__ __align__(16) uint32_t acc[2 * NBOXP];
+  uint32_t* const acc_lo = acc;
+  uint32_t* const acc_hi = acc + NBOXP;
   if (blockIdx.x >= *wl.count) return;  // the grid is sized for the worst case
   const int t = (int)wl.tile[blockIdx.x];
   const i64 n0 = wl.beg[blockIdx.x];
@@ -1087,8 +1094,7 @@ k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, WorkList wl, 
   if (n0 >= n1) return;  // uniform across the block
   if (pf) l2_prefetch_particles<RANK, PRE>(p, n0, n1);  // lands while the box is being zeroed
   const int ttx = t % tg.ntx, tty = (t / tg.ntx) % tg.nty, ttz = t / (tg.ntx * tg.nty);
-  for (int c = threadIdx.x; c < NBOX / 2; c += 256) ((uint4*)acc)[c] = make_uint4(0u, 0u, 0u, 0u);
-  if (threadIdx.x == 0 && (NBOX & 1)) { acc[2 * NBOX - 2] = 0u; acc[2 * NBOX - 1] = 0u; }
+  for (int c = threadIdx.x; c < NBOXP / 2; c += 256) ((uint4*)acc)[c] = make_uint4(0u, 0u, 0u, 0u);
   const int N1 = (int)g.N1, N2 = (int)g.N2, N3 = (int)g.N3;
   const int bi0 = ttx * tg.tx - NNPM_TH - 1, bj0 = tty * tg.ty - NNPM_TH;  // mesh cell of box cell (0,0,0)
   const int bk0 = (int)g.kz0 + ttz * tg.tz - NNPM_TH;                       // global plane
@@ -1102,13 +1108,21 @@ k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, WorkList wl, 
   const int cnt = (int)(n1 - n0);
   __syncthreads();
   // 64-bit fixed-point add from two native 32-bit shared atomics (the low word returns the old value)
-  auto sadd = [&](int idx, double w) {
-    const u64 q = (u64)__double2ll_rn(w);
+  auto sadd = [&](int idx, u64 q) {
     const uint32_t lo = (uint32_t)q;
-    const uint32_t old = atomicAdd(&acc[2 * idx], lo);
-    atomicAdd(&acc[2 * idx + 1], (uint32_t)(q >> 32) + (old > ~lo ? 1u : 0u));
+    const uint32_t old = atomicAdd(&acc_lo[idx], lo);
+    atomicAdd(&acc_hi[idx], (uint32_t)(q >> 32) + (old > ~lo ? 1u : 0u));
   };
-  auto scatter = [&](int q, double x0, double x1, double x2) {
+  const int lane = threadIdx.x & 31;
+  // One particle per lane (valid = false: the lane has none).  Weights -> 2^B fixed point -> two atomics per CIC corner.
+  // AGG (work items of tiles holding >= 4096 particles: collapsed halos of the clustered late-time state, BASELINE config 4):
+  // warp-aggregated atomics.  Cell-sorted particles of one cell sit in adjacent lanes; when the warp holds a run of >= 8
+  // of them, the runs of equal cells are summed by a segmented shuffle reduction (integer sums: exact, order-independent,
+  // so the fixed-point mode stays bit-exact) and only the head lane of every run touches shared memory.  Without it a warp of
+  // 32 same-cell particles serialises every one of its 16 atomics 32-fold: the cell-order sort alone made the clustered
+  // deposit 29.9 ms against 15.9.  The run detection costs ~30 % more instructions, so sparse tiles take the plain path.
+  auto scatter = [&](auto AGG, bool valid, int q, double x0, double x1, double x2) {
+    constexpr bool agg_path = decltype(AGG)::value;
     int i, j, k = 0;
     double dx, dy, dz = 0.0;
     cell_fast(wrap01_sel(x0), g.fN1, i, dx);
@@ -1121,53 +1135,85 @@ k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, WorkList wl, 
       rk = (unsigned)tile_rel(k, bk0, N3);
       fast = fast && rk < fz;
     }
-    if (!fast) {  // strayed beyond the box since the sort: the global-atomic kernel takes it
-      slow_list[atomicAdd(slow_count, 1ull)] = (uint32_t)(n0 + q);
-      return;
-    }
+    if (valid && !fast) slow_list[atomicAdd(slow_count, 1ull)] = (uint32_t)(n0 + q);  // strayed beyond the box: the global-atomic kernel takes it
+    const bool on = valid && fast;
+    if (!agg_path && !on) return;
     // unit-mass weights in the reference's order (1-dx)*(1-dy)*(1-dz) ... (ParticleMesh.jl:376-379,
     // :395-402), pre-scaled by 2^B (exact: a power of two commutes with every rounding)
     const double wx0 = __dmul_rn(__dsub_rn(1.0, dx), fscale), wx1 = __dmul_rn(dx, fscale);
     const double ody = __dsub_rn(1.0, dy);
     const double w00 = __dmul_rn(wx0, ody), w01 = __dmul_rn(wx0, dy), w10 = __dmul_rn(wx1, ody), w11 = __dmul_rn(wx1, dy);
     const int b = (int)(rk * DXY + rj * DX + ri);
-    if (RANK == 2) {
-      sadd(b, w00); sadd(b + DX, w01); sadd(b + 1, w10); sadd(b + DX + 1, w11);
-    } else {
-      const double odz = __dsub_rn(1.0, dz);
-      sadd(b, __dmul_rn(w00, odz)); sadd(b + DX, __dmul_rn(w01, odz));
-      sadd(b + 1, __dmul_rn(w10, odz)); sadd(b + DX + 1, __dmul_rn(w11, odz));
-      sadd(b + DXY, __dmul_rn(w00, dz)); sadd(b + DXY + DX, __dmul_rn(w01, dz));
-      sadd(b + DXY + 1, __dmul_rn(w10, dz)); sadd(b + DXY + DX + 1, __dmul_rn(w11, dz));
+    bool agg = false, writer = on;
+    int runend = 31;
+    if (agg_path) {
+      // runs of equal cells in lane order
+      const int key = on ? b : (int)(0x40000000 | lane);
+      const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+      const unsigned follow = __ballot_sync(0xffffffffu, lane > 0 && key == prev);   // bit l: lane l continues lane l-1's run
+      const unsigned t1 = follow & (follow >> 1), t2 = t1 & (t1 >> 2);
+      agg = (t2 & (t1 >> 4) & (follow >> 6)) != 0u;   // some run has >= 8 lanes (7 consecutive followers): warp-uniform
+      if (agg) {
+        const unsigned heads_above = ~follow & ~((2u << lane) - 1u);             // run heads in lanes > lane
+        runend = heads_above ? __ffs(heads_above) - 2 : 31;                      // last lane of my run
+        writer = on && !((follow >> lane) & 1u);                                 // the head of every run adds the run's sums
+      }
     }
-  };
-  for (int q = threadIdx.x; q < cnt; q += 256 * UNR) {
-    double x0[UNR], x1[UNR], x2[UNR], v0[UNR], v1[UNR], v2[UNR];
+    // one CIC corner for the whole warp: weight -> fixed point, (segmented sum over the run,) two atomics
+    auto corner = [&](int idx, double w) {
+      u64 qq = (u64)__double2ll_rn(w);
+      if (agg_path && agg) {
 #pragma unroll
-    for (int u = 0; u < UNR; u++) {
-      const int qu = q + 256 * u;
-      x0[u] = x1[u] = x2[u] = v0[u] = v1[u] = v2[u] = 0.0;
-      if (u == 0 || qu < cnt) {
-        x0[u] = px0[qu]; x1[u] = px1[qu];
-        if (RANK == 3) x2[u] = px2[qu];
-        if (PRE) {
-          v0[u] = pv0[qu]; v1[u] = pv1[qu];
-          if (RANK == 3) v2[u] = pv2[qu];
+        for (int d = 1; d < 32; d <<= 1) {
+          const u64 o = __shfl_down_sync(0xffffffffu, qq, d);
+          if (lane + d <= runend) qq += o;
         }
       }
+      if (writer) sadd(idx, qq);
+    };
+    if (RANK == 2) {
+      corner(b, w00); corner(b + DX, w01); corner(b + 1, w10); corner(b + DX + 1, w11);
+    } else {
+      const double odz = __dsub_rn(1.0, dz);
+      corner(b, __dmul_rn(w00, odz)); corner(b + DX, __dmul_rn(w01, odz));
+      corner(b + 1, __dmul_rn(w10, odz)); corner(b + DX + 1, __dmul_rn(w11, odz));
+      corner(b + DXY, __dmul_rn(w00, dz)); corner(b + DXY + DX, __dmul_rn(w01, dz));
+      corner(b + DXY + 1, __dmul_rn(w10, dz)); corner(b + DXY + DX + 1, __dmul_rn(w11, dz));
     }
+  };
+  // warp-uniform trip count: every lane of a warp runs the same iterations (the aggregated path's shuffles need all 32 lanes)
+  auto run = [&](auto AGG) {
+    for (int q0 = (int)(threadIdx.x & ~31u); q0 < cnt; q0 += 256 * UNR) {
+      const int q = q0 + lane;
+      double x0[UNR], x1[UNR], x2[UNR], v0[UNR], v1[UNR], v2[UNR];
 #pragma unroll
-    for (int u = 0; u < UNR; u++) {
-      const int qu = q + 256 * u;
-      if (u > 0 && qu >= cnt) break;
-      if (PRE) {
-        x0[u] = __dadd_rn(x0[u], __dmul_rn(c0, v0[u]));
-        x1[u] = __dadd_rn(x1[u], __dmul_rn(c0, v1[u]));
-        if (RANK == 3) x2[u] = __dadd_rn(x2[u], __dmul_rn(c0, v2[u]));
+      for (int u = 0; u < UNR; u++) {
+        const int qu = q + 256 * u;
+        x0[u] = x1[u] = x2[u] = v0[u] = v1[u] = v2[u] = 0.0;
+        if (qu < cnt) {
+          x0[u] = px0[qu]; x1[u] = px1[qu];
+          if (RANK == 3) x2[u] = px2[qu];
+          if (PRE) {
+            v0[u] = pv0[qu]; v1[u] = pv1[qu];
+            if (RANK == 3) v2[u] = pv2[qu];
+          }
+        }
       }
-      scatter(qu, x0[u], x1[u], x2[u]);
+#pragma unroll
+      for (int u = 0; u < UNR; u++) {
+        const int qu = q + 256 * u;
+        if (q0 + 256 * u >= cnt) break;   // warp-uniform
+        if (PRE) {
+          x0[u] = __dadd_rn(x0[u], __dmul_rn(c0, v0[u]));
+          x1[u] = __dadd_rn(x1[u], __dmul_rn(c0, v1[u]));
+          if (RANK == 3) x2[u] = __dadd_rn(x2[u], __dmul_rn(c0, v2[u]));
+        }
+        scatter(AGG, qu < cnt, qu, x0[u], x1[u], x2[u]);
+      }
     }
-  }
+  };
+  if (tile_off[t + 1] - tile_off[t] >= 4096u) run(std::true_type{});   // block-uniform
+  else run(std::false_type{});
   __syncthreads();
   // flush: box cell (bx,by,bz) -> mesh cell (bi0 + bx, bj0 + by, bk0 + bz), periodic.  Box extents are
   // <= N + 3, so one fold brings every coordinate into [0, N).
@@ -1175,9 +1221,22 @@ k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, WorkList wl, 
   const double inv_scale = 1.0 / fscale;  // exact: fscale = 2^B
   u64* acc64 = (u64*)acc;
   if (bulk) {
-    if (!FIXED) {  // integers -> m * q * 2^-B, in place
-      for (int c = threadIdx.x; c < NBOX; c += 256)
-        ((double*)acc)[c] = __dmul_rn(m, __dmul_rn((double)(i64)acc64[c], inv_scale));
+    // (lo[c], hi[c]) -> one 8-byte value per cell, in place through registers: u64 sums (FIXED) or m * q * 2^-B
+    constexpr int PER = (NBOX + 255) / 256;
+    u64 qv[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      const int c = threadIdx.x + 256 * k;
+      qv[k] = c < NBOX ? ((u64)acc_hi[c] << 32) | (u64)acc_lo[c] : 0ull;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      const int c = threadIdx.x + 256 * k;
+      if (c < NBOX) {
+        if (FIXED) acc64[c] = qv[k];
+        else ((double*)acc)[c] = __dmul_rn(m, __dmul_rn((double)(i64)qv[k], inv_scale));
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async-proxy reads
     __syncthreads();
@@ -1201,7 +1260,7 @@ k_deposit_tile(PartPtrs p, i64 np, double c0, Geom g, TileGeom tg, WorkList wl, 
   }
   const int ex = tg.tx + 2 * NNPM_TH + 2;
   for (int c = threadIdx.x; c < NBOX; c += 256) {
-    const u64 q = acc64[c];
+    const u64 q = ((u64)acc_hi[c] << 32) | (u64)acc_lo[c];
     if (!q) continue;
     const int bx = c % DX, by = (c / DX) % DY, bz = c / DXY;  // compile-time divisors
     if (bx >= ex || by >= ey || bz >= ez) continue;
