@@ -167,7 +167,7 @@ def run_cpu(n, mesh, steps, warmup, threads):
     return n ** 3 / sec, sec
 
 
-def parity_small_step(rank, world, local_rank, dist):
+def parity_small_step(rank, world, local_rank, dist, opts=()):
     """CHECKER (oracle/ used as the checker only, outside every timed region): one comoving step of a 64^3 / 64^3
     problem on the same rank layout as the bench -- upload each rank's share, redistribute, step -- against the CPU
     oracle.  Returns normalised L-inf errors of phi and v and the max |dx| over all ranks."""
@@ -184,6 +184,9 @@ def parity_small_step(rank, world, local_rank, dist):
     sc = (1.001, 1.002, 0.81, 1.003)
     O.step_comoving(f, xr, vr, m, 0.01, *sc)
     dev = DevicePM(dims, npart, rank=3, device=local_rank, nranks=world, rank_id=rank, sort_every=1, part_capacity=npart)
+    for kv in opts:   # the same nnpm_set_option overrides as the timed run
+        k, _, v_ = kv.partition("=")
+        dev.set_option(k, float(v_))
     try:
         if world > 1:
             uid = [DevicePM.comm_unique_id() if rank == 0 else None]
@@ -309,7 +312,7 @@ def main():
     parity = None
     if not args.no_parity:
         try:
-            parity = {"small_step": parity_small_step(rank, world, local_rank, dist)}
+            parity = {"small_step": parity_small_step(rank, world, local_rank, dist, args.opt)}
         except Exception as ex:  # report, do not hide
             parity = {"small_step": {"ok": False, "error": repr(ex)}}
 

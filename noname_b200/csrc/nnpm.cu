@@ -119,7 +119,7 @@ struct nnpm_ctx {
   double* peer_mesh[64];
   double* peer_meshT[64];
   bool peer_ok;
-  int opt_peer;   // un-fused transposes: 0 = NCCL send/recv, 1 = copy-engine peer copies (default)
+  int opt_peer;   // un-fused transposes: 0 = NCCL send/recv, 1 = copy-engine peer copies, 2 = SM bulk-copy kernel, 3 = copy engines + SM kernel for the last chunk (default from 4 ranks)
   int* bar_buf;
   // TMA-staged column FFT engine (nnpm_colfft.cuh)
   CUtensorMap tm_y, tm_z8, tm_z4;
@@ -134,6 +134,9 @@ struct nnpm_ctx {
   unsigned* f2_sync;            // work queue, fault flag and per-plane counters of the fused 2-D transform (k_fft2d)
   int opt_fft2d, opt_fft2d_block;
   struct PeerMaps* peer_maps;   // tensor maps over every rank's transposed spectrum (fused forward transpose)
+  cudaStream_t st_hi;     // highest-priority side stream of the SM transport ("peer_transpose" = 2)
+  cudaEvent_t ev_hi;
+  int opt_xfer_ctas;      // its grid (0 = one CTA per SM)
   cudaStream_t st2[8];    // side streams: the blocks of a transpose go out on several copy engines at once
   cudaEvent_t ev_fork, ev_join[8];
   int opt_ce_streams, opt_pipe_chunks;
@@ -192,6 +195,7 @@ static int dalloc(nnpm_ctx* ctx, T** p, size_t count) {
 #include "nnpm_zfft.cuh"
 #include "nnpm_colfft.cuh"
 #include "nnpm_rowfft.cuh"
+#include "nnpm_xfer.cuh"
 
 // ------------------------------------------------------------------------------------------
 // lifetime
@@ -392,9 +396,10 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->pk_buf = nullptr; c->ic_partial = nullptr;
   c->ztw = nullptr;
   for (int i = 0; i < 64; i++) { c->peer_mesh[i] = nullptr; c->peer_meshT[i] = nullptr; }
-  c->peer_ok = false; c->opt_peer = 1; c->bar_buf = nullptr;
+  c->peer_ok = false; c->opt_peer = c->P >= 4 ? 3 : 1; c->bar_buf = nullptr;
   c->ev_fork = nullptr;
   for (int i = 0; i < 8; i++) { c->st2[i] = nullptr; c->ev_join[i] = nullptr; }
+  c->st_hi = nullptr; c->ev_hi = nullptr; c->opt_xfer_ctas = 0;
   c->opt_ce_streams = 0; c->opt_pipe_chunks = 0;   // 0 = automatic (see do_solve)
   c->pipe_nch = 4; c->ce_ns = 4;
   c->opt_pipeline = 1;
@@ -1035,7 +1040,7 @@ static int do_solve(nnpm_ctx* ctx, cudaEvent_t* ev) {
   ctx->ce_ns = ctx->opt_ce_streams > 0 ? ctx->opt_ce_streams : 4;
   const int nch = ctx->opt_pipe_chunks > 0 ? ctx->opt_pipe_chunks : (ctx->P == 2 ? 4 : 2);
   const bool pipe = ctx->opt_pipeline >= 1;
-  if (ctx->P > 1 && !fuse && pipe && ctx->peer_ok && ctx->opt_peer == 1 && fusedz && ycol && rowfft_supported_n(g.N1) && ctx->opt_rowfft &&
+  if (ctx->P > 1 && !fuse && pipe && ctx->peer_ok && ctx->opt_peer >= 1 && fusedz && ycol && rowfft_supported_n(g.N1) && ctx->opt_rowfft &&
       g.nzl % nch == 0 && ctx->njl % nch == 0 && g.nzl / nch >= 1) {
     ctx->pipe_nch = nch;
     ctx->ce_ns = ctx->opt_ce_streams > 0 ? ctx->opt_ce_streams : (ctx->P > 4 ? 8 : 4);
@@ -1369,7 +1374,8 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   else if (!strcmp(name, "ce_streams")) ctx->opt_ce_streams = v < 0 ? 0 : (v > 8 ? 8 : v);
   else if (!strcmp(name, "fuse_transpose")) ctx->opt_fuse_transpose = v;
   else if (!strcmp(name, "mig_in_push")) ctx->opt_mig_in_push = v;
-  else if (!strcmp(name, "peer_transpose")) ctx->opt_peer = v;
+  else if (!strcmp(name, "peer_transpose")) ctx->opt_peer = v < 0 ? (ctx->P >= 4 ? 3 : 1) : v;
+  else if (!strcmp(name, "xfer_ctas")) ctx->opt_xfer_ctas = v;
   else if (!strcmp(name, "zsplit")) ctx->opt_zsplit = v;
   else if (!strcmp(name, "l2pf_push")) ctx->opt_l2pf_push = v;
   else if (!strcmp(name, "l2pf_deposit")) ctx->opt_l2pf_deposit = v;

@@ -160,6 +160,12 @@ extern "C" int nnpm_comm_init(nnpm_ctx* ctx, const uint8_t id[128]) {
     CK(cudaStreamCreateWithFlags(&ctx->st2[i], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
   }
+  {  // the SM transport of the transposes ("peer_transpose" = 2) runs beside the transforms: its CTAs go first
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&ctx->st_hi, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&ctx->ev_hi, cudaEventDisableTiming));
+  }
   return NNPM_OK;
 }
 
@@ -177,6 +183,8 @@ static void comm_destroy(nnpm_ctx* ctx) {
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   ctx->ev_fork = nullptr;
+  if (ctx->st_hi) { cudaStreamSynchronize(ctx->st_hi); cudaStreamDestroy(ctx->st_hi); ctx->st_hi = nullptr; }
+  if (ctx->ev_hi) { cudaEventDestroy(ctx->ev_hi); ctx->ev_hi = nullptr; }
   if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(COMM);
   ctx->comm = nullptr;
 }
@@ -267,8 +275,13 @@ static int comm_barrier(nnpm_ctx* ctx) {
 //   backward  src T[d*nzl+kl][:][:]   (contiguous)                   ->  A_d[kl][j0 ..][:]  (plane stride)
 // so the whole all-to-all is P-1 peer cudaMemcpy2DAsync calls on the NVLink copy engines (no SM
 // time), spread over up to four side streams so several copy engines run at once.
+static int comm_xfer_sm(nnpm_ctx* ctx, bool fwd, int c, int nch, cudaStream_t s);   // nnpm_xfer.cuh
 static int comm_transpose_ce(nnpm_ctx* ctx, bool fwd) {
   const Geom& g = ctx->g;
+  if (ctx->opt_peer >= 2) {   // SM transport: one kernel on the compute stream moves every block
+    CKR(comm_xfer_sm(ctx, fwd, 0, 1, ctx->st));
+    return comm_barrier(ctx);
+  }
   const size_t chunk = (size_t)ctx->njl * ctx->icn * 16;      // bytes of one (plane, j-block) chunk
   const size_t plane_b = (size_t)g.plane * 8;
   const size_t glo_b = (size_t)g.plane * g.glo * 8;
@@ -302,6 +315,11 @@ static int comm_transpose_ce(nnpm_ctx* ctx, bool fwd) {
 // so they run on the copy engines while the next chunk is being transformed.
 static int comm_chunk_ce(nnpm_ctx* ctx, bool fwd, int c, int nch, cudaEvent_t after) {
   const Geom& g = ctx->g;
+  // 2: every chunk by the SM transport; 3: only the last one, which no transform is left to run beside
+  if (ctx->opt_peer == 2 || (ctx->opt_peer == 3 && c == nch - 1)) {
+    CK(cudaStreamWaitEvent(ctx->st_hi, after, 0));
+    return comm_xfer_sm(ctx, fwd, c, nch, ctx->st_hi);
+  }
   const size_t chunk = (size_t)ctx->njl * ctx->icn * 16;
   const size_t plane_b = (size_t)g.plane * 8;
   const size_t glo_b = (size_t)g.plane * g.glo * 8;
@@ -326,6 +344,11 @@ static int comm_chunk_ce(nnpm_ctx* ctx, bool fwd, int c, int nch, cudaEvent_t af
   return NNPM_OK;
 }
 static int comm_join_barrier(nnpm_ctx* ctx) {
+  if (ctx->opt_peer >= 2) {
+    CK(cudaEventRecord(ctx->ev_hi, ctx->st_hi));
+    CK(cudaStreamWaitEvent(ctx->st, ctx->ev_hi, 0));
+    if (ctx->opt_peer == 2) return comm_barrier(ctx);
+  }
   const int ns = ctx->P < ctx->ce_ns ? ctx->P : ctx->ce_ns;
   for (int i = 0; i < ns; i++) {
     CK(cudaEventRecord(ctx->ev_join[i], ctx->st2[i]));

@@ -106,8 +106,9 @@ def main():
             print(f"[mgpu P={P} {mode} sort_every={sort_every}] untiled={st.n_untiled} migrated(last step, all ranks)={int(cnt[1].item())} ms={st.as_dict()['ms']}")
         dev.close()
 
-    # the four transpose paths -- fused into the FFT kernels' stores (default), copy engines pipelined with chunked
-    # transforms, copy engines un-pipelined, grouped NCCL send/recv -- equal the oracle and each other bit for bit
+    # the transpose paths -- fused into the FFT kernels' stores, copy engines pipelined with chunked transforms
+    # (default), copy engines un-pipelined, the SM bulk-copy transport (alone and pipelined), grouped NCCL send/recv
+    # -- equal the oracle and each other bit for bit
     # (N1 = 128 so that the own row-FFT x passes run too)
     N2 = 64
     rng = np.random.default_rng(5)
@@ -116,7 +117,10 @@ def main():
     O.compute_potential(ref, rho - rho.mean(), np.zeros((N2, N2, N2 + 1), dtype=np.complex128))
     nz2 = N2 // P
     got = {}
-    for name, opts in (("fused", {}), ("pipelined", {"fuse_transpose": 0, "pipeline": 2}), ("unpipelined", {"fuse_transpose": 0, "pipeline": 0}),
+    for name, opts in (("fused", {"fuse_transpose": 1}), ("default", {}), ("pipelined", {"fuse_transpose": 0, "pipeline": 2}),
+                       ("unpipelined", {"fuse_transpose": 0, "pipeline": 0}), ("sm", {"peer_transpose": 2, "pipeline": 0}),
+                       ("sm_pipelined", {"peer_transpose": 2, "pipeline": 2}), ("sm_few_ctas", {"peer_transpose": 2, "xfer_ctas": 3}),
+                       ("sm_last_chunk", {"peer_transpose": 3, "pipeline": 2}),
                        ("nccl", {"fuse_transpose": 0, "peer_transpose": 0})):
         dev = DevicePM((2 * N2, N2, N2), 8, rank=3, device=lr, nranks=P, rank_id=rank)
         uid = [DevicePM.comm_unique_id() if rank == 0 else None]
@@ -130,7 +134,7 @@ def main():
             got[name] = dev.get_field("phi")
         check(f"solve {name}", nlinf(got[name], ref[rank * nz2:(rank + 1) * nz2]) < 1e-12 * np.max(np.abs(ref)) / np.max(np.abs(ref[rank * nz2:(rank + 1) * nz2])))
         dev.close()
-    for name in ("pipelined", "unpipelined", "nccl"):
+    for name in ("default", "pipelined", "unpipelined", "sm", "sm_pipelined", "sm_few_ctas", "sm_last_chunk", "nccl"):
         check(f"solve fused == {name}", np.array_equal(got["fused"], got[name]))
 
     # fine mesh along z (N3 = 2048, BASELINE config 5): slab transposes + the radix-2-wrapped fused z pass
