@@ -228,12 +228,13 @@ int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, in
  *                  memory, no separate all-to-all pass).  Bit-identical to the other paths, but measured SLOWER:
  *                  the 64 / 128-byte pieces such stores put on NVLink reach ~380 GB/s against ~600 GB/s for the
  *                  copy engines' 1 MB runs; 0 = separate transposes (default)
- *   "peer_transpose" un-fused transposes: 1 = copy-engine peer copies over NVLink (default below 4 ranks), 2 = one SM kernel whose
- *                  single-thread CTAs relay 8 KB pieces HBM -> shared memory -> peer mesh with bulk asynchronous
- *                  copies (nnpm_xfer.cuh), 3 = copy engines for the chunks of the pipeline that travel beside a
- *                  transform and the SM kernel for the last chunk of each transpose (default from 4 ranks: at 8 x
- *                  B200 the copy engines reach ~510 GB/s per GPU on the all-to-all, the SM kernel ~630), 0 = grouped ncclSend/ncclRecv (also the fallback when CUDA IPC mapping of
- *                  the peers' meshes fails)
+ *   "peer_transpose" un-fused transposes over the CUDA-IPC peer mappings: 1 = copy-engine peer copies; 2 = one SM
+ *                  kernel whose single-thread CTAs relay 8 KB pieces HBM -> shared memory -> peer mesh with bulk
+ *                  asynchronous copies (nnpm_xfer.cuh); 3 = copy engines for the chunks of the pipeline that travel
+ *                  beside a transform and the SM kernel for the last chunk of each transpose, which nothing is left
+ *                  to run beside (default: on the all-to-all of 8 x B200 the copy engines reach ~510 GB/s per GPU,
+ *                  the SM kernel ~630; profiles/bench_r02_transport_variants.txt); 0 = grouped ncclSend/ncclRecv
+ *                  (also the fallback when CUDA IPC mapping of the peers' meshes fails)
  *   "xfer_ctas"    grid of that SM kernel; 0 = one CTA per SM (default)
  *   "pipeline"     un-fused copy-engine transposes: 1 / 2 = overlap them with chunked transforms whenever the slab
  *                  divides into the chunks (default), 0 = never

@@ -119,7 +119,7 @@ struct nnpm_ctx {
   double* peer_mesh[64];
   double* peer_meshT[64];
   bool peer_ok;
-  int opt_peer;   // un-fused transposes: 0 = NCCL send/recv, 1 = copy-engine peer copies, 2 = SM bulk-copy kernel, 3 = copy engines + SM kernel for the last chunk (default from 4 ranks)
+  int opt_peer;   // un-fused transposes: 0 = NCCL send/recv, 1 = copy-engine peer copies, 2 = SM bulk-copy kernel, 3 = copy engines + SM kernel for the last chunk (default)
   int* bar_buf;
   // TMA-staged column FFT engine (nnpm_colfft.cuh)
   CUtensorMap tm_y, tm_z8, tm_z4;
@@ -396,7 +396,7 @@ extern "C" int nnpm_create(nnpm_ctx** out, const nnpm_config* cfg) {
   c->pk_buf = nullptr; c->ic_partial = nullptr;
   c->ztw = nullptr;
   for (int i = 0; i < 64; i++) { c->peer_mesh[i] = nullptr; c->peer_meshT[i] = nullptr; }
-  c->peer_ok = false; c->opt_peer = c->P >= 4 ? 3 : 1; c->bar_buf = nullptr;
+  c->peer_ok = false; c->opt_peer = 3; c->bar_buf = nullptr;
   c->ev_fork = nullptr;
   for (int i = 0; i < 8; i++) { c->st2[i] = nullptr; c->ev_join[i] = nullptr; }
   c->st_hi = nullptr; c->ev_hi = nullptr; c->opt_xfer_ctas = 0;
@@ -1374,7 +1374,7 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   else if (!strcmp(name, "ce_streams")) ctx->opt_ce_streams = v < 0 ? 0 : (v > 8 ? 8 : v);
   else if (!strcmp(name, "fuse_transpose")) ctx->opt_fuse_transpose = v;
   else if (!strcmp(name, "mig_in_push")) ctx->opt_mig_in_push = v;
-  else if (!strcmp(name, "peer_transpose")) ctx->opt_peer = v < 0 ? (ctx->P >= 4 ? 3 : 1) : v;
+  else if (!strcmp(name, "peer_transpose")) ctx->opt_peer = v < 0 ? 3 : v;
   else if (!strcmp(name, "xfer_ctas")) ctx->opt_xfer_ctas = v;
   else if (!strcmp(name, "zsplit")) ctx->opt_zsplit = v;
   else if (!strcmp(name, "l2pf_push")) ctx->opt_l2pf_push = v;
