@@ -207,6 +207,8 @@ int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, in
  *                  64..1024), 0 = cuFFT batched 1-D plans
  *   "fft2d"        1 = x and y passes of a plane in ONE persistent kernel with the intermediate held in L2 (work queue
  *                  of row / column items, per-plane completion counters; N1 = N2 in 128..1024); 0 = separate kernels
+ *                  (default).  Measured slower than the separate passes: only built with -DNNPM_EXPERIMENTS
+ *                  (make EXPERIMENTS=1); the default library returns NNPM_ERR_ARG for 1
  *   "fft2d_block"  planes per block of that kernel (default 4: ~34 MB of intermediate in flight at 1024^2)
  *   "colfft"       1 = TMA-staged column FFT for the y passes (default when N2 is 64..1024), 0 = cuFFT 2-D plans
  *   "zfused"       3 = fused z-FFT * Green * z-iFFT kernel, persistent, next column group loaded by TMA during the
@@ -227,7 +229,8 @@ int nnpm_power_spectrum(nnpm_ctx *ctx, double *karray_out, double *power_out, in
  *                  TMA tensor maps, the z pass stores its rows straight into the owning ranks' slabs (NVLink peer
  *                  memory, no separate all-to-all pass).  Bit-identical to the other paths, but measured SLOWER:
  *                  the 64 / 128-byte pieces such stores put on NVLink reach ~380 GB/s against ~600 GB/s for the
- *                  copy engines' 1 MB runs; 0 = separate transposes (default)
+ *                  copy engines' 1 MB runs; 0 = separate transposes (default).  Only built with
+ *                  -DNNPM_EXPERIMENTS (make EXPERIMENTS=1); the default library returns NNPM_ERR_ARG for 1
  *   "peer_transpose" un-fused transposes over the CUDA-IPC peer mappings: 1 = copy-engine peer copies; 2 = one SM
  *                  kernel whose single-thread CTAs relay 8 KB pieces HBM -> shared memory -> peer mesh with bulk
  *                  asynchronous copies (nnpm_xfer.cuh); 3 = copy engines for the chunks of the pipeline that travel

@@ -1030,7 +1030,7 @@ static int do_solve(nnpm_ctx* ctx, cudaEvent_t* ev) {
   // NVLink transposes fused into the transform kernels: forward into the y pass' tensor stores (needs the TMA
   // column engine), backward into the z pass' register stores (needs the fused z pass and a power-of-two slab)
   ZDst zd;
-  const bool fuse = ctx->P > 1 && ctx->opt_fuse_transpose && ctx->peer_ok && ctx->P <= 8;
+  const bool fuse = NNPM_EXP_PEER && ctx->P > 1 && ctx->opt_fuse_transpose && ctx->peer_ok && ctx->P <= 8;
   const bool fuse_fwd = fuse && ycol;
   const bool fuse_bwd = fuse && fusedz && zdst_peers(ctx, &zd);
   if (fuse_fwd) CKR(colfft_peer_maps(ctx));
@@ -1367,12 +1367,18 @@ extern "C" int nnpm_set_option(nnpm_ctx* ctx, const char* name, double value) {
   else if (!strcmp(name, "sort_cells")) ctx->opt_sort_cells = v;
   else if (!strcmp(name, "colfft")) ctx->opt_colfft = v;
   else if (!strcmp(name, "rowfft")) ctx->opt_rowfft = v;
-  else if (!strcmp(name, "fft2d")) ctx->opt_fft2d = v;
+  else if (!strcmp(name, "fft2d")) {
+    if (v && !NNPM_EXP_PEER) return fail(ctx, NNPM_ERR_ARG, "option fft2d needs a library built with -DNNPM_EXPERIMENTS (make EXPERIMENTS=1)");
+    ctx->opt_fft2d = v;
+  }
   else if (!strcmp(name, "fft2d_block")) ctx->opt_fft2d_block = v;
   else if (!strcmp(name, "pipeline")) ctx->opt_pipeline = v;
   else if (!strcmp(name, "pipeline_chunks")) ctx->opt_pipe_chunks = v < 0 ? 0 : (v > 4 ? 4 : v);
   else if (!strcmp(name, "ce_streams")) ctx->opt_ce_streams = v < 0 ? 0 : (v > 8 ? 8 : v);
-  else if (!strcmp(name, "fuse_transpose")) ctx->opt_fuse_transpose = v;
+  else if (!strcmp(name, "fuse_transpose")) {
+    if (v && !NNPM_EXP_PEER) return fail(ctx, NNPM_ERR_ARG, "option fuse_transpose needs a library built with -DNNPM_EXPERIMENTS (make EXPERIMENTS=1)");
+    ctx->opt_fuse_transpose = v;
+  }
   else if (!strcmp(name, "mig_in_push")) ctx->opt_mig_in_push = v;
   else if (!strcmp(name, "peer_transpose")) ctx->opt_peer = v < 0 ? 3 : v;
   else if (!strcmp(name, "xfer_ctas")) ctx->opt_xfer_ctas = v;

@@ -52,6 +52,14 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* 
 // d == this rank), i.e. the y pass and the forward all-to-all are ONE kernel and the NVLink transfer of group g
 // overlaps the arithmetic of group g + 1.
 struct PeerMaps { CUtensorMap m[8]; };
+// The transposes fused into the transform kernels' stores ("fuse_transpose" = 1) are bit-identical to the separate
+// transposes but measured slower: their PEER = true instantiations are only built with
+// -DNNPM_EXPERIMENTS (make EXPERIMENTS=1); the default library refuses the option.
+#ifdef NNPM_EXPERIMENTS
+constexpr bool NNPM_EXP_PEER = true;
+#else
+constexpr bool NNPM_EXP_PEER = false;
+#endif
 
 template <int R1, int R2, int MODE, bool PEER>
 __global__ void __launch_bounds__(4 * (R1 > R2 ? R1 : R2), 1)
@@ -521,7 +529,8 @@ static int colfft_y(nnpm_ctx* ctx, bool inverse, i64 plane0 = 0, i64 nplanes = -
   static const PeerMaps no_peers = {};
   if (to_peers) {
     if (inverse || !ctx->peer_maps) return fail(ctx, NNPM_ERR_STATE, "fused forward transpose: peer tensor maps missing");
-    return colfft_dispatch<CF_FWD, true>(ctx, g.N2, ctx->tm_y, a, ctx->peer_maps);
+    if (!NNPM_EXP_PEER) return fail(ctx, NNPM_ERR_STATE, "fused forward transpose: built without -DNNPM_EXPERIMENTS");
+    return colfft_dispatch<CF_FWD, NNPM_EXP_PEER>(ctx, g.N2, ctx->tm_y, a, ctx->peer_maps);
   }
   return inverse ? colfft_dispatch<CF_INV, false>(ctx, g.N2, ctx->tm_y, a, &no_peers)
                  : colfft_dispatch<CF_FWD, false>(ctx, g.N2, ctx->tm_y, a, &no_peers);
@@ -600,8 +609,8 @@ static int zfused_p_launch(nnpm_ctx* ctx, double2* T, double scale, i64 jlbeg, i
     const size_t smem = (size_t)R1_ * R2_ * (8 * 16 + (TWO_ ? 2 : 1) * (16 + 8));                                        \
     const int grid = a.ngroups < ctx->nsm ? a.ngroups : ctx->nsm;                                                       \
     if (dst) {                                                                                                         \
-      CK(cudaFuncSetAttribute(k_zfused_p<R1_, R2_, TWO_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      k_zfused_p<R1_, R2_, TWO_, true><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(TWO_ ? ctx->tm_z4 : ctx->tm_z8, d, a); \
+      CK(cudaFuncSetAttribute(k_zfused_p<R1_, R2_, TWO_, NNPM_EXP_PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      k_zfused_p<R1_, R2_, TWO_, NNPM_EXP_PEER><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(TWO_ ? ctx->tm_z4 : ctx->tm_z8, d, a); \
     } else {                                                                                                           \
       CK(cudaFuncSetAttribute(k_zfused_p<R1_, R2_, TWO_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       k_zfused_p<R1_, R2_, TWO_, false><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(TWO_ ? ctx->tm_z4 : ctx->tm_z8, d, a); \
@@ -658,8 +667,8 @@ static int zfused_s_launch(nnpm_ctx* ctx, double2* T, double scale, i64 jlbeg, i
     const size_t smem = (size_t)N_ * 8 * 16 + ((size_t)N_ * 8 + 8 * (N_ / 32)) * 8 + (size_t)N_ * 24;                    \
     const int grid = a.ngroups < ctx->nsm ? a.ngroups : ctx->nsm;                                                       \
     if (dst) {                                                                                                         \
-      CK(cudaFuncSetAttribute(k_zfused_s<R1_, R2_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-      k_zfused_s<R1_, R2_, true><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(ctx->tm_z8, d, a);                 \
+      CK(cudaFuncSetAttribute(k_zfused_s<R1_, R2_, NNPM_EXP_PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+      k_zfused_s<R1_, R2_, NNPM_EXP_PEER><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(ctx->tm_z8, d, a);                 \
     } else {                                                                                                           \
       CK(cudaFuncSetAttribute(k_zfused_s<R1_, R2_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
       k_zfused_s<R1_, R2_, false><<<grid, 8 * (R1_ > R2_ ? R1_ : R2_), smem, ctx->st>>>(ctx->tm_z8, d, a);                \

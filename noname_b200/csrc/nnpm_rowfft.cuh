@@ -260,6 +260,12 @@ static int rowfft_x(nnpm_ctx* ctx, bool inverse, i64 plane0 = 0, i64 nplanes = -
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef NNPM_EXPERIMENTS
+// The fused x + y transform (k_fft2d, option "fft2d") is bit-identical to the separate passes but measured slower
+// (DESIGN.md section 3): only built with -DNNPM_EXPERIMENTS (make EXPERIMENTS=1).
+static bool fft2d_supported(const nnpm_ctx*) { return false; }
+static int fft2d_xy(nnpm_ctx* ctx, bool, i64 = 0, i64 = -1) { return fail(ctx, NNPM_ERR_STATE, "fft2d: built without -DNNPM_EXPERIMENTS"); }
+#else
 // Fused 2-D transform of the owned planes with the intermediate held in L2 (k_fft2d).
 //
 // Run as separate kernels, the x pass and the y pass each read and write the whole mesh from / to HBM: 4 x 8.6 GB per
@@ -524,3 +530,4 @@ static int fft2d_xy(nnpm_ctx* ctx, bool inverse, i64 plane0 = 0, i64 nplanes = -
 #undef F2
   return fail(ctx, NNPM_ERR_STATE, "fused 2-D transform does not support N1 = N2 = %lld", (long long)g.N1);
 }
+#endif  // NNPM_EXPERIMENTS

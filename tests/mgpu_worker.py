@@ -15,7 +15,7 @@ def main():
     import torch
     import torch.distributed as dist
     from conftest import make_particles, nlinf
-    from noname_b200 import DevicePM
+    from noname_b200 import DevicePM, NNPMError
     from oracle import pm_ref as O
 
     rank = int(os.environ["RANK"])
@@ -38,9 +38,9 @@ def main():
             errs.append(f"rank {rank}: {name} FAILED {detail}")
 
     # (deposit mode, sort cadence): sort_every > 0 runs the tiled shared-memory deposit / push on slabs
-    # the last case runs the un-fused slab transposes (copy engines) instead of the ones fused into the FFT kernels
+    # the last case runs the slab transposes on the copy engines alone instead of the default (copy engines + SM kernel)
     for mode, sort_every, opts in (("atomic", 0, {}), ("fixedpoint", 0, {}), ("atomic", 1, {}), ("fixedpoint", 2, {}),
-                                   ("atomic", 1, {"fuse_transpose": 0})):
+                                   ("atomic", 1, {"peer_transpose": 1})):
         dev = DevicePM(dims, npart, rank=3, device=lr, nranks=P, rank_id=rank, deposit_mode=mode, timing=True,
                        sort_every=sort_every, part_capacity=npart)   # clustered particles: a slab may hold far more than npart / P
         for k_, v_ in opts.items():
@@ -126,16 +126,22 @@ def main():
         uid = [DevicePM.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         dev.comm_init(uid[0])
-        for k_, v_ in opts.items():
-            dev.set_option(k_, v_)
+        try:
+            for k_, v_ in opts.items():
+                dev.set_option(k_, v_)
+        except NNPMError as ex:   # "fuse_transpose" = 1 exists only in `make EXPERIMENTS=1` builds (same library on every rank)
+            assert name == "fused" and "NNPM_EXPERIMENTS" in str(ex), str(ex)
+            dev.close()
+            continue
         for rep in range(2):
             dev.set_field("rho", np.ascontiguousarray(rho[rank * nz2:(rank + 1) * nz2]))
             dev.solve()
             got[name] = dev.get_field("phi")
         check(f"solve {name}", nlinf(got[name], ref[rank * nz2:(rank + 1) * nz2]) < 1e-12 * np.max(np.abs(ref)) / np.max(np.abs(ref[rank * nz2:(rank + 1) * nz2])))
         dev.close()
+    base = "fused" if "fused" in got else "default"
     for name in ("default", "pipelined", "unpipelined", "sm", "sm_pipelined", "sm_few_ctas", "sm_last_chunk", "nccl"):
-        check(f"solve fused == {name}", np.array_equal(got["fused"], got[name]))
+        check(f"solve {base} == {name}", np.array_equal(got[base], got[name]))
 
     # fine mesh along z (N3 = 2048, BASELINE config 5): slab transposes + the radix-2-wrapped fused z pass
     d5 = (16, 16, 2048)

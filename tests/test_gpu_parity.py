@@ -173,7 +173,13 @@ def test_potential_fused_2d_transform(lib_built, O, dims, block):
     """k_fft2d: x and y passes of a plane in one persistent kernel (work queue of row / column items, per-plane
     completion counters, intermediate in L2) == the separate-kernel path bit for bit (same arithmetic, different
     schedule) == oracle; 2-D and 3-D meshes, plane counts that are not a multiple of the block."""
-    from noname_b200 import DevicePM
+    from noname_b200 import DevicePM, NNPMError
+    with DevicePM((64, 64, 1), 1, rank=2) as probe:
+        try:
+            probe.set_option("fft2d", 1)
+        except NNPMError as ex:   # the shipped library refuses the option: the kernel is built with `make EXPERIMENTS=1` only
+            assert "NNPM_EXPERIMENTS" in str(ex)
+            pytest.skip("k_fft2d is only built with -DNNPM_EXPERIMENTS (measured slower than the separate passes: DESIGN.md)")
     rng = np.random.default_rng(41)
     shape = (dims[2], dims[1], dims[0])
     rho = rng.random(shape)
