@@ -46,7 +46,10 @@ B_C = 96.0             # algorithmic bytes / mesh cell / step
 PHASE_BYTES = {"deposit": (48.0, 8.0), "fft_x": (0.0, 32.0), "fft_y": (0.0, 32.0), "fft_z": (0.0, 16.0), "push": (96.0, 8.0)}
 NVLINK_NOMINAL = 900e9   # per direction per GPU
 NVLINK_MEASURED = 770e9  # peer copy measured on this pool (B200_PROFILING.md)
-COSMO = dict(h=0.7, OmegaM=0.3, OmegaR=0.0)
+# hubble_time_gyr: the workload's time unit is pinned to the value the stored full-size P(k) references
+# (profiles/pk_ref.json, recorded on 1 GPU in rounds 1-2) were produced with; the package default is now 9.77813952
+# (noname_b200/cosmology.py).  A property of the synthetic workload, irrelevant to its cost.
+COSMO = dict(h=0.7, OmegaM=0.3, OmegaR=0.0, hubble_time_gyr=9.77793)
 ZINIT = 50.0
 PK_REF = os.path.join(ROOT, "profiles", "pk_ref.json")
 
@@ -253,7 +256,8 @@ def main():
     config = {"workload": workload, "particles": n ** 3, "mesh_cells": mesh ** 3, "interpolation": "cic/cic", "ic": args.ic,
               "l2": "inputs (>= 48 B/particle resident state) exceed the 126 MB L2 for n >= 256; no flush needed",
               "sort_every": args.sort_every, "deposit_mode": args.deposit_mode,
-              "parallelism": f"slab{world}" if world > 1 else "single"}
+              "parallelism": f"slab{world}" if world > 1 else "single",
+              "cosmology": dict(COSMO, zinit=ZINIT)}
 
     if args.impl == "reference":
         if rank != 0:

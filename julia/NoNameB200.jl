@@ -307,7 +307,7 @@ function parse_cosmology(expr)
     return Cosmo(get(kw, "h", 0.69), Ωm, 1.0 - get(kw, "OmegaK", 0.0) - Ωm - Ωr, Ωr)
 end
 const gyr_in_s = 1.e9 * 31_556_952                                            # :4
-const hubble_time_gyr = 9.77793                                               # Cosmology.jl: hubble_time_gyr(h) = 9.77793 / h
+const hubble_time_gyr = 9.77813952                                            # Cosmology.jl: hubble_time_gyr0(c) = 9.77813952 / c.h
 function age_gyr(c::Cosmo, z)                                                 # flat matter + Λ, closed form
     a = 1.0 / (1.0 + z); tH = hubble_time_gyr / c.h
     c.Ω_Λ == 0.0 && return tH * (2.0 / 3.0) * a^1.5 / sqrt(c.Ω_m)

@@ -3,7 +3,7 @@ src/cosmology.jl:4-46, 61-72 of the reference (a(t), da/dt, z(t), Enzo code unit
 
 The reference root-finds Cosmology.jl's `age_gyr` with Roots.jl's `fzero` five times per step
 (cosmology.jl:7-11); both packages are un-vendored and unpinned.  Here age(a) is a 1-D integral
-  age = t_H * int_0^a x dx / sqrt(Or + Om x + Ok x^2 + OL x^4),   t_H = 9.77793 Gyr / h
+  age = t_H * int_0^a x dx / sqrt(Or + Om x + Ok x^2 + OL x^4),   t_H = 9.77813952 Gyr / h
 evaluated by composite Gauss-Legendre in s = sqrt(x) (closed form for Or = Ok = 0), and a(t) is
 found by safeguarded Newton iterations on it (dt/da is the integrand) -- microseconds per call,
 so the five scalars per step stay off the GPU step's critical path.
@@ -16,7 +16,13 @@ import re
 import numpy as np
 
 gyr_in_s = 1.0e9 * 31_556_952            # cosmology.jl:4
-HUBBLE_TIME_GYR = 9.77793                # Cosmology.jl: hubble_time_gyr(h) = 9.77793 / h
+# Cosmology.jl (un-vendored, unpinned): hubble_time_gyr0(c) = 9.77813952 / c.h in the releases of the reference's era
+# (quoted from memory of the package -- "parity unpinned").  The value is corroborated by the reference's own constants:
+# da/dt = dadt(a) (cosmology.jl:30-37) holds for a(t) = a_from_t_internal(t) only if
+# t_H = 2.519445e17 / gyr_in_s / sqrt(2/3) = 9.778122 Gyr (get_units' T, cosmology.jl:4, :69) -- 9.77813952 matches that
+# to 1.8e-6, the Julian-year figure 9.7779222 to 2e-5 (tests/test_oracle_kats.py).  Rounds 1-2 of this repo used 9.77793;
+# `Cosmology(..., hubble_time_gyr=9.77793)` reproduces them (bench.py does, for its stored P(k) reference).
+HUBBLE_TIME_GYR = 9.77813952
 
 _GL_X, _GL_W = np.polynomial.legendre.leggauss(48)
 
@@ -24,7 +30,8 @@ _GL_X, _GL_W = np.polynomial.legendre.leggauss(48)
 class Cosmology:
     """`cosmology(h=, OmegaM=, OmegaK=0, OmegaR=nothing)` of Cosmology.jl (fields h, Ω_m, Ω_Λ, Ω_r)."""
 
-    def __init__(self, h=0.69, OmegaM=0.29, OmegaK=0.0, OmegaR=None, Tcmb=2.7255, Neff=3.04):
+    def __init__(self, h=0.69, OmegaM=0.29, OmegaK=0.0, OmegaR=None, Tcmb=2.7255, Neff=3.04, hubble_time_gyr=None):
+        self.tH = float(HUBBLE_TIME_GYR if hubble_time_gyr is None else hubble_time_gyr)   # Gyr * h
         if OmegaR is None:
             og = 4.48131e-7 * Tcmb ** 4 / h ** 2
             OmegaR = og + Neff * og * (7.0 / 8.0) * (4.0 / 11.0) ** (4.0 / 3.0)
@@ -56,11 +63,11 @@ class Cosmology:
         return float(np.sum(f * _GL_W[None, :] * half))
 
     def age_gyr(self, z):
-        return HUBBLE_TIME_GYR / self.h * self.age_th(1.0 / (1.0 + z))
+        return self.tH / self.h * self.age_th(1.0 / (1.0 + z))
 
     def a_of_age_gyr(self, t_gyr):
         """Inverse of age_gyr in terms of a = 1/(1+z): safeguarded Newton."""
-        tau = t_gyr * self.h / HUBBLE_TIME_GYR
+        tau = t_gyr * self.h / self.tH
         if tau <= 0.0:
             raise ValueError("time must be positive")
         a = (1.5 * tau * math.sqrt(self.Om)) ** (2.0 / 3.0)      # EdS guess

@@ -281,15 +281,19 @@ def kick(v, a, dt, ascale=None, dadt=None):
 # --------------------------------------------------------------------------------------
 
 gyr_in_s = 1.0e9 * 31_556_952                  # cosmology.jl:4
-# Cosmology.jl (unpinned, not vendored): hubble_time_gyr = 9.77793 / h.
-HUBBLE_TIME_GYR = 9.77793
+# Cosmology.jl (unpinned, not vendored): hubble_time_gyr0(c) = 9.77813952 / c.h in the releases of the reference's
+# era, quoted from memory.  Corroborated by the reference's own constants: da/dt = dadt(a) (cosmology.jl:30-37) holds
+# for a(t) = a_from_t_internal(t) only if t_H = 2.519445e17 / gyr_in_s / sqrt(2/3) = 9.778122 Gyr (cosmology.jl:4, :69);
+# 9.77813952 matches that to 1.8e-6 (tests/test_oracle_kats.py).  Rounds 1-2 used 9.77793 (2e-5 off).
+HUBBLE_TIME_GYR = 9.77813952
 
 
 class Cosmo:
     """Restates Cosmology.jl's `cosmology(h=, OmegaM=, OmegaK=0, OmegaR=nothing)` constructor
     and `age_gyr` (published algorithm: age = t_H * int_0^a x dx / sqrt(Or + Om x + Ok x^2 + OL x^4))."""
 
-    def __init__(self, h=0.69, OmegaM=0.29, OmegaK=0.0, OmegaR=None, Tcmb=2.7255, Neff=3.04):
+    def __init__(self, h=0.69, OmegaM=0.29, OmegaK=0.0, OmegaR=None, Tcmb=2.7255, Neff=3.04, hubble_time_gyr=None):
+        self.tH = float(HUBBLE_TIME_GYR if hubble_time_gyr is None else hubble_time_gyr)
         if OmegaR is None:
             og = 4.48131e-7 * Tcmb ** 4 / h ** 2
             on = Neff * og * (7.0 / 8.0) * (4.0 / 11.0) ** (4.0 / 3.0)
@@ -308,7 +312,7 @@ class Cosmo:
         # substitution a = s^2 removes the sqrt(a) endpoint behaviour when Or == 0
         val, _ = integrate.quad(lambda s: 2.0 * s ** 3 / self.a2E(s * s), 0.0, math.sqrt(a1),
                                 epsabs=0.0, epsrel=1e-13, limit=200)
-        return HUBBLE_TIME_GYR / self.h * val
+        return self.tH / self.h * val
 
 
 def get_units_T(cosmo, zinit):

@@ -102,7 +102,10 @@ def test_cosmology_eds_closed_form():
     zi = 400.0
     u = cos.get_units(c, zi, zinit=zi)
     ts = c.age_gyr(zi) * (cos.gyr_in_s / u.T)
-    assert ts == pytest.approx(math.sqrt(2.0 / 3.0), rel=2e-4)           # cosmology.jl:69 constants
+    assert ts == pytest.approx(math.sqrt(2.0 / 3.0), rel=5e-6)           # cosmology.jl:69 constants pin t_H (test_kat8)
+    assert cos.HUBBLE_TIME_GYR == O.HUBBLE_TIME_GYR
+    old = cos.Cosmology(h=1.0, OmegaM=1.0, OmegaR=0.0, hubble_time_gyr=9.77793)   # rounds 1-2 (bench.py's stored P(k))
+    assert old.age_gyr(zi) / c.age_gyr(zi) == pytest.approx(9.77793 / 9.77813952, rel=1e-15)
     assert cos.a_from_t_internal(c, 27 * ts, zi, zwherea1=zi) == pytest.approx(9.0, rel=1e-12)
     assert cos.dadt(c, 4.0, zwherea1=zi) == math.sqrt(2.0 / (3.0 * 4.0))
     assert cos.z_from_a(c, 2.0, zwherea1=3.0) == 1.0

@@ -195,12 +195,19 @@ def test_kat7_comoving_kick_without_force():
 
 
 def test_kat8_einstein_de_sitter_scalars():
-    """cosmology(h=1,OmegaM=1,OmegaR=0): StartTime = sqrt(2/3), a ~ t^(2/3), adot = sqrt(2/(3a))
-    (cosmology.jl:33,69; the numerical constants of the Enzo unit system agree to ~1e-4)."""
+    """cosmology(h=1,OmegaM=1,OmegaR=0): StartTime = sqrt(2/3), a ~ t^(2/3), adot = sqrt(2/(3a)) (cosmology.jl:33,69).
+    The reference's own constants pin Cosmology.jl's Hubble time: the kick integrates da/dt = dadt(a) = sqrt(2/3) at
+    a = 1, while a(t) comes from age_gyr -- the two agree only if t_H = 2.519445e17 s / gyr_in_s / sqrt(2/3)
+    = 9.778122 Gyr.  9.77813952 (the oracle's value) matches to 1.8e-6; the Julian-year 9.7779222 would miss by 2e-5."""
     c = O.Cosmo(h=1.0, OmegaM=1.0, OmegaR=0.0)
     zi = 400.0
     ts, te = O.start_stop_times(c, zi, 9.0)
-    assert ts == pytest.approx(math.sqrt(2.0 / 3.0), rel=2e-4)
+    assert ts == pytest.approx(math.sqrt(2.0 / 3.0), rel=5e-6)
+    assert O.HUBBLE_TIME_GYR == pytest.approx(2.519445e17 / O.gyr_in_s / math.sqrt(2.0 / 3.0), rel=5e-6)
+    # da/dt of the tabulated a(t) against the closed-form rate the comoving kick uses (cosmology.jl:30-37)
+    h = 1e-4 * ts
+    dadt_fd = (O.a_from_t_internal(c, ts + h, zi, zwherea1=zi) - O.a_from_t_internal(c, ts - h, zi, zwherea1=zi)) / (2 * h)
+    assert dadt_fd == pytest.approx(O.dadt(c, 1.0, zwherea1=zi), rel=5e-6)
     a1 = O.a_from_t_internal(c, ts, zi, zwherea1=zi)
     assert a1 == pytest.approx(1.0, rel=1e-10)
     a2 = O.a_from_t_internal(c, 8 * ts, zi, zwherea1=zi)
