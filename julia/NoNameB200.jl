@@ -14,11 +14,18 @@
 # file against include/nnpm.h.  Host arrays cross the ABI unchanged: Julia's column-major Array{Float64}
 # (rank, Npart) / (N1,N2,N3) is exactly the layout nnpm.h documents.
 #
-# Deliberately NOT here (out of the hot path, SURVEY.md section 2): Hydro/SPH/FOF, Winston plots, the HDF5/JLD
-# writers themselves -- analyzePM takes the reference's IOtools functions as `writer` (default: Serialization).
+# Deliberately NOT here (out of the hot path, SURVEY.md section 2): Hydro/SPH/FOF, Winston plots, the `Profile` dump.
+# Optional packages, used when installed: HDF5.jl -- analyzePM then writes NNNNN.h5 with the groups and datasets of
+# IOtools.grid_output / particle_output (src/IOtools.jl:73-116), else a Serialization file under the same names;
+# MPI.jl -- conf key NGPUs = P (one Julia process per GPU, `mpiexec -n P julia ...`; the reference has no parallelism).
 module NoNameB200
 
 using Printf, Serialization
+
+const HAVE_HDF5 = Base.find_package("HDF5") !== nothing
+const HAVE_MPI = Base.find_package("MPI") !== nothing
+HAVE_HDF5 && @eval import HDF5
+HAVE_MPI && @eval import MPI
 
 export run_noname, noname, evolvePM, evolvePMCosmology, InitializeParticleSimulation, restart, DevicePM,
        deposit, compute_potential, compute_acceleration, interpVecToPoints, drift, kick, make_periodic,
@@ -406,24 +413,75 @@ output_due(c, t, cycle) = !get(c, "OutputDisabled", false) &&
     ((c["OutputEveryNCycle"] > 0 && mod(cycle, c["OutputEveryNCycle"]) == 0) ||
      (c["OutputDtDataDump"] != 0 && abs(t - c["LastOutputTime"]) >= c["OutputDtDataDump"]))
 
-"device -> host copy of what the reference keeps in gd / p; gd[1].d[\"ρD\"] is the density of the last deposit"
+"device -> host copy of what the reference keeps in gd / p; gd[1].d[\"ρD\"] is the density of the last deposit.
+With NGPUs > 1 the slabs / particle shares of all ranks are gathered: every rank ends up with the complete arrays."
 function sync_host!(dev, gd, p)
     n = local_count(dev)
-    if p["x"] === nothing || size(p["x"], 2) != n
-        p["x"] = zeros(dev.rank, n); p["v"] = zeros(dev.rank, n)
+    if dev.nranks == 1
+        if p["x"] === nothing || size(p["x"], 2) != n
+            p["x"] = zeros(dev.rank, n); p["v"] = zeros(dev.rank, n)
+        end
+        download!(dev, p["x"], p["v"])
+        get_field!(dev, FIELD_PHI, gd[1].d["Φ"])
+        get_field!(dev, FIELD_RHO, gd[1].d["ρD"])       # kept by the step (option keep_rho)
+        return nothing
     end
-    download!(dev, p["x"], p["v"])
-    get_field!(dev, FIELD_PHI, gd[1].d["Φ"])
-    get_field!(dev, FIELD_RHO, gd[1].d["ρD"])       # kept by the step (option keep_rho)
+    comm = MPI.COMM_WORLD
+    xl = zeros(dev.rank, n); vl = zeros(dev.rank, n); ids = zeros(Int64, n)
+    download_ids!(dev, xl, vl, ids)
+    counts = MPI.Allgather(Int32(n), comm)               # particles held by every rank (Int32 counts: < 2^31 / rank each)
+    ntot = Int(sum(counts))
+    idall = zeros(Int64, ntot); xall = zeros(dev.rank, ntot); vall = zeros(dev.rank, ntot)
+    MPI.Allgatherv!(ids, MPI.VBuffer(idall, counts), comm)
+    MPI.Allgatherv!(xl, MPI.VBuffer(xall, counts .* Int32(dev.rank)), comm)
+    MPI.Allgatherv!(vl, MPI.VBuffer(vall, counts .* Int32(dev.rank)), comm)
+    if p["x"] === nothing || size(p["x"], 2) != ntot
+        p["x"] = zeros(dev.rank, ntot); p["v"] = zeros(dev.rank, ntot)
+    end
+    p["x"][:, idall .+ 1] = xall                         # the reference's particle order (ids are 0-based)
+    p["v"][:, idall .+ 1] = vall
+    N1, N2, N3 = dev.dims
+    slab = zeros(N1, N2, div(N3, dev.nranks))            # slabs are contiguous in k, the slowest Julia index
+    for (which, key) in ((FIELD_PHI, "Φ"), (FIELD_RHO, "ρD"))
+        get_field!(dev, which, slab)
+        MPI.Allgather!(slab, MPI.UBuffer(gd[1].d[key], length(slab)), comm)
+    end
     nothing
 end
-default_writer(fname, gp, gd, p) = open(io -> serialize(io, Dict("grid1/ρD" => gd[1].d["ρD"], "grid1/Φ" => gd[1].d["Φ"],
-                                                                 "particles" => p)), fname * ".jls", "w")
+
+# IOtools.grid_output + particle_output (src/IOtools.jl:73-116) through HDF5.jl
+function hdf5_writer(fname, gp, gd, p)
+    HDF5.h5open(fname * ".h5", "w") do f
+        for (_, cgp) in gp
+            g = HDF5.create_group(f, string("grid", cgp.id))
+            for (name, a) in gd[cgp.id].d
+                g[name] = dropdims(a; dims = Tuple(findall(size(a) .== 1)))      # IOtools.squeeze
+                HDF5.attributes(g[name])["vsz_range"] = Float64[gp[1].LE[1], gp[1].LE[2], gp[1].RE[1], gp[1].RE[2]]
+            end
+        end
+        g = HDF5.create_group(f, "particles")
+        rank = size(p["x"], 1)
+        g["x"] = p["x"][1, :]; g["vx"] = p["v"][1, :]
+        if rank > 1; g["y"] = p["x"][2, :]; g["vy"] = p["v"][2, :]; end
+        if rank > 2; g["z"] = p["x"][3, :]; g["vz"] = p["v"][3, :]; end
+        g["m"] = p["m"]
+    end
+    nothing
+end
+serialization_writer(fname, gp, gd, p) = open(io -> serialize(io, Dict("grid1/ρD" => gd[1].d["ρD"], "grid1/Φ" => gd[1].d["Φ"],
+                                                                       "particles" => p)), fname * ".jls", "w")
+default_writer(fname, gp, gd, p) = HAVE_HDF5 ? hdf5_writer(fname, gp, gd, p) : serialization_writer(fname, gp, gd, p)
+
 function analyzePM(gp, gd, p, conf, dev; force = false, writer = default_writer)
     (!readyForOutput(conf) && !force) && return nothing
     get(conf, "OutputDisabled", false) && return nothing
     sync_host!(dev, gd, p)
     c = conf
+    pk = get(c, "OutputPowerSpectrum", false) === true ? power_spectrum(dev) : nothing   # :47-61 (numbers, not a plot)
+    if dev.nranks > 1 && dev.rank_id != 0
+        c["CurrentOutputNumber"] += 1                    # same counters on every rank; rank 0 writes the files
+        return nothing
+    end
     isdir(c["OutputDirectory"]) || mkpath(c["OutputDirectory"])
     s = @sprintf("%5.5i", c["CurrentOutputNumber"])
     newD = c["OutputSeparateDirectories"] ? joinpath(c["OutputDirectory"], string(get(c, "OutputDirPrefix", ""), s)) : c["OutputDirectory"]
@@ -432,20 +490,43 @@ function analyzePM(gp, gd, p, conf, dev; force = false, writer = default_writer)
         for (k, v) in c; startswith(k, "_") || write(f, string(k, " = ", v, "\n")); end
     end
     c["CurrentOutputNumber"] += 1
-    writer(joinpath(newD, s), gp, gd, p)            # IOtools.grid_output + particle_output in a full NoName install
+    writer(joinpath(newD, s), gp, gd, p)
+    if pk !== nothing
+        open(joinpath(newD, s * "_PS.txt"), "w") do f
+            println(f, "# k P(k)   time = ", c["CurrentTime"])
+            for (k, q) in zip(pk[1], pk[2]); println(f, k, " ", q); end
+        end
+    end
     nothing
 end
 
 # ---- evolve loops: conf["Evolve"] plugins ------------------------------------------------------
 function device_for(gp, p, conf)
-    dev = DevicePM(gp[1].dim, prod(Int.(conf["ParticleDimensions"])); rank = conf["_rank"],
+    P = Int(get(conf, "NGPUs", 1)); rid = 0; device = Int(get(conf, "Device", 0))
+    npart = prod(Int.(conf["ParticleDimensions"]))
+    if P > 1
+        HAVE_MPI || error("NGPUs = $P needs MPI.jl (one Julia process per GPU: mpiexec -n $P julia ...)")
+        MPI.Initialized() || MPI.Init()
+        comm = MPI.COMM_WORLD
+        MPI.Comm_size(comm) == P || error("NGPUs = $P needs $P processes; this job has $(MPI.Comm_size(comm))")
+        rid = MPI.Comm_rank(comm); device = rid % P      # one node: local rank == rank
+    end
+    cap = (P > 1 && haskey(conf, "PartCapacityFactor")) ? Int(floor(Float64(conf["PartCapacityFactor"]) * npart / P)) + 4096 : 0
+    dev = DevicePM(gp[1].dim, npart; rank = conf["_rank"],
                    deposit = conf["ParticleDepositInterpolation"], backinterp = conf["ParticleBackInterpolation"],
                    sort_every = get(conf, "SortEvery", 8), deposit_mode = get(conf, "DepositMode", "atomic") == "fixedpoint" ? 1 : 0,
-                   device = get(conf, "Device", 0), bugcompat_interp_z = get(conf, "BackInterpBugCompat", false))
+                   device = device, bugcompat_interp_z = get(conf, "BackInterpBugCompat", false),
+                   nranks = P, rank_id = rid, part_capacity = cap)
+    P > 1 && comm_init!(dev, id -> MPI.Bcast!(id, 0, MPI.COMM_WORLD))
     ic = get(p, "_ic", nothing)
     pd = Int.(conf["ParticleDimensions"])
     if ic !== nothing && p["x"] === nothing
         ic[1] == :grf ? init_grf!(dev, pd, ic[2]..., Float64(p["m"])) : init_pancake!(dev, pd, ic[2]..., Float64(p["m"]))
+    elseif P > 1
+        # every rank holds the full host arrays (the initialisers ran on each): upload one contiguous share, then route
+        lo, hi = div(rid * npart, P), div((rid + 1) * npart, P)
+        upload!(dev, p["x"][:, lo+1:hi], p["v"][:, lo+1:hi], Float64(p["m"]); first_id = lo)
+        redistribute!(dev)
     else
         upload!(dev, p["x"], p["v"], Float64(p["m"]))
     end

@@ -362,9 +362,29 @@ def _output_due(c, t, cycle):
     return c["OutputDtDataDump"] != 0 and abs(t - c["LastOutputTime"]) >= c["OutputDtDataDump"]
 
 
+def _write_hdf5(fname, gp, gd, p):
+    """IOtools.grid_output + particle_output (src/IOtools.jl:73-116): group grid<id> with every gd array squeezed (and
+    the vsz_range attribute veusz reads), group particles with x, vx[, y, vy[, z, vz]], m."""
+    import h5py
+    with h5py.File(fname, "w") as f:
+        for k, cgp in gp.items():
+            g = f.create_group(f"grid{cgp.id}")
+            for name, a in gd[cgp.id].d.items():
+                # numpy C order with the Julia axes reversed == the bytes HDF5.jl writes for the column-major array
+                ds = g.create_dataset(name, data=np.squeeze(a))
+                ds.attrs["vsz_range"] = [gp[1].LE[0], gp[1].LE[1], gp[1].RE[0], gp[1].RE[1]]
+        g = f.create_group("particles")
+        for d, nm in enumerate("xyz"[: p["x"].shape[1]]):
+            g[nm] = np.ascontiguousarray(p["x"][:, d])
+            g[f"v{nm}"] = np.ascontiguousarray(p["v"][:, d])
+        g["m"] = p["m"]
+
+
 def analyzePM(gp, gd, p, conf, dev=None, force=False):
-    """:13-63.  HDF5/Winston are not available to this host; datasets with the reference's names
-    (grid1/ρD, grid1/Φ, particles/x, vx, ...) go to NNNNN.npz beside NNNNN_parameters.info."""
+    """:13-63.  NNNNN_parameters.info beside the data file: NNNNN.h5 with the reference's group / dataset names
+    (grid1/ρD, grid1/Φ, particles/x, vx, ..., m) when h5py is importable, else NNNNN.npz under the same names (conf
+    OutputFormat = hdf5 | npz forces one).  OutputPowerSpectrum = true (:47-61 saves a Winston plot) writes the numbers
+    instead: NNNNN_PS.txt, columns k and P(k) from the device-side powerSpectrum."""
     if not readyForOutput(conf) and not force:
         return None
     if conf.get("OutputDisabled"):
@@ -372,6 +392,10 @@ def analyzePM(gp, gd, p, conf, dev=None, force=False):
     c = conf
     if dev is not None:
         _sync_host(dev, gd, p)
+    pk = None
+    if c.get("OutputPowerSpectrum") is True:
+        # after the sync: the device-side P(k) re-deposits into the mesh (the next step deposits again anyway)
+        pk = dev.power_spectrum() if dev is not None else powerSpectrum(gp, gd, p, c)
     if dev is not None and dev.nranks > 1 and dev.rank_id != 0:
         c["CurrentOutputNumber"] += 1     # every rank keeps the same counters; rank 0 writes the files
         return None
@@ -387,11 +411,25 @@ def analyzePM(gp, gd, p, conf, dev=None, force=False):
             if not k.startswith("_"):
                 f.write(f"{k} = {v}\n")
     c["CurrentOutputNumber"] += 1
-    out = {"grid1/ρD": np.squeeze(gd[1].d["ρD"]), "grid1/Φ": np.squeeze(gd[1].d["Φ"]), "particles/m": p["m"]}
-    for d, nm in enumerate("xyz"[: p["x"].shape[1]]):
-        out[f"particles/{nm}"] = p["x"][:, d]
-        out[f"particles/v{nm}"] = p["v"][:, d]
-    np.savez(os.path.join(newd, s + ".npz"), **out)
+    fmt = str(c.get("OutputFormat", "auto")).lower()
+    if fmt not in ("auto", "hdf5", "npz"):
+        raise ValueError(f"OutputFormat must be hdf5, npz or auto (got {fmt!r})")
+    if fmt == "auto":
+        try:
+            import h5py  # noqa: F401
+            fmt = "hdf5"
+        except ImportError:
+            fmt = "npz"
+    if fmt == "hdf5":
+        _write_hdf5(os.path.join(newd, s + ".h5"), gp, gd, p)
+    else:
+        out = {"grid1/ρD": np.squeeze(gd[1].d["ρD"]), "grid1/Φ": np.squeeze(gd[1].d["Φ"]), "particles/m": p["m"]}
+        for d, nm in enumerate("xyz"[: p["x"].shape[1]]):
+            out[f"particles/{nm}"] = p["x"][:, d]
+            out[f"particles/v{nm}"] = p["v"][:, d]
+        np.savez(os.path.join(newd, s + ".npz"), **out)
+    if pk is not None:
+        np.savetxt(os.path.join(newd, s + "_PS.txt"), np.column_stack(pk), header=f"k P(k)   time = {c['CurrentTime']}")
     return None
 
 

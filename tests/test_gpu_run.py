@@ -97,7 +97,8 @@ def test_run_noname_shipped_cosmology_conf(lib_built, O, tmp_path, device_ics):
     z = 400 -> 9, ~7600 steps of evolvePMCosmology's dt control) end to end against the oracle's loop."""
     from noname_b200 import run_noname
     outdir = str(tmp_path / "out")
-    over = {"OutputDirectory": outdir, "RestartFileName": str(tmp_path / "restart.bin"), "SortEvery": 8}
+    over = {"OutputDirectory": outdir, "RestartFileName": str(tmp_path / "restart.bin"), "SortEvery": 8,
+            "OutputFormat": "npz"}
     if device_ics:
         over["DeviceInitialConditions"] = True
     gp, gd, p = run_noname(_conf_file(tmp_path, SHIPPED_COSMOLOGY_PM), overrides=over)
@@ -147,7 +148,8 @@ def test_run_noname_shipped_pm_conf_shape(lib_built, O, tmp_path):
     device generator, whose lattice (100 x 100) differs from the mesh: the temporary lattice context is exercised."""
     from noname_b200 import run_noname, NoName
     outdir = str(tmp_path / "out")
-    over = {"OutputDirectory": outdir, "RestartFileName": str(tmp_path / "restart.bin"), "InputPowerSpectrum": "scaleFreePS(-1, .3)"}
+    over = {"OutputDirectory": outdir, "RestartFileName": str(tmp_path / "restart.bin"), "InputPowerSpectrum": "scaleFreePS(-1, .3)",
+            "OutputFormat": "npz"}
     gp, gd, p = run_noname(_conf_file(tmp_path, SHIPPED_PM), overrides=over)
     c = NoName.conf
     xr, vr = O.synthetic_grf((100, 100, 1), 2, 12345, -1.0, 0.3 / 1000, 0.0)

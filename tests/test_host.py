@@ -300,6 +300,48 @@ def test_evolvepmcosmology_scalars_and_dt(monkeypatch, tmp_path):
         dt = min(0.5 * (1.0 / 64) / (0.05 + 1e-30), 0.1 * t, 1.0)
 
 
+def test_analyzepm_writes_reference_dataset_names_and_power_spectrum(monkeypatch, tmp_path):
+    """:13-63 + IOtools.jl:73-116: NNNNN_parameters.info, the data file under the reference's dataset names, and -- with
+    OutputPowerSpectrum = true -- the P(k) numbers the reference would have plotted (:47-61)."""
+    class Dev(_FakeDev):
+        def power_spectrum(self):
+            self.calls.append("pk")
+            return np.array([1.0, 2.0]), np.array([0.5, 0.25])
+    dev = Dev(1.0)
+    synced = []
+    monkeypatch.setattr(PM, "_sync_host", lambda *a, **k: synced.append(len(dev.calls)))
+    c = dict(cf.DEFAULTS, OutputDirectory=str(tmp_path / "out"), OutputDirPrefix="pm_", OutputPowerSpectrum=True,
+             OutputFormat="npz", CurrentTime=0.75, _hidden=1)
+    gp = {1: PM.GridPatch([0, 0, 0], [1, 1, 1], 1, 1, (4, 4, 1))}
+    gd = {1: PM.GridData({"ρD": np.full((1, 4, 4), 2.0), "Φ": np.zeros((1, 4, 4))})}
+    p = {"x": np.arange(6.0).reshape(3, 2), "v": -np.arange(6.0).reshape(3, 2), "m": 0.5}
+    assert PM.analyzePM(gp, gd, p, c, dev) is None and not synced          # nothing due, nothing copied
+    PM.analyzePM(gp, gd, p, c, dev, force=True)
+    assert synced == [0] and dev.calls == ["pk"]                            # host state first, then the P(k) deposit
+    d = tmp_path / "out" / "pm_00000"
+    assert sorted(f.name for f in d.iterdir()) == ["00000.npz", "00000_PS.txt", "00000_parameters.info"]
+    z = np.load(d / "00000.npz")
+    assert sorted(z.files) == ["grid1/Φ", "grid1/ρD", "particles/m", "particles/vx", "particles/vy", "particles/x", "particles/y"]
+    assert z["grid1/ρD"].shape == (4, 4) and z["particles/y"].tolist() == [1.0, 3.0, 5.0] and float(z["particles/m"]) == 0.5
+    assert np.loadtxt(d / "00000_PS.txt").tolist() == [[1.0, 0.5], [2.0, 0.25]]
+    info = (d / "00000_parameters.info").read_text(encoding="utf-8")
+    assert "CurrentTime = 0.75" in info and "_hidden" not in info
+    assert c["CurrentOutputNumber"] == 1
+    with pytest.raises(ValueError):
+        PM.analyzePM(gp, gd, p, dict(c, OutputFormat="jld"), dev, force=True)
+
+
+def test_hdf5_output_layout_when_h5py_is_available(tmp_path):
+    h5py = pytest.importorskip("h5py")     # not in the build image: the writer runs where the reference's HDF5 tooling exists
+    gp = {1: PM.GridPatch([0, 0, 0], [1, 1, 1], 1, 1, (4, 4, 1))}
+    gd = {1: PM.GridData({"ρD": np.full((1, 4, 4), 2.0), "Φ": np.zeros((1, 4, 4))})}
+    p = {"x": np.arange(6.0).reshape(3, 2), "v": -np.arange(6.0).reshape(3, 2), "m": 0.5}
+    PM._write_hdf5(str(tmp_path / "o.h5"), gp, gd, p)
+    with h5py.File(tmp_path / "o.h5") as f:
+        assert sorted(f["grid1"]) == ["Φ", "ρD"] and sorted(f["particles"]) == ["m", "vx", "vy", "x", "y"]
+        assert f["grid1/ρD"].attrs["vsz_range"].tolist() == [0, 0, 1, 1]
+
+
 def test_restart_roundtrip_resumes_time(tmp_path):
     """src/restart.jl + IOtools.jl:118-138 (with the F10 arity bug fixed): state and clock survive."""
     gp = {1: PM.GridPatch([0, 0, 0], [1, 1, 1], 1, 1, (8, 8, 1))}

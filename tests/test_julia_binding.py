@@ -145,3 +145,65 @@ def test_documents_cite_an_existing_julia_file():
         txt = open(os.path.join(ROOT, doc), encoding="utf-8").read()
         if "julia/NoNameB200.jl" in txt:
             assert os.path.isfile(JULIA)
+
+
+def _julia_code_only(src):
+    """the source with comments, string and character literals blanked (enough of a lexer for the checks below)"""
+    out, i, n = [], 0, len(src)
+    while i < n:
+        ch = src[i]
+        if ch == "#":
+            while i < n and src[i] != "\n":
+                i += 1
+            continue
+        if ch == '"':
+            if src.startswith('"""', i):
+                i = src.index('"""', i + 3) + 3
+            else:
+                j = i + 1
+                while src[j] != '"':
+                    j += 2 if src[j] == "\\" else 1
+                i = j + 1
+            out.append('""')
+            continue
+        if ch == "'" and i + 2 < n and (src[i + 2] == "'" or (src[i + 1] == "\\" and src[i + 3] == "'")):
+            i += 3 if src[i + 2] == "'" else 4
+            out.append("' '")
+            continue
+        out.append(ch)
+        i += 1
+    return "".join(out)
+
+
+def test_julia_blocks_and_brackets_balance():
+    """No julia binary here: at least every function / if / for / while / do / struct / module / try block is closed by
+    its `end` (an `end` inside [] or () is an index, a for / if inside them a comprehension) and brackets pair up."""
+    code = _julia_code_only(open(JULIA, encoding="utf-8").read())
+    stack, br, line = [], [], 1
+    for m in re.finditer(r"[\[\](){}]|\b(function|if|for|while|do|struct|module|begin|let|try|quote|end)\b|\n", code):
+        t = m.group(0)
+        if t == "\n":
+            line += 1
+        elif t in "[({":
+            br.append((t, line))
+        elif t in "])}":
+            assert br and "[({".index(br[-1][0]) == "])}".index(t), f"line {line}: unmatched {t}"
+            br.pop()
+        elif t == "end":
+            if not br:
+                assert stack, f"line {line}: `end` without an open block"
+                stack.pop()
+        elif not (br and t in ("for", "if")):
+            stack.append((t, line))
+    assert not stack and not br, f"unclosed: {stack} {br}"
+
+
+def test_julia_host_covers_the_reference_surface():
+    """names a NoName user calls (src/NoName.jl:8, src/ParticleMesh.jl operator list) are defined in the module"""
+    code = _julia_code_only(open(JULIA, encoding="utf-8").read())
+    for name in ("run_noname", "noname", "restart", "evolvePM", "evolvePMCosmology", "InitializeParticleSimulation", "analyzePM",
+                 "readyForOutput", "write_all", "deposit", "compute_potential", "compute_acceleration", "interpVecToPoints",
+                 "drift", "kick", "make_periodic", "powerSpectrum", "UniformParticles", "UniformParticleWind",
+                 "ZeldovichPancakeParticles", "PowerSpectrumParticles", "a_from_t_internal", "dadt_from_t_internal",
+                 "z_from_t_internal", "hdf5_writer", "device_for", "sync_host!"):
+        assert re.search(rf"(^|\n)\s*(function\s+)?{re.escape(name)}\(", code), name
