@@ -159,6 +159,14 @@ int nnpm_init_synthetic(nnpm_ctx *ctx, int kind, const int64_t pdims[3], uint64_
  * FFT passes (and slab transposes when nranks > 1).  oracle/pm_ref.py:synthetic_grf is the checker. */
 int nnpm_init_grf(nnpm_ctx *ctx, const int64_t pdims[3], uint64_t seed, double ps_index, double disp_rms,
                   double vfac, double m);
+/* The same generator with multiplePeaksPS(n, norm, k, lnwidth) (src/InputPowerSpectra.jl:6-24, P at :28-36;
+ * doc/InputPowerSpectra.md), the spectrum run/PM/particle_mesh.conf names:
+ *   P(k) = k^ps_index  where |k - kpeak[p]| / k < lnwidth[p] / 2 for some p < npeaks,  0 elsewhere
+ * (k = |k| in rad/cell, as the reference evaluates it, :229-231).  1 <= npeaks <= NNPM_MAX_PEAKS.  A spectrum whose
+ * windows contain no mode of the lattice gives zero displacements.  oracle/pm_ref.py:synthetic_grf(peaks=...) checks it. */
+#define NNPM_MAX_PEAKS 8
+int nnpm_init_grf_peaks(nnpm_ctx *ctx, const int64_t pdims[3], uint64_t seed, double ps_index, int32_t npeaks,
+                        const double *kpeak, const double *lnwidth, double disp_rms, double vfac, double m);
 /* ZeldovichPancakeParticles (src/ParticleMesh.jl:177-198) on the device: lattice, then
  *   v1 = vamp * sin(2 pi x1),  x1 += xamp * sin(2 pi x1),  make_periodic;
  * the host passes xamp = 2/5 A a and vamp = 2/5 A adot with A, a, adot evaluated as the reference does. */

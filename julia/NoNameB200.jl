@@ -133,6 +133,10 @@ init_synthetic!(dev, kind, pdims, seed, nmodes, kmax, disp_rms, vfac, m) =
 init_grf!(dev, pdims, seed, ps_index, disp_rms, vfac, m) =
     check(dev, ccall((:nnpm_init_grf, libnnpm), Cint, (Ptr{Cvoid}, Ptr{Int64}, UInt64, Float64, Float64, Float64, Float64),
                      dev.h, Int64[pdims...], seed, ps_index, disp_rms, vfac, m))
+init_grf_peaks!(dev, pdims, seed, ps_index, kpeak::Vector{Float64}, lnwidth::Vector{Float64}, disp_rms, vfac, m) =
+    check(dev, ccall((:nnpm_init_grf_peaks, libnnpm), Cint,
+                     (Ptr{Cvoid}, Ptr{Int64}, UInt64, Float64, Int32, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Float64),
+                     dev.h, Int64[pdims...], seed, ps_index, length(kpeak), kpeak, lnwidth, disp_rms, vfac, m))
 init_pancake!(dev, pdims, xamp, vamp, m) =
     check(dev, ccall((:nnpm_init_pancake, libnnpm), Cint, (Ptr{Cvoid}, Ptr{Int64}, Float64, Float64, Float64),
                      dev.h, Int64[pdims...], xamp, vamp, m))
@@ -361,16 +365,28 @@ function pancake_amplitudes(conf)                                             # 
 end
 # generated on the device: only the request is recorded; p["x"] / p["v"] are filled at the first output
 ZeldovichPancakeParticles(gp, gd, p, conf) = (p["_ic"] = (:pancake, pancake_amplitudes(conf)); nothing)   # :177-198
-function PowerSpectrumParticles(gp, gd, p, conf)                              # :209-254 with scaleFreePS (seeded)
-    m = match(r"^\s*scaleFreePS\(\s*([-+0-9.eE]+)\s*,\s*([-+0-9.eE]+)\s*\)\s*$", string(get(conf, "InputPowerSpectrum", "")))
-    m === nothing && error("Requested to use PowerSpectrumParticles: InputPowerSpectrum = scaleFreePS(n, norm) required")
+# InputPowerSpectrum = scaleFreePS(n, norm) | multiplePeaksPS(n, norm, [k...], lnwidth | [w...])   (src/InputPowerSpectra.jl:1-24)
+function parse_input_power_spectrum(expr)
+    m = match(r"^\s*(scaleFreePS|multiplePeaksPS)\s*\((.*)\)\s*$", string(expr))
+    m === nothing && error("InputPowerSpectrum = $expr: scaleFreePS(n, norm) or multiplePeaksPS(n, norm, k, lnwidth) required")
+    args = Any[parse_value(q) for q in split_top(m.captures[2])]
+    m.captures[1] == "scaleFreePS" && return Float64(args[1]), Float64(args[2]), nothing
+    ks = Float64[q for q in args[3]]
+    ws = args[4] isa AbstractVector ? Float64[q for q in args[4]] : fill(Float64(args[4]), length(ks))   # :20-24
+    length(ws) == length(ks) || error("multiplePeaksPS: one width per peak (or a single number)")
+    return Float64(args[1]), Float64(args[2]), (ks, ws)
+end
+function PowerSpectrumParticles(gp, gd, p, conf)                              # :209-254 (seeded, on the device)
+    haskey(conf, "InputPowerSpectrum") || error("Requested to use PowerSpectrumParticles but did not specify InputPowerSpectrum")
+    n, _, peaks = parse_input_power_spectrum(conf["InputPowerSpectrum"])
     vfac = 0.0
     if haskey(conf, "_cosmo") && haskey(conf, "InitialRedshift")
         zi = conf["InitialRedshift"]
         vfac = dadt_from_t_internal(conf["_cosmo"], conf["StartTime"], zi) / a_from_t_internal(conf["_cosmo"], conf["StartTime"], zi, zwherea1 = zi)
     end
-    p["_ic"] = (:grf, (UInt64(get(conf, "RandomSeed", 12345)), parse(Float64, m.captures[1]),
-                       Float64(get(conf, "DisplacementRMS", 0.3 / maximum(conf["TopgridDimensions"]))), vfac)); nothing
+    seed = UInt64(get(conf, "RandomSeed", 12345))
+    rms = Float64(get(conf, "DisplacementRMS", 0.3 / maximum(conf["TopgridDimensions"])))
+    p["_ic"] = peaks === nothing ? (:grf, (seed, n, rms, vfac)) : (:grfpeaks, (seed, n, peaks[1], peaks[2], rms, vfac)); nothing
 end
 const PROBLEMS = Dict("UniformParticles" => UniformParticles, "UniformParticleWind" => UniformParticleWind,
                       "ZeldovichPancakeParticles" => ZeldovichPancakeParticles, "PowerSpectrumParticles" => PowerSpectrumParticles)
@@ -521,7 +537,13 @@ function device_for(gp, p, conf)
     ic = get(p, "_ic", nothing)
     pd = Int.(conf["ParticleDimensions"])
     if ic !== nothing && p["x"] === nothing
-        ic[1] == :grf ? init_grf!(dev, pd, ic[2]..., Float64(p["m"])) : init_pancake!(dev, pd, ic[2]..., Float64(p["m"]))
+        if ic[1] == :grf
+            init_grf!(dev, pd, ic[2]..., Float64(p["m"]))
+        elseif ic[1] == :grfpeaks
+            init_grf_peaks!(dev, pd, ic[2]..., Float64(p["m"]))
+        else
+            init_pancake!(dev, pd, ic[2]..., Float64(p["m"]))
+        end
     elseif P > 1
         # every rank holds the full host arrays (the initialisers ran on each): upload one contiguous share, then route
         lo, hi = div(rid * npart, P), div((rid + 1) * npart, P)

@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import math
 import os
+import re
 
 import numpy as np
 
@@ -223,31 +224,48 @@ def SyntheticZeldovichParticles(gp, gd, p, conf):
                                   vfac=float(conf.get("SyntheticVfac", 0.0))))
 
 
-def _parse_scale_free_ps(expr):
-    """InputPowerSpectrum = scaleFreePS(n, norm)  (src/InputPowerSpectra.jl:1-4, :26) -> (n, norm).  multiplePeaksPS is
-    not provided (the shipped run/PM conf names it, but its ProblemDefinition does not parse in the reference)."""
-    import re
-    m = re.match(r"^\s*scaleFreePS\(\s*([-+0-9.eE]+)\s*,\s*([-+0-9.eE]+)\s*\)\s*$", str(expr))
+def _parse_input_power_spectrum(expr):
+    """InputPowerSpectrum = scaleFreePS(n, norm) | multiplePeaksPS(n, norm, [k1, k2, ...], lnwidth | [w1, w2, ...])
+    (src/InputPowerSpectra.jl:1-24; doc/InputPowerSpectra.md) -> (n, norm, peaks) with peaks = None or (k_list, w_list);
+    a scalar width applies to every peak (:20-24)."""
+    from .conf import parse_value, _split_top
+    m = re.match(r"^\s*(scaleFreePS|multiplePeaksPS)\s*\((.*)\)\s*$", str(expr))
     if not m:
-        raise NotImplementedError(f"InputPowerSpectrum = {expr!r}: only scaleFreePS(n, norm) is provided")
-    return float(m.group(1)), float(m.group(2))
+        raise NotImplementedError(f"InputPowerSpectrum = {expr!r}: scaleFreePS(n, norm) and multiplePeaksPS(n, norm, k, lnwidth) are provided")
+    args = [parse_value(a) for a in _split_top(m.group(2))]
+    num = (int, float)
+    if m.group(1) == "scaleFreePS":
+        if len(args) != 2 or not all(isinstance(a, num) for a in args):
+            raise ValueError(f"scaleFreePS(n, norm) takes two numbers: {expr!r}")
+        return float(args[0]), float(args[1]), None
+    if len(args) != 4 or not all(isinstance(a, num) for a in args[:2]) or not isinstance(args[2], list):
+        raise ValueError(f"multiplePeaksPS(n, norm, [k...], lnwidth) expected: {expr!r}")
+    ks = [float(q) for q in args[2]]
+    ws = [float(q) for q in args[3]] if isinstance(args[3], list) else [float(args[3])] * len(ks)
+    if len(ws) != len(ks) or not ks:
+        raise ValueError(f"multiplePeaksPS: one width per peak (or a single number): {expr!r}")
+    return float(args[0]), float(args[1]), (ks, ws)
 
 
 def PowerSpectrumParticles(gp, gd, p, conf):
-    """:209-254 with InputPowerSpectrum = scaleFreePS(n, norm), generated on the device by nnpm_init_grf -- seeded
-    (conf RandomSeed, default 12345), rescaled to a per-component RMS displacement of DisplacementRMS (box units,
-    default 0.3 cell) and with growing-mode velocities v = (adot/a) psi when a cosmology is set: the reference's own
-    function does not parse (:246), draws unseeded randn and leaves the velocities unimplemented (:251)."""
+    """:209-254 with InputPowerSpectrum = scaleFreePS(n, norm) or multiplePeaksPS(n, norm, k, lnwidth), generated on the
+    device by nnpm_init_grf / nnpm_init_grf_peaks -- seeded (conf RandomSeed, default 12345), rescaled to a per-component
+    RMS displacement of DisplacementRMS (box units, default 0.3 cell) and with growing-mode velocities v = (adot/a) psi
+    when a cosmology is set: the reference's own function does not parse (:246), draws unseeded randn and leaves the
+    velocities unimplemented (:251)."""
     if "InputPowerSpectrum" not in conf:
         raise KeyError("Requested to use PowerSpectrumParticles but did not specify InputPowerSpectrum")   # :212-216
-    n, _norm = _parse_scale_free_ps(conf["InputPowerSpectrum"])
+    n, _norm, peaks = _parse_input_power_spectrum(conf["InputPowerSpectrum"])
     vfac = 0.0
     if "_cosmo" in conf and "InitialRedshift" in conf:
         zi = conf["InitialRedshift"]
         a = _cos.a_from_t_internal(conf["_cosmo"], conf["StartTime"], zi, zwherea1=zi)
         vfac = _cos.dadt_from_t_internal(conf["_cosmo"], conf["StartTime"], zi) / a
-    p["_ic"] = ("grf", dict(seed=int(conf.get("RandomSeed", 12345)), ps_index=n,
-                            disp_rms=float(conf.get("DisplacementRMS", 0.3 / max(conf["TopgridDimensions"]))), vfac=vfac))
+    kw = dict(seed=int(conf.get("RandomSeed", 12345)), ps_index=n,
+              disp_rms=float(conf.get("DisplacementRMS", 0.3 / max(conf["TopgridDimensions"]))), vfac=vfac)
+    if peaks is not None:
+        kw["peaks"] = peaks
+    p["_ic"] = ("grf", kw)
 
 
 PROBLEMS = {f.__name__: f for f in (UniformParticles, UniformParticleWind, ZeldovichPancakeParticles,

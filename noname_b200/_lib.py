@@ -26,7 +26,7 @@ SYMBOLS = (
     "nnpm_version", "nnpm_create", "nnpm_destroy", "nnpm_last_error", "nnpm_comm_unique_id",
     "nnpm_comm_init", "nnpm_host_alloc", "nnpm_host_free", "nnpm_upload_particles",
     "nnpm_redistribute", "nnpm_local_count", "nnpm_download_particles", "nnpm_init_synthetic", "nnpm_init_grf",
-    "nnpm_init_pancake",
+    "nnpm_init_grf_peaks", "nnpm_init_pancake",
     "nnpm_sort", "nnpm_make_periodic", "nnpm_deposit", "nnpm_solve", "nnpm_accel", "nnpm_interp",
     "nnpm_drift", "nnpm_kick", "nnpm_kick_comoving", "nnpm_get_field", "nnpm_set_field",
     "nnpm_step_static", "nnpm_step_comoving", "nnpm_reduce_stats", "nnpm_device_bytes",
@@ -95,6 +95,8 @@ def load():
         "nnpm_init_synthetic": ([vp, C.c_int, C.POINTER(i64), C.c_uint64, C.c_int32, C.c_int32,
                                  C.c_double, C.c_double, C.c_double], C.c_int),
         "nnpm_init_grf": ([vp, C.POINTER(i64), C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double], C.c_int),
+        "nnpm_init_grf_peaks": ([vp, C.POINTER(i64), C.c_uint64, C.c_double, C.c_int32, C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double], C.c_int),
         "nnpm_init_pancake": ([vp, C.POINTER(i64), C.c_double, C.c_double, C.c_double], C.c_int),
         "nnpm_sort": ([vp], C.c_int),
         "nnpm_make_periodic": ([vp], C.c_int),

@@ -1,6 +1,8 @@
 // nnpm_ic.cuh -- device-side initial conditions that need the FFT machinery or the cosmology scalars:
 //   nnpm_init_grf      PowerSpectrumParticles (src/ParticleMesh.jl:209-254) + scaleFreePS (src/InputPowerSpectra.jl:26):
 //                      seeded Gaussian-random-field Zel'dovich displacements on the particle lattice
+//   nnpm_init_grf_peaks  the same with multiplePeaksPS (src/InputPowerSpectra.jl:6-24, :28-36), the spectrum the shipped
+//                      run/PM/particle_mesh.conf names
 //   nnpm_init_pancake  ZeldovichPancakeParticles (src/ParticleMesh.jl:177-198)
 // Included by nnpm.cu after the transform code (uses fft_inverse and the slab transposes).
 #pragma once
@@ -11,16 +13,29 @@ __device__ __forceinline__ double ic_kf(int idx, int N) {
   return __ddiv_rn(__dmul_rn(6.283185307179586, (double)w), (double)N);
 }
 
+// multiplePeaksPS: P(k) = k^n where |k - k_p| / k < lnwidth_p / 2 for some peak p, 0 elsewhere (InputPowerSpectra.jl:28-36)
+struct PeakTab {
+  int n;
+  double k[NNPM_MAX_PEAKS], w[NNPM_MAX_PEAKS];
+};
+
 // complex amplitude (ak - i bk)/2 of mode (i, j, k), ak = sqrt(P(|k|)) g1 / k^2, bk likewise with g2 (:230-236);
 // (g1, g2) = Box-Muller of two uniforms drawn from mix64 keyed by (seed, linear index of the mode in the half spectrum)
+template <bool PEAKS>
 __device__ __forceinline__ double2 ic_mode_amp(int i, int j, int k, int N1, int N2, int N3, u64 seed, double ps_index,
-                                               double& kx, double& ky, double& kz) {
+                                               const PeakTab& pk, double& kx, double& ky, double& kz) {
   kx = ic_kf(i, N1);
   ky = ic_kf(j, N2);
   kz = N3 > 1 ? ic_kf(k, N3) : 0.0;
   const double k2 = kx * kx + ky * ky + kz * kz;
   if (k2 == 0.0) return make_double2(0.0, 0.0);
   const double ka = sqrt(k2);
+  if (PEAKS) {
+    bool inside = false;
+    for (int q = 0; q < pk.n; q++)
+      if (__ddiv_rn(fabs(__dsub_rn(ka, pk.k[q])), ka) < __ddiv_rn(pk.w[q], 2.0)) inside = true;
+    if (!inside) return make_double2(0.0, 0.0);
+  }
   const double psv = sqrt(pow(ka, ps_index));
   const u64 lin = (u64)i + (u64)(N1 / 2 + 1) * ((u64)j + (u64)N2 * (u64)k);
   const u64 h = mix64(seed ^ mix64(lin));
@@ -32,7 +47,9 @@ __device__ __forceinline__ double2 ic_mode_amp(int i, int j, int k, int N1, int 
 
 // component D of the displacement spectrum at (i, j, k): amp * k_D, with the planes i = 0 and i = N1/2 made Hermitian
 // ((j, k) whose mirror (-j, -k) has the smaller linear index takes the conjugate of the mirror; self-mirrored bins are real)
-__device__ __forceinline__ double2 ic_mode_value(int D, int i, int j, int k, int N1, int N2, int N3, u64 seed, double ps_index) {
+template <bool PEAKS>
+__device__ __forceinline__ double2 ic_mode_value(int D, int i, int j, int k, int N1, int N2, int N3, u64 seed, double ps_index,
+                                                 const PeakTab& pk) {
   bool conj = false, real_only = false;
   if (i == 0 || 2 * i == N1) {
     const int jm = (N2 - j) % N2, km = (N3 - k) % N3;
@@ -41,7 +58,7 @@ __device__ __forceinline__ double2 ic_mode_value(int D, int i, int j, int k, int
     else if (b == a) real_only = true;
   }
   double kf[3];
-  const double2 amp = ic_mode_amp(i, j, k, N1, N2, N3, seed, ps_index, kf[0], kf[1], kf[2]);
+  const double2 amp = ic_mode_amp<PEAKS>(i, j, k, N1, N2, N3, seed, ps_index, pk, kf[0], kf[1], kf[2]);
   double2 c = make_double2(amp.x * kf[D], amp.y * kf[D]);
   if (conj) c.y = -c.y;
   if (real_only) c.y = 0.0;
@@ -49,13 +66,14 @@ __device__ __forceinline__ double2 ic_mode_value(int D, int i, int j, int k, int
 }
 
 // fill the (slab-transposed) half spectrum T[k][jl][ic], jl = j - j0
+template <bool PEAKS>
 __global__ void k_ic_grf_fill(double2* __restrict__ T, int D, int icn, int njl, int j0, int N1, int N2, int N3, u64 seed,
-                              double ps_index) {
+                              double ps_index, const __grid_constant__ PeakTab pk) {
   const int ic = blockIdx.x * blockDim.x + threadIdx.x;
   const int jl = blockIdx.y;
   if (ic >= icn) return;
   for (int k = blockIdx.z; k < N3; k += gridDim.z)
-    T[ic + (i64)icn * (jl + (i64)njl * k)] = ic_mode_value(D, ic, j0 + jl, k, N1, N2, N3, seed, ps_index);
+    T[ic + (i64)icn * (jl + (i64)njl * k)] = ic_mode_value<PEAKS>(D, ic, j0 + jl, k, N1, N2, N3, seed, ps_index, pk);
 }
 
 // psi_D at this rank's lattice sites (the transformed mesh, unnormalised) -> dst[t]; the squares are summed in a fixed
@@ -149,9 +167,8 @@ extern "C" int nnpm_init_pancake(nnpm_ctx* ctx, const int64_t pdims[3], double x
   return ic_finish(ctx, per, m);
 }
 
-extern "C" int nnpm_init_grf(nnpm_ctx* ctx, const int64_t pdims[3], uint64_t seed, double ps_index, double disp_rms,
-                             double vfac, double m) {
-  if (!ctx || !pdims) return NNPM_ERR_ARG;
+static int init_grf_impl(nnpm_ctx* ctx, const int64_t pdims[3], uint64_t seed, double ps_index, const PeakTab& pk,
+                         double disp_rms, double vfac, double m) {
   CK(cudaSetDevice(ctx->cfg.device));
   const i64 P1 = pdims[0], P2 = pdims[1], P3 = ctx->R == 3 ? pdims[2] : 1;
   if (P1 * P2 * P3 != ctx->cfg.npart_total) return fail(ctx, NNPM_ERR_ARG, "prod(pdims) != npart_total");
@@ -188,8 +205,12 @@ extern "C" int nnpm_init_grf(nnpm_ctx* ctx, const int64_t pdims[3], uint64_t see
   double2* T = ic->P > 1 ? (double2*)ic->meshT : (double2*)(ic->mesh + g.plane * g.glo);
   for (int d = 0; d < ctx->R; d++) {
     dim3 grid(nblk(ic->icn, 128), (unsigned)ic->njl, (unsigned)(P3 < 64 ? P3 : 64));
-    k_ic_grf_fill<<<grid, 128, 0, ctx->st>>>(T, d, (int)ic->icn, (int)ic->njl, (int)(ic->njl * ic->r), (int)P1, (int)P2, (int)P3,
-                                             (u64)seed, ps_index);
+    if (pk.n > 0)
+      k_ic_grf_fill<true><<<grid, 128, 0, ctx->st>>>(T, d, (int)ic->icn, (int)ic->njl, (int)(ic->njl * ic->r), (int)P1, (int)P2,
+                                                     (int)P3, (u64)seed, ps_index, pk);
+    else
+      k_ic_grf_fill<false><<<grid, 128, 0, ctx->st>>>(T, d, (int)ic->icn, (int)ic->njl, (int)(ic->njl * ic->r), (int)P1, (int)P2,
+                                                      (int)P3, (u64)seed, ps_index, pk);
     LAUNCHED(ctx);
     if (cudaGetLastError() != cudaSuccess) return done(fail(ctx, NNPM_ERR_CUDA, "k_ic_grf_fill launch failed"));
     CKI(fft_inverse(ic, true, nullptr, false));
@@ -219,4 +240,27 @@ extern "C" int nnpm_init_grf(nnpm_ctx* ctx, const int64_t pdims[3], uint64_t see
   int rc = done(cudaGetLastError() == cudaSuccess ? NNPM_OK : fail(ctx, NNPM_ERR_CUDA, "random-field ICs: apply kernel failed"));
   if (rc != NNPM_OK) return rc;
   return ic_finish(ctx, per, m);
+}
+
+extern "C" int nnpm_init_grf(nnpm_ctx* ctx, const int64_t pdims[3], uint64_t seed, double ps_index, double disp_rms,
+                             double vfac, double m) {
+  if (!ctx || !pdims) return NNPM_ERR_ARG;
+  PeakTab pk;
+  memset(&pk, 0, sizeof pk);
+  return init_grf_impl(ctx, pdims, seed, ps_index, pk, disp_rms, vfac, m);
+}
+
+extern "C" int nnpm_init_grf_peaks(nnpm_ctx* ctx, const int64_t pdims[3], uint64_t seed, double ps_index, int32_t npeaks,
+                                   const double* kpeak, const double* lnwidth, double disp_rms, double vfac, double m) {
+  if (!ctx || !pdims || !kpeak || !lnwidth) return NNPM_ERR_ARG;
+  if (npeaks < 1 || npeaks > NNPM_MAX_PEAKS) return fail(ctx, NNPM_ERR_ARG, "npeaks must be 1 .. %d", NNPM_MAX_PEAKS);
+  PeakTab pk;
+  memset(&pk, 0, sizeof pk);
+  pk.n = npeaks;
+  for (int q = 0; q < npeaks; q++) {
+    if (!(kpeak[q] > 0.0) || !(lnwidth[q] > 0.0)) return fail(ctx, NNPM_ERR_ARG, "peak %d: k and lnwidth must be positive", q);
+    pk.k[q] = kpeak[q];
+    pk.w[q] = lnwidth[q];
+  }
+  return init_grf_impl(ctx, pdims, seed, ps_index, pk, disp_rms, vfac, m);
 }

@@ -150,11 +150,20 @@ class DevicePM:
         self._ck(self._L.nnpm_init_synthetic(self._h, k, pd, int(seed), int(nmodes), int(kmax),
                                              float(disp_rms), float(vfac), self.m))
 
-    def init_grf(self, pdims, seed=12345, ps_index=-1.0, disp_rms=0.0, vfac=0.0, m=1.0):
-        """PowerSpectrumParticles + scaleFreePS(ps_index, .) on the device, seeded (ParticleMesh.jl:209-254)."""
+    def init_grf(self, pdims, seed=12345, ps_index=-1.0, disp_rms=0.0, vfac=0.0, m=1.0, peaks=None):
+        """PowerSpectrumParticles on the device, seeded (ParticleMesh.jl:209-254): scaleFreePS(ps_index, .), or -- with
+        peaks = (k_list, lnwidth_list) -- multiplePeaksPS(ps_index, ., k_list, lnwidth_list) (InputPowerSpectra.jl:6-36)."""
         pd = (C.c_int64 * 3)(*[int(p) for p in pdims])
         self.m = float(m)
-        self._ck(self._L.nnpm_init_grf(self._h, pd, int(seed), float(ps_index), float(disp_rms), float(vfac), self.m))
+        if peaks is None:
+            self._ck(self._L.nnpm_init_grf(self._h, pd, int(seed), float(ps_index), float(disp_rms), float(vfac), self.m))
+            return
+        ks, ws = [float(q) for q in peaks[0]], [float(q) for q in peaks[1]]
+        if len(ks) != len(ws):
+            raise ValueError("peaks = (k_list, lnwidth_list) of equal lengths")
+        n = len(ks)
+        self._ck(self._L.nnpm_init_grf_peaks(self._h, pd, int(seed), float(ps_index), n, (C.c_double * max(n, 1))(*ks),
+                                             (C.c_double * max(n, 1))(*ws), float(disp_rms), float(vfac), self.m))
 
     def init_pancake(self, pdims, xamp, vamp, m=1.0):
         """ZeldovichPancakeParticles on the device (ParticleMesh.jl:177-198): xamp = 2/5 A a, vamp = 2/5 A adot."""

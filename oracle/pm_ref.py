@@ -484,7 +484,7 @@ def synthetic_clustered(pdims, rank, seed, nblobs, sigma, vdisp):
     return x, v
 
 
-def grf_spectrum(pdims, comp, seed, ps_index):
+def grf_spectrum(pdims, comp, seed, ps_index, peaks=None):
     """Half spectrum c_d[k, j, i] (i <= P1/2) of displacement component `comp`, PowerSpectrumParticles :224-240 with
     scaleFreePS P(k) = k^n (InputPowerSpectra.jl:26; the norm drops out of the rescaled field): amplitude
     sqrt(P(|k|)) (g1 - i g2)/2 / k^2 * k_d, k in rad/cell via fftfreq (:202-206), k = 0 skipped.  Deviations SURVEY.md
@@ -508,7 +508,14 @@ def grf_spectrum(pdims, comp, seed, ps_index):
     k2 = kk[0] * kk[0] + kk[1] * kk[1] + kk[2] * kk[2]
     nz = k2 > 0.0
     k2s = np.where(nz, k2, 1.0)
-    psv = np.sqrt(np.power(np.sqrt(k2s), ps_index))
+    ka = np.sqrt(k2s)
+    psv = np.sqrt(np.power(ka, ps_index))
+    if peaks is not None:
+        # multiplePeaksPS, InputPowerSpectra.jl:28-36: P = P_scalefree(k) if |k - k_p| / k < lnwidth_p / 2 for some p, else 0
+        inside = np.zeros(ka.shape, dtype=bool)
+        for kp, w in zip(*peaks):
+            inside |= np.abs(ka - float(kp)) / ka < float(w) / 2
+        nz = nz & inside
     with np.errstate(over="ignore"):
         lin = I.astype(np.uint64) + np.uint64(icn) * (Jc.astype(np.uint64) + np.uint64(P2) * Kc.astype(np.uint64))
         h = _mix64(np.uint64(seed) ^ _mix64(lin))
@@ -522,7 +529,7 @@ def grf_spectrum(pdims, comp, seed, ps_index):
     return re + 1j * im
 
 
-def synthetic_grf(pdims, rank, seed, ps_index, disp_rms, vfac):
+def synthetic_grf(pdims, rank, seed, ps_index, disp_rms, vfac, peaks=None):
     """Seeded Gaussian-random-field Zel'dovich ICs (checker of nnpm_init_grf): x = wrap(q + s psi), v = vfac s psi with
     psi_d = irfft(c_d) on the particle lattice (:241) and s rescaling psi to a per-component RMS of disp_rms."""
     P1, P2, P3 = (int(q) for q in pdims)
@@ -531,7 +538,7 @@ def synthetic_grf(pdims, rank, seed, ps_index, disp_rms, vfac):
     q = initialize_particles_uniform(pdims, rank)
     psi = np.empty_like(q)
     for d in range(rank):
-        c = grf_spectrum((P1, P2, P3), d, seed, ps_index)
+        c = grf_spectrum((P1, P2, P3), d, seed, ps_index, peaks)
         f = sfft.irfftn(c, s=(P3, P2, P1), axes=(0, 1, 2)) * float(P1 * P2 * P3)   # unnormalised, like the device
         psi[:, d] = f.reshape(-1)
     rms = math.sqrt(float(np.sum(psi * psi)) / (psi.shape[0] * rank))

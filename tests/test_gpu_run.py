@@ -190,6 +190,51 @@ def test_grf_initial_conditions_match_oracle(lib_built, O, pdims, dims, rank):
         assert st.n_halo_violations == 0 and np.isfinite(st.max_abs_v)
 
 
+PM_PEAKS = ([0.1, 1.0, 10.0], [1.0, 1.0, 1.0])      # multiplePeaksPS(-1, 1, [0.1, 1, 10], 1.) of run/PM/particle_mesh.conf
+
+
+@pytest.mark.parametrize("pdims,dims,rank", [((100, 100, 1), (1000, 1000, 1), 2), ((128, 64, 64), (128, 64, 64), 3),
+                                             ((32, 32, 32), (32, 32, 32), 3)])
+def test_grf_multiple_peaks_initial_conditions_match_oracle(lib_built, O, pdims, dims, rank):
+    """nnpm_init_grf_peaks (PowerSpectrumParticles + multiplePeaksPS, src/InputPowerSpectra.jl:6-36) == oracle twin: the
+    run/PM shape (100^2 lattice on a 1000^2 mesh: library transforms on a temporary lattice context), the own x / y / z
+    passes, and a small cube; a spectrum with no lattice mode inside its windows leaves the lattice untouched."""
+    from noname_b200 import DevicePM
+    npart = int(np.prod(pdims))
+    xr, vr = O.synthetic_grf(pdims, rank, 777, -1.0, 0.3 / max(dims), 0.7, peaks=PM_PEAKS)
+    xf, _ = O.synthetic_grf(pdims, rank, 777, -1.0, 0.3 / max(dims), 0.7)
+    assert float(np.max(np.abs(xr - xf))) > 1e-6            # the windows do change the field
+    with DevicePM(dims, npart, rank=rank) as dev:
+        dev.init_grf(pdims, seed=777, ps_index=-1.0, disp_rms=0.3 / max(dims), vfac=0.7, m=1.0, peaks=PM_PEAKS)
+        xg, vg = dev.download()
+        d = np.abs(xg - xr)
+        d = np.minimum(d, 1.0 - d)
+        assert float(d.max()) < 1e-13
+        assert nlinf(vg, vr) < 1e-11
+        dev.init_grf(pdims, seed=777, ps_index=-1.0, disp_rms=0.3 / max(dims), vfac=0.7, m=1.0, peaks=([50.0], [0.01]))
+        x0, v0 = dev.download()
+        assert np.array_equal(x0, O.initialize_particles_uniform(pdims, rank)) and not v0.any()
+        with pytest.raises(Exception):
+            dev.init_grf(pdims, peaks=([1.0] * 9, [1.0] * 9))      # more than NNPM_MAX_PEAKS
+
+
+def test_run_noname_shipped_pm_conf_verbatim(lib_built, O, tmp_path):
+    """BASELINE config 1 with NOTHING overridden but the output paths: run/PM/particle_mesh.conf as shipped, including its
+    InputPowerSpectrum = multiplePeaksPS(-1, 1, [0.1, 1, 10], 1.), end to end against the oracle's evolvePM."""
+    from noname_b200 import run_noname, NoName
+    over = {"OutputDirectory": str(tmp_path / "out"), "RestartFileName": str(tmp_path / "restart.bin"), "OutputFormat": "npz"}
+    gp, gd, p = run_noname(_conf_file(tmp_path, SHIPPED_PM), overrides=over)
+    c = NoName.conf
+    xr, vr = O.synthetic_grf((100, 100, 1), 2, 12345, -1.0, 0.3 / 1000, 0.0, peaks=PM_PEAKS)
+    m = 1000.0 * 1000.0 / 1e4
+    rc = dict(StartTime=0.0, StopTime=1.0, StartCycle=0, StopCycle=1000000, InitialDt=1e-7, CourantFactor=0.2, MaximumDt=0.1)
+    t, cyc, f = O.evolvePM(xr, vr, m, (1000, 1000, 1), rc)
+    assert c["CurrentCycle"] == cyc and abs(c["CurrentTime"] - t) <= 1e-12
+    assert float(np.max(np.abs(p["x"] - xr))) < 1e-11 and nlinf(p["v"], vr) < 1e-9
+    assert nlinf(gd[1].d["Φ"], f.phi) < 1e-10 and nlinf(gd[1].d["ρD"], f.rho) < 1e-10
+    assert len(_outputs(str(tmp_path / "out"))) >= 1
+
+
 def test_pancake_device_matches_oracle(lib_built, O):
     from noname_b200 import DevicePM
     oc = O.Cosmo(h=1.0, OmegaM=1.0, OmegaR=0.0)

@@ -160,9 +160,13 @@ def test_unknown_or_broken_problem_definitions_raise(tmp_path):
     c = cf.load_conf(_write(tmp_path, "TopgridDimensions=[8,8,1]\nParticleDimensions=[8,8,1]\nProblemDefinition = PowerSpectrumParticles\n"), user_default=False)
     with pytest.raises(KeyError):                 # :212-216: InputPowerSpectrum is required
         PM.InitializeParticleSimulation({}, {}, {}, c)
-    c["InputPowerSpectrum"] = "multiplePeaksPS(-1, 1, [0.1, 1, 10], 1.)"     # as shipped in run/PM: not provided
+    c["InputPowerSpectrum"] = "tophatPS(1, 2)"                               # not a spectrum of InputPowerSpectra.jl
     with pytest.raises(NotImplementedError):
         PM.InitializeParticleSimulation({}, {}, {}, c)
+    c["InputPowerSpectrum"] = "multiplePeaksPS(-1, 1, [0.1, 1, 10], [1., 2.])"   # widths must match the peaks (:20-24)
+    with pytest.raises(ValueError):
+        PM.InitializeParticleSimulation({}, {}, {}, c)
+    c["InputPowerSpectrum"] = "scaleFreePS(-1, .3)"
     c["ProblemDefinition"] = "Nope"
     with pytest.raises(KeyError):
         PM.InitializeParticleSimulation({}, {}, {}, c)
@@ -187,6 +191,44 @@ def test_power_spectrum_particles_are_generated_on_the_device(tmp_path):
     ad = O.dadt_from_t_internal(oc, c["StartTime"], 400)
     assert kind == "grf" and kw["ps_index"] == -1.0 and kw["seed"] == 12345
     assert kw["disp_rms"] == pytest.approx(0.3 / 64) and kw["vfac"] == pytest.approx(ad / a, rel=1e-9)
+
+
+def test_multiple_peaks_spectrum_as_shipped_in_run_pm(tmp_path):
+    """run/PM/particle_mesh.conf names InputPowerSpectrum = multiplePeaksPS(-1, 1, [0.1, 1, 10], 1.) (src/InputPowerSpectra.jl:
+    6-24): parsed into (n, norm, peaks); a scalar width applies to every peak; the request goes to nnpm_init_grf_peaks."""
+    assert PM._parse_input_power_spectrum("multiplePeaksPS(-1, 1, [0.1, 1, 10], 1.)") == (-1.0, 1.0, ([0.1, 1.0, 10.0], [1.0, 1.0, 1.0]))
+    assert PM._parse_input_power_spectrum(" multiplePeaksPS(-2,3.5,[1, 10, 30],[0.1, 0.2, 0.3]) ") == (-2.0, 3.5, ([1.0, 10.0, 30.0], [0.1, 0.2, 0.3]))
+    assert PM._parse_input_power_spectrum("scaleFreePS(-1, .3)") == (-1.0, 0.3, None)
+    c = cf.load_conf(_write(tmp_path, "TopgridDimensions=[16,16,1]\nParticleDimensions=[8,8,1]\nProblemDefinition = PowerSpectrumParticles\n"
+                                      "InputPowerSpectrum = multiplePeaksPS(-1, 1, [0.1, 1, 10], 1.)\n"), user_default=False)
+    gp, gd, p = {}, {}, {}
+    PM.InitializeParticleSimulation(gp, gd, p, c)
+    assert p["x"] is None and p["_ic"][0] == "grf" and p["_ic"][1]["peaks"] == ([0.1, 1.0, 10.0], [1.0, 1.0, 1.0])
+    assert p["_ic"][1]["vfac"] == 0.0 and p["_ic"][1]["disp_rms"] == pytest.approx(0.3 / 16)
+
+
+def test_oracle_multiple_peaks_spectrum_is_zero_outside_the_windows():
+    """checker of nnpm_init_grf_peaks: P = k^n where |k - k_p| / k < w_p / 2 (InputPowerSpectra.jl:28-36), else 0 -- and
+    identical to the scale-free field wherever it is non-zero (same seeded draws per mode)"""
+    pd = (32, 24, 1)
+    peaks = ([0.1, 1.0, 10.0], [1.0, 1.0, 1.0])
+    free = O.grf_spectrum(pd, 0, 99, -1.0)
+    pk = O.grf_spectrum(pd, 0, 99, -1.0, peaks)
+    K, J, I = np.meshgrid(np.arange(1), np.arange(24), np.arange(17), indexing="ij")
+    kx = 2 * math.pi * I / 32
+    ky = 2 * math.pi * np.where(J > 12, J - 24, J) / 24
+    ka = np.sqrt(kx * kx + ky * ky)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        inside = ((np.abs(ka - 0.1) / ka < 0.5) | (np.abs(ka - 1.0) / ka < 0.5) | (np.abs(ka - 10.0) / ka < 0.5)) & (ka > 0)
+    assert inside.any() and (~inside).any()
+    assert np.all(pk[~inside] == 0) and np.array_equal(pk[inside], free[inside])
+    x, v = O.synthetic_grf(pd, 2, 99, -1.0, 0.01, 0.5, peaks=peaks)
+    q = O.initialize_particles_uniform(pd, 2)
+    d = x - q
+    d -= np.rint(d)
+    assert np.sqrt(np.mean(d * d)) == pytest.approx(0.01, rel=1e-12) and np.allclose(v, 0.5 * d, atol=1e-15)
+    x0, _ = O.synthetic_grf(pd, 2, 99, -1.0, 0.01, 0.5, peaks=([10.0], [0.1]))      # no lattice mode inside: zero displacement
+    assert np.array_equal(x0, q)
 
 
 def test_device_initial_conditions_key_defers_pancake_and_lattice(tmp_path):
