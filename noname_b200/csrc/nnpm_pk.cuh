@@ -85,7 +85,7 @@ extern "C" int nnpm_power_spectrum(nnpm_ctx* ctx, double* karray_out, double* po
   CKR(do_deposit(ctx, false, 0.0));
   double* own = ctx->mesh + g.plane * g.glo;
   const i64 ncl = g.N1 * g.N2 * g.nzl;
-  k_mesh_sum<<<148 * 4, 256, 0, ctx->st>>>(own, g, d_sum);
+  k_mesh_sum<<<ctx->nsm * 4, 256, 0, ctx->st>>>(own, g, d_sum);
   LAUNCHED(ctx);
   KCHECK();
   double sum = 0.0;
@@ -99,7 +99,7 @@ extern "C" int nnpm_power_spectrum(nnpm_ctx* ctx, double* karray_out, double* po
   CKR(fft_forward(ctx, &T, true, nullptr, false));
   const double ncell = (double)g.N1 * (double)g.N2 * (double)g.N3;
   const double fac = 1.0 / (ncell * ncell);  // prod(box)/prod(dims)^2 with box = 1  :77
-  k_pk_bin<<<148 * 2, 256, (size_t)2 * lenk * 8, ctx->st>>>(T, ctx->icn, ctx->njl, ctx->njl * ctx->r, g, dk, lenk, fac,
+  k_pk_bin<<<ctx->nsm * 2, 256, (size_t)2 * lenk * 8, ctx->st>>>(T, ctx->icn, ctx->njl, ctx->njl * ctx->r, g, dk, lenk, fac,
                                                             d_power, d_counts);
   LAUNCHED(ctx);
   KCHECK();
