@@ -63,7 +63,7 @@ typedef struct {
   int32_t struct_size;      /* = sizeof(nnpm_config), for ABI checks */
   int32_t rank;             /* particle dimensionality: 2 or 3 (ParticleMesh.jl:105) */
   int64_t ngrid[3];         /* TopgridDimensions N1,N2,N3 (N3 = 1 when rank == 2) */
-  int64_t npart_total;      /* prod(ParticleDimensions): particles over all ranks */
+  int64_t npart_total;      /* prod(ParticleDimensions): particles over all ranks; < 2^32 (original-order ids are uint32) */
   int64_t part_capacity;    /* per-rank particle capacity; 0 = npart_total/nranks * 1.25 + 4096 */
   int32_t deposit;          /* NNPM_INTERP_* */
   int32_t backinterp;       /* NNPM_INTERP_* */
