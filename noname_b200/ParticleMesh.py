@@ -343,13 +343,15 @@ def _sync_host(dev, gd, p, fields=True):
     after which an output is due.  If no kept density exists (state uploaded but never stepped) the particles are
     deposited where they are.  With NGPUs > 1 every rank receives the complete arrays."""
     n = dev.local_count
-    if dev.nranks == 1:
+    multi = dev.nranks > 1
+    if multi:
+        from . import slab
+    if not multi:
         if p.get("x") is None or p["x"].shape[0] != n:
             p["x"] = np.empty((n, dev.rank))
             p["v"] = np.empty((n, dev.rank))
         dev.download(p["x"], p["v"])
     else:
-        from . import slab
         xl, vl, ids = dev.download(ids=True)
         ids = slab.allgather_rows(ids)
         xs, vs = slab.allgather_rows(xl), slab.allgather_rows(vl)
@@ -363,10 +365,10 @@ def _sync_host(dev, gd, p, fields=True):
                 a = dev.get_field(which)
             except _lib.NNPMError:
                 return False
-            gd[1].d[key][...] = a if dev.nranks == 1 else __import__("noname_b200.slab", fromlist=["x"]).allgather_slabs(a)
+            gd[1].d[key][...] = slab.allgather_slabs(a) if multi else a
             return True
         fetch("phi", "Φ")
-        if not fetch("rho", "ρD") and n >= 0:
+        if not fetch("rho", "ρD"):
             dev.deposit()           # overwrites the mesh: phi was fetched first
             fetch("rho", "ρD")
 
