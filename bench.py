@@ -232,7 +232,9 @@ def main():
     ap.add_argument("--mesh", type=int, default=1024, help="mesh cells per dimension")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=192, help="n of the n^3/n^3 CPU-baseline sample (0 = skip)")
-    ap.add_argument("--cpu-threads", type=int, default=16, help="--impl reference: host threads of the C restatement (capped by the cores available)")
+    ap.add_argument("--cpu-threads", type=int, default=16, help="--impl reference: host threads of the C restatement (capped by the cores available).  16: in round 1 more threads "
+                         "were slower; the deposit and the reductions have since been made to scale (oracle/pm_ref_c.py), "
+                         "not re-measured beyond 16")
     ap.add_argument("--sort-every", type=int, default=16,
                     help="counting-sort cadence in steps; the default K = 16 timed steps contain exactly one sort")
     ap.add_argument("--deposit-mode", default="atomic")

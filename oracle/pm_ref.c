@@ -13,7 +13,12 @@
  * Every function is serial, as the reference is.  Mesh loops take a [k0,k1) plane range and
  * particle loops take a pointer + count, so the Python driver can (for the all-cores arm of
  * bench.py --impl reference only) run disjoint chunks on a thread pool; libgomp is not in
- * this image.  Threaded deposit uses one private rho per thread, summed afterwards.
+ * this image.  The threaded 3-D CIC deposit bins the particle indices by the z-slab that owns
+ * their cell (pmref_slab_count / pmref_slab_fill, stable), then every thread scatters its own
+ * list into its own planes and one private ghost plane (pmref_cicdensity_slab): no atomics, no
+ * per-thread copy of rho, and the summation order of every cell off a slab boundary is the
+ * serial one.  2-D uses compare-and-swap adds (pmref_cicdensity_atomic); the threaded NGP
+ * deposit keeps one private rho per thread.
  */
 #include <math.h>
 #include <stdint.h>
@@ -75,6 +80,96 @@ void pmref_cicdensity(double *rho, const double *x, double m, i64 npart, int ran
   }
 }
 
+/* threads > 1 only: the same scatter with atomic adds into a rho shared by all threads */
+static inline void atomic_add_f64(double *p, double v) {
+  uint64_t *q = (uint64_t *)p;
+  uint64_t old = __atomic_load_n(q, __ATOMIC_RELAXED), neu;
+  do {
+    double d;
+    __builtin_memcpy(&d, &old, 8);
+    d += v;
+    __builtin_memcpy(&neu, &d, 8);
+  } while (!__atomic_compare_exchange_n(q, &old, neu, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
+void pmref_cicdensity_atomic(double *rho, const double *x, double m, i64 npart, int rank, i64 n1, i64 n2,
+                             i64 n3) {
+  if (rank == 2) {
+    for (i64 n = 0; n < npart; n++) {
+      i64 i, ip, j, jp;
+      double dx, dy;
+      cell(x[0 + 2 * n], n1, &i, &ip, &dx);
+      cell(x[1 + 2 * n], n2, &j, &jp, &dy);
+      atomic_add_f64(&rho[i + n1 * j], m * (1. - dx) * (1. - dy));
+      atomic_add_f64(&rho[i + n1 * jp], m * (1. - dx) * dy);
+      atomic_add_f64(&rho[ip + n1 * j], m * dx * (1. - dy));
+      atomic_add_f64(&rho[ip + n1 * jp], m * dx * dy);
+    }
+    return;
+  }
+  for (i64 n = 0; n < npart; n++) {
+    i64 i, ip, j, jp, k, kp;
+    double dx, dy, dz;
+    cell(x[0 + 3 * n], n1, &i, &ip, &dx);
+    cell(x[1 + 3 * n], n2, &j, &jp, &dy);
+    cell(x[2 + 3 * n], n3, &k, &kp, &dz);
+    atomic_add_f64(&rho[i + n1 * (j + n2 * k)], m * (1 - dx) * (1 - dy) * (1 - dz));
+    atomic_add_f64(&rho[i + n1 * (jp + n2 * k)], m * (1 - dx) * dy * (1 - dz));
+    atomic_add_f64(&rho[ip + n1 * (j + n2 * k)], m * dx * (1 - dy) * (1 - dz));
+    atomic_add_f64(&rho[ip + n1 * (jp + n2 * k)], m * dx * dy * (1 - dz));
+    atomic_add_f64(&rho[i + n1 * (j + n2 * kp)], m * (1 - dx) * (1 - dy) * dz);
+    atomic_add_f64(&rho[i + n1 * (jp + n2 * kp)], m * (1 - dx) * dy * dz);
+    atomic_add_f64(&rho[ip + n1 * (j + n2 * kp)], m * dx * (1 - dy) * dz);
+    atomic_add_f64(&rho[ip + n1 * (jp + n2 * kp)], m * dx * dy * dz);
+  }
+}
+
+/* threads > 1, rank 3: slab-binned scatter.  Slab t of T owns the planes [n3 t / T, n3 (t+1) / T). */
+static inline i64 plane_of(double x3, i64 n3) {
+  i64 z = (i64)floor(x3 * (double)n3);
+  if (z >= n3 || z < 0) {                   /* x == 1.0 and strays: the periodic image, as cell() */
+    z %= n3;
+    if (z < 0) z += n3;
+  }
+  return z;
+}
+/* owner[k] = slab of plane k, filled by the caller's first call (n3 entries) */
+void pmref_slab_table(i64 n3, i64 T, int32_t *owner) {
+  for (i64 t = 0; t < T; t++)
+    for (i64 k = n3 * t / T; k < n3 * (t + 1) / T; k++) owner[k] = (int32_t)t;
+}
+void pmref_slab_count(const double *x, i64 lo, i64 hi, i64 n3, i64 T, const int32_t *owner, i64 *counts) {
+  for (i64 t = 0; t < T; t++) counts[t] = 0;
+  for (i64 n = lo; n < hi; n++) counts[owner[plane_of(x[2 + 3 * n], n3)]]++;
+}
+/* offsets[t] = where this chunk's first particle of slab t goes in idx; advanced as the chunk is written */
+void pmref_slab_fill(const double *x, i64 lo, i64 hi, i64 n3, i64 T, const int32_t *owner, i64 *offsets, i64 *idx) {
+  (void)T;
+  for (i64 n = lo; n < hi; n++) idx[offsets[owner[plane_of(x[2 + 3 * n], n3)]]++] = n;
+}
+/* the particles idx[0 .. nidx) all have k in [k0, k1): adds to the planes k < k1 go to rho, adds to plane k1
+ * (kp of the slab's top plane; plane 0 for the last slab) go to ghost[n1 * n2] */
+void pmref_cicdensity_slab(double *rho, double *ghost, const double *x, const i64 *idx, i64 nidx, double m, i64 n1, i64 n2,
+                           i64 n3, i64 k1) {
+  for (i64 q = 0; q < nidx; q++) {
+    const i64 n = idx[q];
+    i64 i, ip, j, jp, k, kp;
+    double dx, dy, dz;
+    cell(x[0 + 3 * n], n1, &i, &ip, &dx);
+    cell(x[1 + 3 * n], n2, &j, &jp, &dy);
+    cell(x[2 + 3 * n], n3, &k, &kp, &dz);
+    double *lo = rho + n1 * n2 * k;
+    double *up = (k + 1 == k1) ? ghost : rho + n1 * n2 * kp;
+    lo[i + n1 * j] += m * (1 - dx) * (1 - dy) * (1 - dz);
+    lo[i + n1 * jp] += m * (1 - dx) * dy * (1 - dz);
+    lo[ip + n1 * j] += m * dx * (1 - dy) * (1 - dz);
+    lo[ip + n1 * jp] += m * dx * dy * (1 - dz);
+    up[i + n1 * j] += m * (1 - dx) * (1 - dy) * dz;
+    up[i + n1 * jp] += m * (1 - dx) * dy * dz;
+    up[ip + n1 * j] += m * dx * (1 - dy) * dz;
+    up[ip + n1 * jp] += m * dx * dy * dz;
+  }
+}
+
 /* ParticleMesh.jl:326-353 */
 void pmref_ngpdensity(double *rho, const double *x, double m, i64 npart, int rank, i64 n1, i64 n2,
                       i64 n3) {
@@ -103,6 +198,9 @@ double pmref_sum(const double *rho, i64 ncell) {
 }
 void pmref_sub(double *out, const double *rho, double mean, i64 ncell) {
   for (i64 i = 0; i < ncell; i++) out[i] = rho[i] - mean;
+}
+void pmref_zero(double *dst, i64 n) {                     /* the zero fill of deposit, :290-292 */
+  for (i64 i = 0; i < n; i++) dst[i] = 0.;
 }
 void pmref_add_into(double *dst, const double *src, i64 n) {
   for (i64 i = 0; i < n; i++) dst[i] += src[i];

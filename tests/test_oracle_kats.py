@@ -88,6 +88,31 @@ def test_c_restatement_step_equals_numpy(CR, dims, rank, comoving):
     assert nlinf(vb, va) < 1e-14 and np.max(np.abs(xb - xa)) < 1e-15
 
 
+@pytest.mark.parametrize("dims,rank,threads", [((16, 12, 1), 2, 3), ((8, 12, 10), 3, 4), ((8, 8, 7), 3, 5)])
+def test_threaded_c_restatement_equals_the_serial_one(dims, rank, threads):
+    """The all-cores arm of bench.py --impl reference: slab-binned deposit (3-D, when every thread gets >= 2 planes),
+    compare-and-swap deposit (2-D and thin meshes), chunked reductions.  Same weights and per-particle arithmetic as the
+    serial loops; only the summation order of the deposit (slab-boundary cells / races) and of the mean may differ."""
+    from oracle.pm_ref_c import PMRefC
+    npart = 5000
+    x, v = make_particles(13, npart, rank, clustered=True)
+    x[:4] = [[0.0] * rank, [1.0] * rank, [np.nextafter(1.0, 0.0)] * rank, [0.5] * rank]      # edges of the periodic box
+    v *= 0.05
+    fa, fb = O.Fields(dims, npart, rank), O.Fields(dims, npart, rank)
+    xa, va, xb, vb = x.copy(), v.copy(), x.copy(), v.copy()
+    sc = (1.01, 1.02, 0.8, 1.03)
+    ma = PMRefC(threads=1).step_comoving(fa, xa, va, 0.8, 0.01, *sc)
+    mb = PMRefC(threads=threads).step_comoving(fb, xb, vb, 0.8, 0.01, *sc)
+    assert nlinf(fb.rho, fa.rho) < 1e-14 and abs(fb.rho.sum() - fa.rho.sum()) < 1e-10 * fa.rho.sum()
+    assert nlinf(fb.phi, fa.phi) < 1e-13 and nlinf(vb, va) < 1e-13 and np.max(np.abs(xb - xa)) < 1e-14
+    assert ma == pytest.approx(mb, rel=1e-13)
+    for interp in ("none", "cic"):                                   # and the deposits alone, both interpolations
+        ra, rb = np.ones(fa.rho.shape), np.ones(fa.rho.shape)
+        PMRefC(threads=1).deposit(ra, xa, 0.8, interp)
+        PMRefC(threads=threads).deposit(rb, xa, 0.8, interp)
+        assert nlinf(rb, ra) < 1e-14
+
+
 # ---------------------------------------------------------------- (c) analytic known answers
 def test_kat1_single_particle_weights_and_mass():
     """ParticleMesh.jl:395-402: the 8 CIC weights m(1-d|d)... at cells (i|ip, j|jp, k|kp)."""
