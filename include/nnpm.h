@@ -21,6 +21,12 @@
  *     upload/download/get/set calls.
  *   - there is no CPU fallback: without a CUDA device every compute call fails with
  *     NNPM_ERR_CUDA.
+ *
+ * Not provided, deliberately (SURVEY.md section 8b proposed them): a `gradient = spectral` switch -- the fused push
+ * takes the reference's centred difference (deriv1_3d, :549-573) on the fly from the staged phi box, which is both
+ * bit-faithful to the reference and free of the 25.8 GB acc array; multiplying the spectrum by -i sin(k_d) N gives the
+ * same numbers to 6e-16 (tests/test_oracle_kats.py, kat5) at the price of three more inverse transforms.  And a
+ * `rho_mean` statistic -- the mean is never needed (the DC bin is zeroed, :501) and is m * npart / ncell exactly.
  */
 #ifndef NNPM_H
 #define NNPM_H
