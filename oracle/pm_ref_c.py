@@ -103,6 +103,8 @@ class PMRefC:
             return
         self._par(lambda lo, hi: self.lib.pmref_zero(_ptr(rho, lo), hi - lo), rho.size)                # :290-292
         ch = _chunks(x.shape[0], self.threads)
+        if not ch or x.shape[0] == 0:
+            return
         if interpolation == "cic" and rank == 3 and n3 >= 2 * self.threads:
             self._deposit_slabs(rho, x, m, ch)
             return
