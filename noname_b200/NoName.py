@@ -60,7 +60,20 @@ def noname(conf_):
     PM.EVOLVERS[conf_["Evolve"]](gp, gd, p, conf_)
     if conf_.get("RestartFileName") and not conf_.get("OutputDisabled"):
         write_all(conf_["RestartFileName"], conf_, gp, gd, p)
+    if conf_.get("ProfilingOn", False) and conf_.get("_profile") and conf_.get("ProfilingResultsFile"):
+        write_profiling_results(conf_["ProfilingResultsFile"], conf_["_profile"])
     return gp, gd, p
+
+
+def write_profiling_results(fname, prof):
+    """src/IOtools.jl:142-147 writes Julia's sampling-profiler dump; here: total and per-step CUDA-event milliseconds of
+    every phase of the device step (deposit, solve, push, sort, exchange, comm, fft_*) and the launch count, as JSON."""
+    import json
+    n = max(1, prof["steps"])
+    out = {"steps": prof["steps"], "kernel_launches": prof["kernel_launches"],
+           "ms_total": prof["ms"], "ms_per_step": {k: v / n for k, v in prof["ms"].items()}}
+    with open(fname, "w", encoding="utf-8") as f:
+        json.dump(out, f, indent=1)
 
 
 def run_noname(configuration_file=None, restart_=False, rconf=None, overrides=None, argv=None):

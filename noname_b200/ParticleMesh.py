@@ -459,7 +459,8 @@ def analyzePM(gp, gd, p, conf, dev=None, force=False):
 def _device_for(gp, p, conf):
     """Device context(s) for an evolve loop.  New conf keys (no reference counterpart): NGPUs (slab decomposition
     over that many processes / GPUs; the process must have been launched once per GPU), SortEvery, DepositMode =
-    atomic | fixedpoint, BackInterpBugCompat, Device, PartCapacityFactor."""
+    atomic | fixedpoint, BackInterpBugCompat, Device, PartCapacityFactor.  ProfilingOn = true (src/NoName.jl:86-93 wraps the run
+    in Julia's sampling profiler) turns on the per-phase CUDA-event timers of the step calls instead (_profile_step)."""
     dims = tuple(gp[1].dim)
     rank = conf.get("_rank", sum(1 for d in dims if d > 1))
     npart = int(np.prod([int(q) for q in conf["ParticleDimensions"]]))
@@ -476,7 +477,7 @@ def _device_for(gp, p, conf):
                    deposit_mode=conf.get("DepositMode", options["deposit_mode"]),
                    sort_every=int(conf.get("SortEvery", options["sort_every"])),
                    bugcompat_interp_z=bool(conf.get("BackInterpBugCompat", options["bugcompat_interp_z"])),
-                   device=local, nranks=ngpus, rank_id=rid, part_capacity=cap)
+                   device=local, nranks=ngpus, rank_id=rid, part_capacity=cap, timing=bool(conf.get("ProfilingOn", False)))
     if ngpus > 1:
         dev.comm_init(slab.broadcast_bytes(DevicePM.comm_unique_id() if rid == 0 else None))
     if p.get("_ic") is not None and p.get("x") is None:
@@ -505,6 +506,20 @@ def _step_stats(dev, st):
     return dev.reduce_stats(st) if dev.nranks > 1 else st
 
 
+def _profile_step(conf, st):
+    """ProfilingOn: accumulate the step's per-phase CUDA-event milliseconds (nnpm_stats.ms) and launch count in
+    conf["_profile"]; NoName.noname() writes them to ProfilingResultsFile (the reference serialises Profile.retrieve()
+    there, src/IOtools.jl:142-147)."""
+    if not conf.get("ProfilingOn", False):
+        return
+    prof = conf.setdefault("_profile", {"steps": 0, "kernel_launches": 0, "ms": {}})
+    d = st.as_dict()
+    prof["steps"] += 1
+    prof["kernel_launches"] += int(d["kernel_launches"])
+    for k, v in d["ms"].items():
+        prof["ms"][k] = prof["ms"].get(k, 0.0) + float(v)
+
+
 def evolvePM(gp, gd, p, conf, log=None):
     """:738-796 -- static PM loop; dt control on the host from the step's device reductions."""
     c = conf
@@ -519,6 +534,7 @@ def evolvePM(gp, gd, p, conf, log=None):
             t1, cyc1 = c["CurrentTime"] + dt, c["CurrentCycle"] + 1
             dev.set_option("keep_rho", _output_due(c, t1, cyc1) or not (t1 < c["StopTime"] and cyc1 < c["StopCycle"]))
             st = _step_stats(dev, dev.step_static(dt))
+            _profile_step(c, st)
             c["CurrentTime"] += dt
             if log is not None:
                 log.append((c["CurrentTime"], dt, st.max_pa, st.max_v))
@@ -558,6 +574,7 @@ def evolvePMCosmology(gp, gd, p, conf, log=None):
             dev.set_option("keep_rho", _output_due(c, t, c["CurrentCycle"]) or _output_due(c, t1, cyc1)
                            or not (t1 < c["StopTime"] and cyc1 < c["StopCycle"]))
             st = _step_stats(dev, dev.step_comoving(dt, a1, ak, adk, a2))
+            _profile_step(c, st)
             analyzePM(gp, gd, p, c, dev)
             c["CurrentTime"] += dt
             c["CurrentRedshift"] = _cos.z_from_t_internal(cosmo, c["CurrentTime"], zinit)

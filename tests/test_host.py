@@ -384,6 +384,38 @@ def test_hdf5_output_layout_when_h5py_is_available(tmp_path):
         assert f["grid1/ρD"].attrs["vsz_range"].tolist() == [0, 0, 1, 1]
 
 
+def test_profiling_on_collects_the_step_timers(monkeypatch, tmp_path):
+    """ProfilingOn = true (src/NoName.jl:86-93): the per-phase CUDA-event times of every step are accumulated and written
+    to ProfilingResultsFile by noname()"""
+    import json
+
+    class St(_FakeStats):
+        def as_dict(self):
+            return {"kernel_launches": 7, "ms": {"deposit": 1.0, "solve": 2.0, "push": 3.0}}
+
+    class Dev(_FakeDev):
+        def step_static(self, dt):
+            self.calls.append((dt,))
+            return St(self.maxv)
+    fake = Dev(2.0)
+    monkeypatch.setattr(PM, "_device_for", lambda gp, p, c: fake)
+    monkeypatch.setattr(PM, "_sync_host", lambda *a, **k: None)
+    monkeypatch.setitem(NoName.INITIALIZERS, "InitializeParticleSimulation",
+                        lambda gp, gd, p, c: gp.update({1: PM.GridPatch([0, 0, 0], [1, 1, 1], 1, 1, (16, 16, 1))}))
+    prof = str(tmp_path / "prof.json")
+    c = dict(cf.DEFAULTS, Initializer="InitializeParticleSimulation", Evolve="evolvePM", StartTime=0.0, StopTime=1.0, StopCycle=4,
+             InitialDt=1e-3, CourantFactor=0.5, MaximumDt=0.03, OutputDisabled=True, ParticleDimensions=[8, 8, 1],
+             ProfilingOn=True, ProfilingResultsFile=prof)
+    NoName.noname(c)
+    out = json.load(open(prof))
+    assert out["steps"] == 4 and out["kernel_launches"] == 28
+    assert out["ms_total"] == {"deposit": 4.0, "solve": 8.0, "push": 12.0} and out["ms_per_step"]["push"] == 3.0
+    c2 = dict(c, ProfilingOn=False, ProfilingResultsFile=str(tmp_path / "none.json"))
+    c2.pop("_profile", None)
+    NoName.noname(c2)
+    assert not (tmp_path / "none.json").exists()
+
+
 def test_restart_roundtrip_resumes_time(tmp_path):
     """src/restart.jl + IOtools.jl:118-138 (with the F10 arity bug fixed): state and clock survive."""
     gp = {1: PM.GridPatch([0, 0, 0], [1, 1, 1], 1, 1, (8, 8, 1))}
