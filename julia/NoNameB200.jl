@@ -93,11 +93,11 @@ end
 
 function DevicePM(dims, npart; rank = count(d -> d > 1, dims), deposit = "cic", backinterp = "cic",
                   deposit_mode = 0, sort_every = 8, device = 0, nranks = 1, rank_id = 0, part_capacity = 0,
-                  bugcompat_interp_z = false)
+                  bugcompat_interp_z = false, timing = false)
     ccall((:nnpm_version, libnnpm), Cint, ()) == 2 || error("libnnpm.so: ABI version mismatch")
     cfg = NNPMConfig(Int32(sizeof(NNPMConfig)), Int32(rank), (Int64(dims[1]), Int64(dims[2]), Int64(dims[3])),
                      Int64(npart), Int64(part_capacity), INTERP[deposit], INTERP[backinterp], Int32(deposit_mode), 0,
-                     Int32(sort_every), Int32(bugcompat_interp_z), Int32(device), Int32(nranks), Int32(rank_id), 0, C_NULL)
+                     Int32(sort_every), Int32(bugcompat_interp_z), Int32(device), Int32(nranks), Int32(rank_id), Int32(timing), C_NULL)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:nnpm_create, libnnpm), Cint, (Ptr{Ptr{Cvoid}}, Ref{NNPMConfig}), h, cfg)
     check(nothing, rc)
@@ -516,6 +516,23 @@ function analyzePM(gp, gd, p, conf, dev; force = false, writer = default_writer)
     nothing
 end
 
+# ProfilingOn = true (src/NoName.jl:86-93 wraps the run in Julia's profiler): accumulate the per-phase CUDA-event
+# milliseconds of every step instead; noname() writes them to ProfilingResultsFile
+const MS_NAMES = ("deposit", "solve", "push", "sort", "exchange", "comm", "fft_z", "fft_xy", "fft_x", "fft_y")
+function profile_step!(conf, st::NNPMStats)
+    get(conf, "ProfilingOn", false) === true || return nothing
+    prof = get!(conf, "_profile", Dict{String,Any}("steps" => 0, "kernel_launches" => 0, "ms" => Dict{String,Float64}()))
+    prof["steps"] += 1; prof["kernel_launches"] += Int(st.kernel_launches)
+    for (i, name) in enumerate(MS_NAMES); prof["ms"][name] = get(prof["ms"], name, 0.0) + Float64(st.ms[i]); end
+    nothing
+end
+function write_profiling_results(fname, prof)
+    open(fname, "w") do f
+        println(f, "steps = ", prof["steps"]); println(f, "kernel_launches = ", prof["kernel_launches"])
+        for (k, v) in prof["ms"]; println(f, "ms_per_step[", k, "] = ", v / max(1, prof["steps"])); end
+    end
+end
+
 # ---- evolve loops: conf["Evolve"] plugins ------------------------------------------------------
 function device_for(gp, p, conf)
     P = Int(get(conf, "NGPUs", 1)); rid = 0; device = Int(get(conf, "Device", 0))
@@ -532,7 +549,7 @@ function device_for(gp, p, conf)
                    deposit = conf["ParticleDepositInterpolation"], backinterp = conf["ParticleBackInterpolation"],
                    sort_every = get(conf, "SortEvery", 8), deposit_mode = get(conf, "DepositMode", "atomic") == "fixedpoint" ? 1 : 0,
                    device = device, bugcompat_interp_z = get(conf, "BackInterpBugCompat", false),
-                   nranks = P, rank_id = rid, part_capacity = cap)
+                   nranks = P, rank_id = rid, part_capacity = cap, timing = get(conf, "ProfilingOn", false) === true)
     P > 1 && comm_init!(dev, id -> MPI.Bcast!(id, 0, MPI.COMM_WORLD))
     ic = get(p, "_ic", nothing)
     pd = Int.(conf["ParticleDimensions"])
@@ -566,6 +583,7 @@ function evolvePM(gp, gd, p, conf)
         t1, cyc1 = c["CurrentTime"] + dt, c["CurrentCycle"] + 1
         set_option!(dev, "keep_rho", output_due(c, t1, cyc1) || !(t1 < c["StopTime"] && cyc1 < c["StopCycle"]))
         st = step_static!(dev, dt)                                           # :766-778
+        profile_step!(c, st)
         c["CurrentTime"] += dt
         dt = c["CourantFactor"] * dx / (st.max_abs_v + 1e-30)                # :782
         dt = min(dt, c["MaximumDt"])
@@ -598,6 +616,7 @@ function evolvePMCosmology(gp, gd, p, conf)
         set_option!(dev, "keep_rho", output_due(c, t, c["CurrentCycle"]) || output_due(c, t1, cyc1) ||
                                      !(t1 < c["StopTime"] && cyc1 < c["StopCycle"]))
         st = step_comoving!(dev, dt, a1, ak, adk, a2)                                # :854-868
+        profile_step!(c, st)
         analyzePM(gp, gd, p, c, dev)
         c["CurrentTime"] += dt
         c["CurrentRedshift"] = z_from_t_internal(cosmo, c["CurrentTime"], zinit)
@@ -637,6 +656,7 @@ function noname(conf)                                                           
     INITIALIZERS[conf["Initializer"]](gp, gd, p, conf)
     EVOLVERS[conf["Evolve"]](gp, gd, p, conf)
     write_all(conf["RestartFileName"], conf, gp, gd, p)
+    (get(conf, "ProfilingOn", false) === true && haskey(conf, "_profile")) && write_profiling_results(conf["ProfilingResultsFile"], conf["_profile"])
     gp, gd, p
 end
 "gp, gd, p = run_noname(\"particle_mesh.conf\")   (NoName.jl:51-100; restart = true makes the file a restart dump)"
