@@ -94,7 +94,7 @@ enum {
   NNPM_MS_FFT_Z = 6,   /* of SOLVE: the z pass (z-FFT, Green multiply, z-iFFT) */
   NNPM_MS_FFT_XY = 7,  /* of SOLVE: the two batched 2-D transforms */
   NNPM_MS_FFT_X = 8,   /* of FFT_XY: the x passes (r2c + c2r); 0 when not separately timed */
-  NNPM_MS_FFT_Y = 9,   /* of FFT_XY: the y passes (forward + inverse; with nranks > 1 the forward one carries the fused NVLink transpose) */
+  NNPM_MS_FFT_Y = 9,   /* of FFT_XY: the y passes (forward + inverse); 0 when not separately timed (chunked multi-rank pipeline) */
   NNPM_MS_COUNT = 10
 };
 
