@@ -471,7 +471,7 @@ function hdf5_writer(fname, gp, gd, p)
         for (_, cgp) in gp
             g = HDF5.create_group(f, string("grid", cgp.id))
             for (name, a) in gd[cgp.id].d
-                g[name] = dropdims(a; dims = Tuple(findall(size(a) .== 1)))      # IOtools.squeeze
+                g[name] = dropdims(a; dims = Tuple(i for i in 1:ndims(a) if size(a, i) == 1))   # IOtools.squeeze
                 HDF5.attributes(g[name])["vsz_range"] = Float64[gp[1].LE[1], gp[1].LE[2], gp[1].RE[1], gp[1].RE[2]]
             end
         end
