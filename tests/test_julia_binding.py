@@ -207,3 +207,17 @@ def test_julia_host_covers_the_reference_surface():
                  "ZeldovichPancakeParticles", "PowerSpectrumParticles", "a_from_t_internal", "dadt_from_t_internal",
                  "z_from_t_internal", "hdf5_writer", "device_for", "sync_host!"):
         assert re.search(rf"(^|\n)\s*(function\s+)?{re.escape(name)}\(", code), name
+
+
+def test_julia_file_lexes_cleanly():
+    """Pygments' Julia lexer finds no malformed token (it does not know regex literals: backslashes inside r"..." are
+    the only tokens it may flag)"""
+    pygments = __import__("pytest").importorskip("pygments")
+    from pygments.lexers import JuliaLexer
+    from pygments.token import Error
+    src = open(JULIA, encoding="utf-8").read()
+    lines, line = src.splitlines(), 1
+    for tok, val in JuliaLexer().get_tokens(src):
+        if tok in Error:
+            assert val == "\\" and 'r"' in lines[line - 1], (line, val, lines[line - 1])
+        line += val.count("\n")
