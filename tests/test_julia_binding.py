@@ -221,3 +221,19 @@ def test_julia_file_lexes_cleanly():
         if tok in Error:
             assert val == "\\" and 'r"' in lines[line - 1], (line, val, lines[line - 1])
         line += val.count("\n")
+
+
+def test_julia_calls_resolve_to_definitions_or_base():
+    """every name called as f(...) is defined in the file or is one of the Base / stdlib functions listed here (catches
+    typos that only a Julia run would otherwise find)"""
+    base = set("""Dict Float64 IOBuffer Int Int32 Int64 String Tuple UInt64 UInt8 abs asinh copy count div dropdims eachline
+        endswith enumerate fill first floor get get! haskey joinpath match max maximum min mkpath mod occursin ones parse prod
+        replace round serialize deserialize similar sinh size sizeof split sprintf sqrt startswith string strip sum take!
+        tryparse unsafe_string zeros zip error isdir isfile isempty length merge! open println push! write finalizer ccall
+        Ref ndims collect findall sin cos exp log""".split())
+    code = _julia_code_only(open(JULIA, encoding="utf-8").read())
+    defs = set(re.findall(r"(?:^|\n)\s*(?:function\s+)?([A-Za-z_][\w!]*)\(", code))
+    defs |= set(re.findall(r"\bstruct\s+(\w+)", code)) | set(re.findall(r"\bconst\s+(\w+)", code))
+    calls = set(re.findall(r"(?<![\w.:@])([A-Za-z_][\w!]*)\(", code))
+    unknown = sorted(c for c in calls if c not in defs and c not in base)
+    assert not unknown, unknown
