@@ -1,0 +1,105 @@
+"""The product's host loop end to end on CPU: run_noname() on the reference's shipped run/CosmologyPM conf (pancake ICs,
+evolvePMCosmology's dt control, output cadence, keep_rho requests, restart file) with the device context replaced by an
+adapter over the C restatement of the operators -- so that only HOST logic differs from the oracle's own loop, and the
+two must agree in step count, final time (to the last bits) and state.  The same run on the GPU is
+tests/test_gpu_run.py::test_run_noname_shipped_cosmology_conf."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pm_ref as O
+from test_gpu_run import SHIPPED_COSMOLOGY_PM
+
+
+class _Stats:
+    def __init__(self, a, b, c):
+        self.max_abs_v, self.max_v, self.max_pa = a, b, c
+
+
+def _adapter():
+    from noname_b200 import _lib
+    from oracle.pm_ref_c import PMRefC
+
+    class OracleDev:
+        """DevicePM's interface (the part the evolve loops and analyzePM use) over oracle/pm_ref.c, single process"""
+        nranks, rank_id = 1, 0
+
+        def __init__(self, dims, npart_total, rank=3, **kw):
+            self.dims, self.rank = tuple(dims), rank
+            self.f = O.Fields(self.dims, npart_total, rank)
+            self.c = PMRefC(threads=1)
+            self.keep, self.rho, self.steps_kept = False, None, 0
+
+        def set_option(self, name, value):
+            assert name == "keep_rho"
+            self.keep = bool(value)
+
+        def upload(self, x, v, m, first_id=0):
+            self.x, self.v, self.m = x.copy(), v.copy(), m
+
+        @property
+        def local_count(self):
+            return len(self.x)
+
+        def step_comoving(self, dt, a1, ak, adk, a2):
+            mabs, mv = self.c.step_comoving(self.f, self.x, self.v, self.m, dt, a1, ak, adk, a2)
+            self.rho = self.f.rho.copy() if self.keep else None
+            self.steps_kept += self.keep
+            return _Stats(mabs, mv, 0.0)
+
+        def download(self, x=None, v=None, ids=False):
+            x[...], v[...] = self.x, self.v
+            return x, v
+
+        def get_field(self, which):
+            if which == "phi":
+                return self.f.phi.copy()
+            if self.rho is None:
+                raise _lib.NNPMError(-6, "mesh does not currently hold rho")
+            return self.rho.copy()
+
+        def deposit(self):
+            raise AssertionError("an output was written after a step whose density the loop had not asked to keep")
+
+        def close(self):
+            OracleDev.last = self
+
+    return OracleDev
+
+
+@pytest.mark.parametrize("zfinal", [100.0, 40.0])
+def test_run_noname_host_loop_equals_the_oracle_loop(monkeypatch, tmp_path, zfinal):
+    from noname_b200 import ParticleMesh as PM, NoName, run_noname
+    dev_cls = _adapter()
+    monkeypatch.setattr(PM, "DevicePM", dev_cls)
+    conf = tmp_path / "particle_mesh.conf"
+    conf.write_text(SHIPPED_COSMOLOGY_PM, encoding="utf-8")
+    over = {"OutputDirectory": str(tmp_path / "out"), "RestartFileName": str(tmp_path / "restart.bin"), "OutputFormat": "npz",
+            "FinalRedshift": zfinal}
+    gp, gd, p = run_noname(str(conf), overrides=over)
+    c = NoName.conf
+
+    oc = O.Cosmo(h=1.0, OmegaM=1.0, OmegaR=0.0)
+    ts, te = O.start_stop_times(oc, 400, zfinal)
+    a = O.a_from_t_internal(oc, ts, 400, zwherea1=400)
+    ad = O.dadt_from_t_internal(oc, ts, 400)
+    xr, vr = O.zeldovich_pancake((128, 128, 1), 2, 10.0, 400, a, ad)
+    m = 64 * 64 / (128.0 * 128.0)
+    rc = dict(StartTime=ts, StopTime=te, StartCycle=0, StopCycle=1000000, InitialDt=1e-4, CourantFactor=0.5, MaximumDt=1.0,
+              DtFractionOfTime=0.1, InitialRedshift=400)
+    t, cyc, f = O.evolvePMCosmology(xr, vr, m, (64, 64, 1), rc, oc)
+    # the product's closed-form / Newton a(t) against the oracle's quadrature + root finder, through the whole dt control
+    assert c["CurrentCycle"] == cyc and c["CurrentTime"] == pytest.approx(t, rel=1e-13)
+    assert c["CurrentRedshift"] == pytest.approx(zfinal, abs=1e-4)            # final-step clamp (1 + 1e-6), :882-885
+    assert np.max(np.abs(p["x"] - xr)) < 1e-12 and np.max(np.abs(p["v"] - vr)) < 1e-12 * np.max(np.abs(vr))
+    assert np.max(np.abs(gd[1].d["Φ"] - f.phi)) <= 1e-12 * np.max(np.abs(f.phi))
+    assert np.max(np.abs(gd[1].d["ρD"] - f.rho)) <= 1e-12 * np.max(np.abs(f.rho))
+    # outputs: OutputDtDataDump = 3.5 with LastOutputTime = StartTime - 3.5 -> a dump right after the first step, then every
+    # 3.5 time units, then the forced final one; each holds the density of the step it follows (the adapter raises otherwise)
+    outs = sorted(os.path.join(dp, q) for dp, _, fs in os.walk(over["OutputDirectory"]) for q in fs if q.endswith(".npz"))
+    assert len(outs) >= 2
+    assert np.load(outs[0])["grid1/ρD"].sum() == pytest.approx(m * 128 * 128, rel=1e-12)
+    assert np.array_equal(np.load(outs[-1])["grid1/ρD"], np.squeeze(gd[1].d["ρD"]))
+    assert 0 < dev_cls.last.steps_kept < cyc                                    # kept only where needed
+    assert os.path.exists(over["RestartFileName"])
