@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import pm_ref as O
-from test_gpu_run import SHIPPED_COSMOLOGY_PM
+from test_gpu_run import SHIPPED_COSMOLOGY_PM, SHIPPED_PM
 
 
 class _Stats:
@@ -41,6 +41,16 @@ def _adapter():
         @property
         def local_count(self):
             return len(self.x)
+
+        def init_grf(self, pdims, seed=12345, ps_index=-1.0, disp_rms=0.0, vfac=0.0, m=1.0, peaks=None):
+            self.x, self.v = O.synthetic_grf(tuple(int(q) for q in pdims), self.rank, seed, ps_index, disp_rms, vfac, peaks=peaks)
+            self.m, OracleDev.ic_request = m, dict(seed=seed, ps_index=ps_index, disp_rms=disp_rms, vfac=vfac, peaks=peaks)
+
+        def step_static(self, dt):
+            mabs, mv = self.c.step_static(self.f, self.x, self.v, self.m, dt)
+            self.rho = self.f.rho.copy() if self.keep else None
+            self.steps_kept += self.keep
+            return _Stats(mabs, mv, 0.0)
 
         def step_comoving(self, dt, a1, ak, adk, a2):
             mabs, mv = self.c.step_comoving(self.f, self.x, self.v, self.m, dt, a1, ak, adk, a2)
@@ -103,3 +113,27 @@ def test_run_noname_host_loop_equals_the_oracle_loop(monkeypatch, tmp_path, zfin
     assert np.array_equal(np.load(outs[-1])["grid1/ρD"], np.squeeze(gd[1].d["ρD"]))
     assert 0 < dev_cls.last.steps_kept < cyc                                    # kept only where needed
     assert os.path.exists(over["RestartFileName"])
+
+
+def test_run_noname_shipped_pm_conf_verbatim_host_loop(monkeypatch, tmp_path):
+    """run/PM/particle_mesh.conf as shipped (static evolvePM, InputPowerSpectrum = multiplePeaksPS(-1, 1, [0.1, 1, 10], 1.),
+    100^2 particles on a 1000 x 1000 x 1 mesh): the conf parser, the IC request handed to the device and evolvePM's dt
+    control / output cadence, on CPU.  GPU twin: tests/test_gpu_run.py::test_run_noname_shipped_pm_conf_verbatim."""
+    from noname_b200 import ParticleMesh as PM, NoName, run_noname
+    dev_cls = _adapter()
+    monkeypatch.setattr(PM, "DevicePM", dev_cls)
+    conf = tmp_path / "particle_mesh.conf"
+    conf.write_text(SHIPPED_PM, encoding="utf-8")
+    over = {"OutputDirectory": str(tmp_path / "out"), "RestartFileName": str(tmp_path / "restart.bin"), "OutputFormat": "npz"}
+    gp, gd, p = run_noname(str(conf), overrides=over)
+    c = NoName.conf
+    assert dev_cls.ic_request == dict(seed=12345, ps_index=-1.0, disp_rms=0.3 / 1000, vfac=0.0, peaks=([0.1, 1.0, 10.0], [1.0, 1.0, 1.0]))
+    xr, vr = O.synthetic_grf((100, 100, 1), 2, 12345, -1.0, 0.3 / 1000, 0.0, peaks=([0.1, 1.0, 10.0], [1.0, 1.0, 1.0]))
+    m = 1000.0 * 1000.0 / 1e4
+    rc = dict(StartTime=0.0, StopTime=1.0, StartCycle=0, StopCycle=1000000, InitialDt=1e-7, CourantFactor=0.2, MaximumDt=0.1)
+    t, cyc, f = O.evolvePM(xr, vr, m, (1000, 1000, 1), rc)
+    assert c["CurrentCycle"] == cyc and c["CurrentTime"] == pytest.approx(t, rel=1e-14) and p["m"] == m
+    assert np.max(np.abs(p["x"] - xr)) < 1e-13 and np.max(np.abs(p["v"] - vr)) <= 1e-12 * np.max(np.abs(vr))
+    assert np.max(np.abs(gd[1].d["ρD"] - f.rho)) <= 1e-12 * np.max(np.abs(f.rho))
+    outs = [q for dp, _, fs in os.walk(over["OutputDirectory"]) for q in fs if q.endswith(".npz")]
+    assert len(outs) == 1                      # OutputDtDataDump = 0.5: one dump at t = 0.5 + InitialDt, none at StopTime (:780-796)
