@@ -137,3 +137,30 @@ def test_run_noname_shipped_pm_conf_verbatim_host_loop(monkeypatch, tmp_path):
     assert np.max(np.abs(gd[1].d["ρD"] - f.rho)) <= 1e-12 * np.max(np.abs(f.rho))
     outs = [q for dp, _, fs in os.walk(over["OutputDirectory"]) for q in fs if q.endswith(".npz")]
     assert len(outs) == 1                      # OutputDtDataDump = 0.5: one dump at t = 0.5 + InitialDt, none at StopTime (:780-796)
+
+
+def test_restart_continues_a_stopped_run(monkeypatch, tmp_path):
+    """src/restart.jl through run_noname(restart=True): a run stopped by StopCycle leaves a restart file; restarting
+    from it (with an rconf that lifts StopCycle) resumes at the dumped time and cycle, with the particles of the dump,
+    and reaches StopTime"""
+    from noname_b200 import ParticleMesh as PM, NoName, run_noname
+    monkeypatch.setattr(PM, "DevicePM", _adapter())
+    conf = tmp_path / "particle_mesh.conf"
+    conf.write_text(SHIPPED_COSMOLOGY_PM, encoding="utf-8")
+    rfile = str(tmp_path / "restart.bin")
+    over = {"OutputDirectory": str(tmp_path / "out"), "RestartFileName": rfile, "OutputFormat": "npz", "FinalRedshift": 100.0,
+            "StopCycle": 20}
+    gp, gd, p = run_noname(str(conf), overrides=over)
+    c1 = dict(NoName.conf)
+    assert c1["CurrentCycle"] == 20 and c1["CurrentTime"] < c1["StopTime"]
+    x20 = p["x"].copy()
+    rconf = tmp_path / "restart.conf"
+    rconf.write_text("StopCycle = 1000000\n", encoding="utf-8")
+    gp2, gd2, p2 = run_noname(rfile, restart_=True, rconf=str(rconf), overrides={"OutputDirectory": str(tmp_path / "out2"),
+                                                                                   "RestartFileName": str(tmp_path / "r2.bin")})
+    c2 = NoName.conf
+    assert c2["StartTime"] == c1["CurrentTime"] and c2["StartCycle"] == 20
+    assert c2["CurrentCycle"] > 20 and c2["CurrentTime"] >= c2["StopTime"] == c1["StopTime"]
+    assert c2["CurrentRedshift"] == pytest.approx(100.0, abs=1e-3)
+    assert p2["x"].shape == x20.shape and not np.array_equal(p2["x"], x20)
+    assert gd2[1].d["ρD"].sum() == pytest.approx(p2["m"] * 128 * 128, rel=1e-12)
