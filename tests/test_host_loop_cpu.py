@@ -30,6 +30,7 @@ def _adapter():
             self.f = O.Fields(self.dims, npart_total, rank)
             self.c = PMRefC(threads=1)
             self.keep, self.rho, self.steps_kept = False, None, 0
+            self.dep, self.back = kw.get("deposit", "cic"), kw.get("backinterp", "cic")
 
         def set_option(self, name, value):
             assert name == "keep_rho"
@@ -47,7 +48,7 @@ def _adapter():
             self.m, OracleDev.ic_request = m, dict(seed=seed, ps_index=ps_index, disp_rms=disp_rms, vfac=vfac, peaks=peaks)
 
         def step_static(self, dt):
-            mabs, mv = self.c.step_static(self.f, self.x, self.v, self.m, dt)
+            mabs, mv = self.c.step_static(self.f, self.x, self.v, self.m, dt, self.dep, self.back)
             self.rho = self.f.rho.copy() if self.keep else None
             self.steps_kept += self.keep
             return _Stats(mabs, mv, 0.0)
@@ -68,6 +69,9 @@ def _adapter():
             if self.rho is None:
                 raise _lib.NNPMError(-6, "mesh does not currently hold rho")
             return self.rho.copy()
+
+        def power_spectrum(self):
+            return O.powerSpectrum(self.x.copy(), self.m, self.dims, self.dep)
 
         def deposit(self):
             raise AssertionError("an output was written after a step whose density the loop had not asked to keep")
@@ -164,3 +168,51 @@ def test_restart_continues_a_stopped_run(monkeypatch, tmp_path):
     assert c2["CurrentRedshift"] == pytest.approx(100.0, abs=1e-3)
     assert p2["x"].shape == x20.shape and not np.array_equal(p2["x"], x20)
     assert gd2[1].d["ρD"].sum() == pytest.approx(p2["m"] * 128 * 128, rel=1e-12)
+
+
+def test_static_3d_wind_run_with_ngp_deposit_cycle_outputs_and_power_spectrum(monkeypatch, tmp_path):
+    """a conf a NoName user could write: UniformParticleWind (:161-175), ParticleDepositInterpolation = none, CIC back-
+    interpolation, OutputEveryNCycle, OutputPowerSpectrum -- the interpolation keys reach the device, every dump is
+    preceded by a kept density, and the P(k) numbers are written beside it"""
+    from noname_b200 import ParticleMesh as PM, NoName, run_noname
+    dev_cls = _adapter()
+    monkeypatch.setattr(PM, "DevicePM", dev_cls)
+    conf = tmp_path / "wind.conf"
+    conf.write_text("""
+Initializer = InitializeParticleSimulation
+ProblemDefinition = UniformParticleWind
+UniformParticleWindVelocity = 0.25
+Evolve = evolvePM
+TopgridDimensions  = [16, 16, 16]
+ParticleDimensions = [16, 16, 16]
+MaximumDt = 0.05
+StopTime = 0.4
+CourantFactor = 0.5
+ParticleDepositInterpolation = none
+ParticleBackInterpolation    = cic
+OutputEveryNCycle = 2
+OutputPowerSpectrum = true
+OutputSeparateDirectories = false
+""", encoding="utf-8")
+    over = {"OutputDirectory": str(tmp_path / "out"), "RestartFileName": str(tmp_path / "restart.bin"), "OutputFormat": "npz"}
+    gp, gd, p = run_noname(str(conf), overrides=over)
+    c = NoName.conf
+    dev = dev_cls.last
+    assert (dev.dep, dev.back) == ("none", "cic") and dev.dims == (16, 16, 16) and dev.rank == 3
+    q = O.initialize_particles_uniform((16, 16, 16), 3)
+    xr, vr = q.copy(), np.zeros_like(q)
+    vr[:, 0] = 0.25
+    rc = dict(StartTime=0.0, StopTime=0.4, StartCycle=0, StopCycle=1000000, InitialDt=1e-7, CourantFactor=0.5, MaximumDt=0.05)
+    t, cyc, f = O.evolvePM(xr, vr, 1.0, (16, 16, 16), rc, dep="none", back="cic")      # evolves xr, vr in place
+    assert c["CurrentCycle"] == cyc and c["CurrentTime"] == pytest.approx(t, rel=1e-14)
+    assert np.max(np.abs(p["x"] - xr)) < 1e-14 and np.max(np.abs(p["v"] - vr)) < 1e-14
+    # a uniform lattice in a uniform wind stays a lattice: no force, positions advance by 0.25 t (mod 1)
+    assert np.max(np.abs(p["v"][:, 0] - 0.25)) < 1e-13 and np.max(np.abs(p["v"][:, 1:])) < 1e-13
+    d = p["x"] - q
+    d -= np.rint(d)
+    assert np.max(np.abs(d[:, 0] - (0.25 * t - np.rint(0.25 * t)))) < 1e-12 and np.max(np.abs(d[:, 1:])) < 1e-13
+    files = sorted(os.listdir(over["OutputDirectory"]))
+    ndump = cyc // 2
+    assert [q for q in files if q.endswith(".npz")] == ["%05d.npz" % i for i in range(ndump)]
+    assert [q for q in files if q.endswith("_PS.txt")] == ["%05d_PS.txt" % i for i in range(ndump)]
+    assert dev.steps_kept == ndump + (cyc % 2)            # one kept density per dump (+ the last step of the loop)
