@@ -47,6 +47,21 @@ def _adapter():
             self.x, self.v = O.synthetic_grf(tuple(int(q) for q in pdims), self.rank, seed, ps_index, disp_rms, vfac, peaks=peaks)
             self.m, OracleDev.ic_request = m, dict(seed=seed, ps_index=ps_index, disp_rms=disp_rms, vfac=vfac, peaks=peaks)
 
+        def init_pancake(self, pdims, xamp, vamp, m=1.0):
+            q = O.initialize_particles_uniform(tuple(int(k) for k in pdims), self.rank)
+            sn = np.sin(2 * np.pi * q[:, 0])
+            self.x, self.v, self.m = q.copy(), np.zeros_like(q), m
+            self.v[:, 0] = vamp * sn
+            self.x[:, 0] += xamp * sn
+            O.make_periodic(self.x)
+            OracleDev.ic_request = dict(kind="pancake", xamp=xamp, vamp=vamp)
+
+        def init_synthetic(self, pdims, kind="zeldovich", m=1.0, **kw):
+            assert kind == "lattice"
+            self.x = O.initialize_particles_uniform(tuple(int(k) for k in pdims), self.rank)
+            self.v, self.m = np.zeros_like(self.x), m
+            OracleDev.ic_request = dict(kind="lattice")
+
         def step_static(self, dt):
             mabs, mv = self.c.step_static(self.f, self.x, self.v, self.m, dt, self.dep, self.back)
             self.rho = self.f.rho.copy() if self.keep else None
@@ -216,3 +231,49 @@ OutputSeparateDirectories = false
     assert [q for q in files if q.endswith(".npz")] == ["%05d.npz" % i for i in range(ndump)]
     assert [q for q in files if q.endswith("_PS.txt")] == ["%05d_PS.txt" % i for i in range(ndump)]
     assert dev.steps_kept == ndump + (cyc % 2)            # one kept density per dump (+ the last step of the loop)
+
+
+def test_north_star_aliases_and_device_initial_conditions(monkeypatch, tmp_path):
+    """the north star's conf spellings -- dims, cosm_Ωm, cosm_h (absent from the reference's code, accepted
+    as aliases) -- with DeviceInitialConditions = true: nothing is allocated on the host, the pancake request reaches the
+    device with the reference's amplitudes (:178-191), and the host arrays appear at the first output"""
+    from noname_b200 import ParticleMesh as PM, NoName, run_noname
+    dev_cls = _adapter()
+    monkeypatch.setattr(PM, "DevicePM", dev_cls)
+    conf = tmp_path / "alias.conf"
+    conf.write_text("""
+Initializer = InitializeParticleSimulation
+ProblemDefinition = ZeldovichPancakeParticles
+ZeldovichCausticRedshift = 10.
+Evolve = evolvePMCosmology
+dims = [32, 32, 1]
+ParticleDimensions = [64, 64, 1]
+cosm_Ωm = 1.0
+cosm_h = 1.0
+InitialRedshift = 400
+FinalRedshift = 200
+InitialDt = 0.0001
+CourantFactor = 0.5
+DtFractionOfTime = 0.1
+MaximumDt = 1.0
+OmegaBaryon = 0.
+DeviceInitialConditions = true
+""", encoding="utf-8")
+    over = {"OutputDirectory": str(tmp_path / "out"), "RestartFileName": str(tmp_path / "restart.bin"), "OutputFormat": "npz"}
+    gp, gd, p = run_noname(str(conf), overrides=over)
+    c = NoName.conf
+    assert tuple(gp[1].dim) == (32, 32, 1) and c["Cosmology"] == "cosmology(h=1.0,OmegaM=1.0,OmegaR=0.0)"
+    oc = O.Cosmo(h=1.0, OmegaM=1.0, OmegaR=0.0)
+    ts, te = O.start_stop_times(oc, 400, 200)
+    a = O.a_from_t_internal(oc, ts, 400, zwherea1=400)
+    ad = O.dadt_from_t_internal(oc, ts, 400)
+    A = 5.0 * 11.0 / 2.0 / 401.0
+    assert dev_cls.ic_request["kind"] == "pancake"
+    assert dev_cls.ic_request["xamp"] == pytest.approx(0.4 * A * a, rel=1e-12) and dev_cls.ic_request["vamp"] == pytest.approx(0.4 * A * ad, rel=1e-12)
+    xr, vr = O.zeldovich_pancake((64, 64, 1), 2, 10.0, 400, a, ad)
+    m = 32 * 32 / (64.0 * 64.0)
+    rc = dict(StartTime=ts, StopTime=te, StartCycle=0, StopCycle=1000000, InitialDt=1e-4, CourantFactor=0.5, MaximumDt=1.0,
+              DtFractionOfTime=0.1, InitialRedshift=400)
+    t, cyc, f = O.evolvePMCosmology(xr, vr, m, (32, 32, 1), rc, oc)
+    assert c["CurrentCycle"] == cyc and p["m"] == pytest.approx(m)
+    assert p["x"].shape == (64 * 64, 2) and np.max(np.abs(p["x"] - xr)) < 1e-12 and np.max(np.abs(p["v"] - vr)) < 1e-12 * np.max(np.abs(vr))
