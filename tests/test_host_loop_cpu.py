@@ -277,3 +277,30 @@ DeviceInitialConditions = true
     t, cyc, f = O.evolvePMCosmology(xr, vr, m, (32, 32, 1), rc, oc)
     assert c["CurrentCycle"] == cyc and p["m"] == pytest.approx(m)
     assert p["x"].shape == (64 * 64, 2) and np.max(np.abs(p["x"] - xr)) < 1e-12 and np.max(np.abs(p["v"] - vr)) < 1e-12 * np.max(np.abs(vr))
+
+
+def test_command_line_like_the_reference(monkeypatch, tmp_path):
+    """IOtools.parse_commandline (src/IOtools.jl:21-38): positional configuration_file, --restart / -r, --rconf"""
+    from noname_b200 import ParticleMesh as PM, NoName, run_noname
+    monkeypatch.setattr(PM, "DevicePM", _adapter())
+    conf = tmp_path / "cli.conf"
+    conf.write_text(f"""
+Initializer = InitializeParticleSimulation
+ProblemDefinition = UniformParticles
+Evolve = evolvePM
+TopgridDimensions  = [8, 8, 1]
+ParticleDimensions = [8, 8, 1]
+MaximumDt = 0.1
+StopTime = 0.3
+OutputDirectory = "{tmp_path / 'out'}"
+RestartFileName = "{tmp_path / 'restart.bin'}"
+""", encoding="utf-8")
+    gp, gd, p = run_noname(argv=[str(conf)])
+    c1 = dict(NoName.conf)
+    assert c1["CurrentTime"] >= 0.3 and c1["CurrentCycle"] >= 3 and os.path.exists(tmp_path / "restart.bin")
+    rconf = tmp_path / "restart.conf"
+    rconf.write_text("StopTime = 0.6\n", encoding="utf-8")
+    gp, gd, p = run_noname(argv=["-r", "--rconf", str(rconf), str(tmp_path / "restart.bin")])
+    c2 = NoName.conf
+    assert c2["StartTime"] == c1["CurrentTime"] and c2["CurrentTime"] >= 0.6 and c2["CurrentCycle"] > c1["CurrentCycle"]
+    assert np.allclose(gd[1].d["ρD"], 1.0)                      # a lattice at rest stays uniform
