@@ -304,3 +304,23 @@ RestartFileName = "{tmp_path / 'restart.bin'}"
     c2 = NoName.conf
     assert c2["StartTime"] == c1["CurrentTime"] and c2["CurrentTime"] >= 0.6 and c2["CurrentCycle"] > c1["CurrentCycle"]
     assert np.allclose(gd[1].d["ρD"], 1.0)                      # a lattice at rest stays uniform
+
+
+@pytest.mark.parametrize("text,path", [(SHIPPED_COSMOLOGY_PM, "run/CosmologyPM/particle_mesh.conf"), (SHIPPED_PM, "run/PM/particle_mesh.conf")])
+def test_embedded_confs_are_the_reference_files_verbatim(text, path):
+    """the tests carry the shipped confs as strings (the reference tree does not travel to the GPU box): where the tree is
+    present they must be the files, byte for byte up to surrounding blank lines"""
+    ref = os.path.join("/root/reference", path)
+    if not os.path.exists(ref):
+        pytest.skip("reference checkout not present")
+    assert open(ref, encoding="utf-8").read().strip() == text.strip()
+
+
+def test_builtin_defaults_equal_the_reference_default_conf():
+    """noname_b200.conf.DEFAULTS restates src/default.conf (the first conf layer, src/NoName.jl:58): where the reference
+    tree is present, parsing the file with the product's parser must give exactly those values"""
+    from noname_b200 import conf as cf
+    ref = "/root/reference/src/default.conf"
+    if not os.path.exists(ref):
+        pytest.skip("reference checkout not present")
+    assert cf.parseconf(ref) == cf.DEFAULTS
