@@ -237,3 +237,16 @@ def test_julia_calls_resolve_to_definitions_or_base():
     calls = set(re.findall(r"(?<![\w.:@])([A-Za-z_][\w!]*)\(", code))
     unknown = sorted(c for c in calls if c not in defs and c not in base)
     assert not unknown, unknown
+
+
+def test_julia_defaults_equal_the_python_defaults():
+    """both hosts restate src/default.conf: the Julia Dict literal must hold the same keys and values"""
+    import sys
+    sys.path.insert(0, ROOT)
+    from noname_b200 import conf as cf
+    src = open(JULIA, encoding="utf-8").read()
+    body = src[src.index("const DEFAULTS = Dict{String,Any}("):]
+    body = body[:body.index("\nfunction load_conf")]
+    pairs = re.findall(r'"([^"]+)"\s*=>\s*(\[[^\]]*\]|"[^"]*"|[^,\)\n]+)', body)
+    got = {k: cf.parse_value(v.strip()) for k, v in pairs}
+    assert got == cf.DEFAULTS
