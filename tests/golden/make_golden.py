@@ -79,9 +79,33 @@ def analytic_case():
     print("analytic_16")
 
 
+IC_CASES = {   # name: (pdims, rank, seed, ps_index, disp_rms, vfac, peaks)
+    "grf2d": ((12, 10, 1), 2, 4242, -1.0, 0.02, 0.7, None),
+    "grf3d": ((8, 6, 4), 3, 99, -2.0, 0.01, 0.0, None),
+    "peaks2d": ((16, 12, 1), 2, 777, -1.0, 0.015, 0.5, ([0.1, 1.0, 10.0], [1.0, 1.0, 1.0])),   # the run/PM spectrum
+}
+
+
+def ic_case():
+    """seeded initial conditions: the counter-based draws, the Hermitian planes and the window test of multiplePeaksPS
+    are pinned against accidental change of the generators' conventions (device twins: nnpm_init_grf[_peaks], nnpm_init_pancake)"""
+    out = {}
+    for name, (pd, rank, seed, n, rms, vfac, peaks) in IC_CASES.items():
+        x, v = O.synthetic_grf(pd, rank, seed, n, rms, vfac, peaks=peaks)
+        out[name + "_x"], out[name + "_v"] = x, v
+    x, v = O.zeldovich_pancake((16, 8, 1), 2, 10.0, 400.0, 1.0, math.sqrt(2.0 / 3.0))
+    out["pancake_x"], out["pancake_v"] = x, v
+    np.savez_compressed(os.path.join(HERE, "ics.npz"), **out)
+    print("ics", sorted(out))
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["ics"]:
+        ic_case()
+        sys.exit(0)
     step_case("step3d_comoving_12x10x16", (12, 10, 16), 3, 1500, 101, True, 4)
     step_case("step3d_static_16", (16, 16, 16), 3, 2000, 102, False, 3)
     step_case("step2d_comoving_24x20", (24, 20, 1), 2, 1200, 103, True, 4)
     step_case("step2d_static_32", (32, 32, 1), 2, 1500, 104, False, 3)
     analytic_case()
+    ic_case()

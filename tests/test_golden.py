@@ -47,6 +47,23 @@ def test_oracle_reproduces_golden(name, impl):
     assert np.max(np.abs(x - g["xN"])) < 1e-14 and nlinf(v, g["vN"]) < 1e-13
 
 
+def test_oracle_reproduces_golden_initial_conditions():
+    """seeded ICs (scale-free and multiplePeaksPS random fields, the pancake): same numbers as when the fixture was written
+    -- pins the hash-based draws, the Hermitian planes and the spectrum windows of the checker of nnpm_init_grf[_peaks]"""
+    import math
+    import sys
+    from oracle import pm_ref as O
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    from make_golden import IC_CASES
+    g = load("ics")
+    for name, (pd, rank, seed, n, rms, vfac, peaks) in IC_CASES.items():
+        x, v = O.synthetic_grf(pd, rank, seed, n, rms, vfac, peaks=peaks)
+        assert np.max(np.abs(x - g[name + "_x"])) < 1e-15 and np.max(np.abs(v - g[name + "_v"])) < 1e-15, name
+        assert np.sqrt(np.mean((v / vfac) ** 2)) == pytest.approx(rms, rel=1e-12) if vfac else not v.any()
+    x, v = O.zeldovich_pancake((16, 8, 1), 2, 10.0, 400.0, 1.0, math.sqrt(2.0 / 3.0))
+    assert np.array_equal(x, g["pancake_x"]) and np.array_equal(v, g["pancake_v"])
+
+
 def test_oracle_matches_analytic_vectors():
     from oracle import pm_ref as O
     g = load("analytic_16")
