@@ -144,12 +144,13 @@ def scalars(t, dt):
 
 def run_cpu(n, mesh, steps, warmup, threads):
     """The reference's loops (C restatement + pocketfft) on the host: comoving steps on an n^3 / mesh^3
-    sample of the same synthetic workload.  Returns (pu/s, seconds per step)."""
+    sample of the same synthetic workload.  `threads` is a count, or a list of candidate counts: each candidate then runs
+    two probe steps on the evolving state and the fastest one does the timed steps.  Returns (pu/s, seconds per step,
+    threads used, {candidate: probe seconds})."""
     from oracle import pm_ref as O
     from oracle.pm_ref_c import PMRefC
     from noname_b200 import cosmology as cos
     scalars.cosmo = cos.Cosmology(**COSMO)
-    ref = PMRefC(threads=threads)
     oc = O.Cosmo(**COSMO)
     ts, _ = O.start_stop_times(oc, ZINIT, 0.0)
     a0 = O.a_from_t_internal(oc, ts, ZINIT, zwherea1=ZINIT)
@@ -157,17 +158,31 @@ def run_cpu(n, mesh, steps, warmup, threads):
     x, v = O.synthetic_grf((n, n, n), 3, 12345, -1.0, 0.3 / mesh, ad0 / a0)
     m = (mesh ** 3) / float(n ** 3) * COSMO["OmegaM"]
     f = O.Fields((mesh, mesh, mesh), n ** 3, 3)
-    t, dt = ts, 1e-4
-    el = []
-    for it in range(warmup + steps):
-        sc = scalars(t, dt)
+    state = {"t": ts, "dt": 1e-4}
+
+    def step(ref):
+        sc = scalars(state["t"], state["dt"])
         t0 = time.perf_counter()
-        mabs, _ = ref.step_comoving(f, x, v, m, dt, *sc)
-        el.append(time.perf_counter() - t0)
-        t += dt
-        dt = min(0.5 * (1.0 / mesh) / mabs, 0.1 * t, 1.0)
+        mabs, _ = ref.step_comoving(f, x, v, m, state["dt"], *sc)
+        el = time.perf_counter() - t0
+        state["t"] += state["dt"]
+        state["dt"] = min(0.5 * (1.0 / mesh) / mabs, 0.1 * state["t"], 1.0)
+        return el
+    probes = {}
+    if isinstance(threads, (list, tuple)):
+        cands = sorted(set(int(q) for q in threads))
+        if len(cands) > 1:
+            for th in cands:
+                ref = PMRefC(threads=th)
+                step(ref)
+                probes[th] = step(ref)
+            threads = min(probes, key=probes.get)
+        else:
+            threads = cands[0]
+    ref = PMRefC(threads=threads)
+    el = [step(ref) for _ in range(warmup + steps)]
     sec = sum(el[warmup:]) / steps
-    return n ** 3 / sec, sec
+    return n ** 3 / sec, sec, threads, probes
 
 
 def parity_small_step(rank, world, local_rank, dist, opts=()):
@@ -232,9 +247,10 @@ def main():
     ap.add_argument("--mesh", type=int, default=1024, help="mesh cells per dimension")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=192, help="n of the n^3/n^3 CPU-baseline sample (0 = skip)")
-    ap.add_argument("--cpu-threads", type=int, default=16, help="--impl reference: host threads of the C restatement (capped by the cores available).  16: in round 1 more threads "
-                         "were slower; the deposit and the reductions have since been made to scale (oracle/pm_ref_c.py), "
-                         "not re-measured beyond 16")
+    ap.add_argument("--cpu-threads", type=int, default=0,
+                    help="--impl reference: host threads of the C restatement (capped by the cores available); 0 = try 16, 32 and all "
+                         "cores with two probe steps each and time the fastest (round 1: 32 threads were slower than 16; the "
+                         "deposit and the reductions have since been made to scale, oracle/pm_ref_c.py)")
     ap.add_argument("--sort-every", type=int, default=16,
                     help="counting-sort cadence in steps; the default K = 16 timed steps contain exactly one sort")
     ap.add_argument("--deposit-mode", default="atomic")
@@ -264,11 +280,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        threads = max(1, min(args.cpu_threads, len(os.sched_getaffinity(0))))
+        ncores = len(os.sched_getaffinity(0))
+        cand = [max(1, min(args.cpu_threads, ncores))] if args.cpu_threads > 0 else sorted({min(16, ncores), min(32, ncores), ncores})
         cs = args.cpu_sample or 192
-        val, sec = run_cpu(cs, cs, K, W, threads)
+        val, sec, threads, probes = run_cpu(cs, cs, K, W, cand)
         sample = (f"{cs}^3 particles / {cs}^3 mesh comoving steps of the same seeded random-field workload; C restatement of "
-                  f"ParticleMesh.jl loops + pocketfft on {threads} host threads (the Julia reference, itself single-threaded, cannot run here)")
+                  f"ParticleMesh.jl loops + pocketfft on {threads} of {ncores} host threads"
+                  + (f" (fastest of the probed counts, s/step: {({k: round(q, 4) for k, q in probes.items()})})" if probes else "")
+                  + " (the Julia reference, itself single-threaded, cannot run here)")
         # the config of this line describes what was RUN: the bounded sample, not the 1024^3 problem it stands in for
         rconfig = dict(config, workload=f"{cs}^3 particles / {cs}^3 mesh comoving PM step (LCDM Om=0.3 h=0.7), {ic_text} "
                                         f"-- bounded CPU sample of the {n}^3 / {mesh}^3 workload",
@@ -504,7 +523,7 @@ def main():
     cpu = None
     if rank == 0 and args.cpu_sample:
         cs = args.cpu_sample
-        val, sec = run_cpu(cs, cs, 2, 1, 1)
+        val, sec, _, _ = run_cpu(cs, cs, 2, 1, 1)
         cpu = {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"2 comoving steps of a {cs}^3 / {cs}^3 sample of the same synthetic workload ({sec:.2f} s/step); "
                          "C restatement of ParticleMesh.jl + pocketfft, 1 thread like the reference (Readme.md:53); "
